@@ -1,0 +1,114 @@
+"""ctypes binding of libgsx.so (include/gsx.h).  There is no CPU fallback: if the shared library is
+missing or fails to load, every product entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libgsx.so')
+CSRC = os.path.join(_HERE, 'csrc')
+
+# enums of gsx_internal.h / gsx.h
+CONV3, UPCONV3, DECONV4, CONV1 = 0, 1, 2, 3
+EPI_LRELU, EPI_STATS, EPI_ARGMAX = 1, 2, 4
+
+
+class SynthCfg(C.Structure):
+    _fields_ = [('max_res_log2', C.c_int), ('base_scale_y', C.c_int), ('base_scale_x', C.c_int),
+                ('fmap_base', C.c_int), ('fmap_decay', C.c_float), ('fmap_max', C.c_int),
+                ('latent_size', C.c_int), ('channels', C.c_int)]
+
+
+class DecCfg(C.Structure):
+    _fields_ = [('num_levels', C.c_int), ('in_channels', C.c_int * 16), ('features', C.c_int * 17),
+                ('use_bn', C.c_int), ('base_y', C.c_int), ('base_x', C.c_int)]
+
+
+class PlanOverride(C.Structure):
+    _fields_ = [('TH', C.c_int), ('TW', C.c_int), ('NB', C.c_int), ('CBK', C.c_int), ('N_tile', C.c_int),
+                ('stages', C.c_int), ('phase_grid', C.c_int)]
+
+
+class GsxError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile libgsx.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(['make', '-C', CSRC, '-j8'], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode:
+        raise GsxError('building libgsx.so failed')
+    return LIB_PATH
+
+
+_lib = None
+
+_vp, _fp, _i, _u64, _sz = C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_size_t
+
+_SIGS = {
+    'gsx_last_error': (C.c_char_p, []),
+    'gsx_abi_version': (_i, []),
+    'gsx_launch_count': (_u64, []),
+    'gsx_synth_create': (_i, [C.POINTER(SynthCfg), C.POINTER(_vp)]),
+    'gsx_synth_destroy': (None, [_vp]),
+    'gsx_synth_set_param': (_i, [_vp, C.c_char_p, _fp, C.POINTER(C.c_int64), _i]),
+    'gsx_synth_finalize': (_i, [_vp]),
+    'gsx_synth_workspace_bytes': (_i, [_vp, _i, C.POINTER(_sz)]),
+    'gsx_synth_num_layers': (_i, [_vp]),
+    'gsx_synth_feature_shape': (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    'gsx_synth_forward': (_i, [_vp, _i, _fp, _fp, C.POINTER(_vp), _u64, _u64, _fp, _vp, C.POINTER(_vp), _vp, _sz, _vp]),
+    'gsx_synth_export_noise': (_i, [_vp, _i, _i, _fp, _vp, _vp]),
+    'gsx_synth_export_latents': (_i, [_vp, _i, _fp, _vp, _vp]),
+    'gsx_dec_create': (_i, [C.POINTER(DecCfg), C.POINTER(_vp)]),
+    'gsx_dec_destroy': (None, [_vp]),
+    'gsx_dec_set_param': (_i, [_vp, C.c_char_p, _fp, C.POINTER(C.c_int64), _i]),
+    'gsx_dec_finalize': (_i, [_vp]),
+    'gsx_dec_workspace_bytes': (_i, [_vp, _i, C.POINTER(_sz)]),
+    'gsx_dec_forward': (_i, [_vp, _i, C.POINTER(_vp), _vp, _vp, _fp, _vp, _vp, _sz, _vp]),
+    'gsx_generate_host': (_i, [_vp, _vp, _i, _fp, _fp, _u64, _u64, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp]),
+    'gsx_op_conv': (_i, [_i] * 7 + [_fp, _fp, _fp, _fp, _fp, _fp, _i, _fp, _fp, _fp, _vp, _fp, _i,
+                         C.POINTER(PlanOverride), C.POINTER(_i), _i, C.POINTER(C.c_float), _vp]),
+    'gsx_plan_query': (_i, [_i] * 7 + [C.POINTER(PlanOverride), C.POINTER(_i)]),
+    'gsx_op_pass1': (_i, [_i, _i, _i, _i, _fp, _i, _i, _fp, _fp, _fp, _fp, _fp, _vp]),
+    'gsx_op_apply': (_i, [_i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _i, _fp, _fp, _vp, _vp]),
+    'gsx_op_fill_normal': (_i, [_fp, _sz, _i, _u64, _u64, _i, _vp]),
+}
+
+EXPORTS = tuple(_SIGS)
+
+
+def lib():
+    """Load libgsx.so (once).  Raises GsxError when it is missing -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GsxError(f'{LIB_PATH} not found: run __graft_entry__.build() (make -C {CSRC}); '
+                           'the generate path has no CPU fallback')
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what=''):
+    if rc < 0:
+        msg = lib().gsx_last_error()
+        raise GsxError(f'{what}: {msg.decode() if msg else rc}')
+    return rc
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def np_ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,748 @@
+// C ABI of libgsx (include/gsx.h): handles, parameter folding/packing, forward orchestration.
+#include "../../include/gsx.h"
+#include "gsx_internal.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+
+namespace gsx {
+const char* last_error_cstr();
+std::atomic<uint64_t> g_launches{0};
+
+struct HostTensor {
+  std::vector<float> v;
+  std::vector<int64_t> shape;
+};
+
+static int ilog2_exact(long v) {
+  int r = 0;
+  while ((1L << r) < v) ++r;
+  return ((1L << r) == v) ? r : -1;
+}
+
+// Legacy prefix names (networks_stylegan.py:16-54,125,136,244-247) -> structural names.
+static std::string canonical_name(const std::string& in) {
+  std::string name = in;
+  if (name.rfind("arg:", 0) == 0 || name.rfind("aux:", 0) == 0) name = name.substr(4);
+  if (name.find('.') != std::string::npos) return name;
+  if (name == "constant_tensor" || name == "latent_avg" || name == "truncation_psi") return name;
+  int i;
+  char rest[128];
+  if (sscanf(name.c_str(), "mp_dense_%d_%127s", &i, rest) == 2) return "mapping." + std::to_string(2 * i + 1) + "." + rest;
+  long scale;
+  if (sscanf(name.c_str(), "%ld_%127s", &scale, rest) == 2) {
+    const int r = ilog2_exact(scale);
+    if (r < 0) return name;
+    const std::string R = std::to_string(r), s = rest;
+    auto tail = [&](const char* pre) { return s.substr(strlen(pre)); };
+    if (s.rfind("conv_1_", 0) == 0) return "net" + R + ".block0." + tail("conv_1_");
+    if (s.rfind("deconv_1_", 0) == 0) return "net" + R + ".block0." + tail("deconv_1_");
+    if (s == "blur_1_w_kernel") return "net" + R + ".blur.w_kernel";
+    if (s == "noise_1_scale_factors") return "net" + R + ".block1.0.scale_factors";
+    if (s == "bias_1_bias") return "net" + R + ".block1.1.bias";
+    if (s == "noise_2_scale_factors") return "net" + R + ".block2.1.scale_factors";
+    if (s == "bias_2_bias") return "net" + R + ".block2.2.bias";
+    if (s.rfind("conv_2_", 0) == 0) return "net" + R + ".block2.0." + tail("conv_2_");
+    if (s.rfind("conv_to_rgb_", 0) == 0) return "to_rgb" + R + ".0." + tail("conv_to_rgb_");
+    for (int k = 1; k <= 2; ++k) {
+      const std::string a = "adain_" + std::to_string(k) + "_dense_affine_", b = "adain_" + std::to_string(k) + "_norm_";
+      if (s.rfind(a, 0) == 0) return "net" + R + ".adain" + std::to_string(k) + ".affine." + s.substr(a.size());
+      if (s.rfind(b, 0) == 0) return "net" + R + ".adain" + std::to_string(k) + ".instance." + s.substr(b.size());
+    }
+  }
+  return name;
+}
+
+template <class T>
+static T* dev_upload(const std::vector<T>& h) {
+  T* d = nullptr;
+  if (!cuda_ok(cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(T)), "cudaMalloc")) return nullptr;
+  if (!cuda_ok(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice), "cudaMemcpy H2D")) return nullptr;
+  return d;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Arena {              // carves a caller-owned workspace
+  uint8_t* base; size_t off = 0;
+  explicit Arena(void* b) : base(static_cast<uint8_t*>(b)) {}
+  template <class T> T* take(size_t n) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off = align_up(off + n * sizeof(T), 1024);
+    return p;
+  }
+};
+
+// Runs one planned conv layer: builds the tensor maps for this batch / these buffers and launches.
+static bool run_conv(const ConvLayer& L, int N, const bf16* x0, const bf16* x1, const ConvEpi& epi, cudaStream_t st) {
+  ConvParams p;
+  p.g = L.g;
+  finish_geom_for_batch(p.g, N);
+  p.e = epi;
+  p.wpack = L.wpack_dev;
+  set_error("");
+  make_act_tensormap(&p.tm[0], x0, L.cin0, N, L.H, L.W, p.g.BW, p.g.BH, p.g.NB, p.g.CBK);
+  if (L.cin1 > 0) make_act_tensormap(&p.tm[1], x1, L.cin1, N, L.H, L.W, p.g.BW, p.g.BH, p.g.NB, p.g.CBK);
+  else p.tm[1] = p.tm[0];
+  if (*last_error_cstr()) return false;
+  launch_shiftconv(p, st);
+  g_launches++;
+  return cuda_ok(cudaGetLastError(), "shiftconv launch");
+}
+
+static bool upload_conv(ConvLayer& L, const float* w) {
+  std::vector<bf16> packed;
+  pack_conv_weights(L, w, packed);
+  L.wpack_elems = packed.size();
+  L.wpack_dev = dev_upload(packed);
+  return L.wpack_dev != nullptr;
+}
+
+}  // namespace gsx
+
+using namespace gsx;
+
+// =============================================================================================
+// generator
+// =============================================================================================
+struct SynthBlock {
+  int r, C, Cin, H, W;
+  ConvLayer conv1, conv2;                 // conv1 unused at r == 2
+  float *ns1 = nullptr, *b1 = nullptr, *ns2 = nullptr, *b2 = nullptr;
+};
+
+struct gsx_synth {
+  gsx_synth_cfg cfg;
+  int L, nlayers, S_total;
+  std::map<std::string, HostTensor> params;
+  bool finalized = false;
+  std::vector<SynthBlock> blocks;
+  std::vector<int> style_off;             // per style layer, offset into the styles row
+  float* d_map_w[8] = {nullptr};
+  float* d_map_b[8] = {nullptr};
+  float *d_aff_w = nullptr, *d_aff_b = nullptr;
+  int* d_unit_layer = nullptr;
+  float *d_latent_avg = nullptr, *d_psi = nullptr, *d_wrgb = nullptr, *d_brgb = nullptr;
+  bf16* d_const = nullptr;
+  int last_n = 0;
+
+  int nf(int r) const {
+    const int f = (int)(cfg.fmap_base / std::pow(2.0, (r - 1) * (double)cfg.fmap_decay));
+    return std::min(f, cfg.fmap_max);
+  }
+  void hw(int r, int& h, int& w) const { h = cfg.base_scale_y << (r - 2); w = cfg.base_scale_x << (r - 2); }
+};
+
+struct SynthWs {
+  float *z, *wa, *wb, *styles, *stats, *psi;
+  std::vector<float*> noise;
+  std::vector<bf16*> feat;
+  bf16 *bufA, *bufB;
+  size_t stats_bytes, total;
+  std::vector<size_t> stats_off;          // floats, per style layer
+};
+
+static SynthWs synth_layout(const gsx_synth* h, int N, void* base) {
+  SynthWs w;
+  Arena a(base);
+  const int Z = h->cfg.latent_size;
+  w.z = a.take<float>((size_t)N * Z);
+  w.wa = a.take<float>((size_t)N * Z);
+  w.wb = a.take<float>((size_t)N * Z);
+  w.styles = a.take<float>((size_t)N * h->S_total);
+  w.psi = a.take<float>(h->nlayers);
+  size_t so = 0;
+  for (int l = 0; l < h->nlayers; ++l) {
+    w.stats_off.push_back(so);
+    so += (size_t)N * h->nf(2 + l / 2) * 2;
+  }
+  w.stats = a.take<float>(so);
+  w.stats_bytes = so * sizeof(float);
+  size_t maxact = 0;
+  for (int r = 2; r <= h->L; ++r) {
+    int hh, ww;
+    h->hw(r, hh, ww);
+    const size_t plane = (size_t)N * hh * ww;
+    w.noise.push_back(a.take<float>(plane));
+    w.noise.push_back(a.take<float>(plane));
+    w.feat.push_back(a.take<bf16>(plane * h->nf(r)));
+    maxact = std::max(maxact, plane * h->nf(r));
+  }
+  w.bufA = a.take<bf16>(maxact);
+  w.bufB = a.take<bf16>(maxact);
+  w.total = a.off;
+  return w;
+}
+
+extern "C" const char* gsx_last_error(void) { return last_error_cstr(); }
+extern "C" int gsx_abi_version(void) { return 1; }
+extern "C" uint64_t gsx_launch_count(void) { return g_launches.load(); }
+
+extern "C" int gsx_synth_create(const gsx_synth_cfg* cfg, gsx_synth** out) {
+  if (!cfg || !out) { set_error("null argument"); return -1; }
+  if (cfg->latent_size != 512 || cfg->max_res_log2 < 2 || cfg->max_res_log2 > 12 || cfg->channels > 4) {
+    set_error("unsupported generator config (latent_size must be 512, channels <= 4)");
+    return -1;
+  }
+  int dev;
+  if (!cuda_ok(cudaGetDevice(&dev), "cudaGetDevice (libgsx has no CPU fallback)")) return -2;
+  gsx_synth* h = new gsx_synth();
+  h->cfg = *cfg;
+  h->L = cfg->max_res_log2;
+  h->nlayers = 2 * (h->L - 1);
+  int off = 0;
+  for (int l = 0; l < h->nlayers; ++l) {
+    h->style_off.push_back(off);
+    off += 2 * h->nf(2 + l / 2);
+  }
+  h->S_total = off;
+  for (int r = 2; r <= h->L; ++r)
+    if (h->nf(r) % 16) { set_error("channel counts must be multiples of 16"); delete h; return -1; }
+  *out = h;
+  return 0;
+}
+
+extern "C" void gsx_synth_destroy(gsx_synth* h) {
+  if (!h) return;
+  for (int i = 0; i < 8; ++i) { cudaFree(h->d_map_w[i]); cudaFree(h->d_map_b[i]); }
+  cudaFree(h->d_aff_w); cudaFree(h->d_aff_b); cudaFree(h->d_unit_layer); cudaFree(h->d_latent_avg);
+  cudaFree(h->d_psi); cudaFree(h->d_wrgb); cudaFree(h->d_brgb); cudaFree(h->d_const);
+  for (auto& b : h->blocks) {
+    cudaFree(b.conv1.wpack_dev); cudaFree(b.conv2.wpack_dev);
+    cudaFree(b.ns1); cudaFree(b.b1); cudaFree(b.ns2); cudaFree(b.b2);
+  }
+  delete h;
+}
+
+static int store_param(std::map<std::string, HostTensor>& params, const char* name, const float* data,
+                       const int64_t* shape, int ndim) {
+  if (!name || !data || ndim < 0 || ndim > 8) { set_error("bad parameter"); return -1; }
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.v.assign(data, data + n);
+  params[canonical_name(name)] = std::move(t);
+  return 0;
+}
+
+extern "C" int gsx_synth_set_param(gsx_synth* h, const char* name, const float* data, const int64_t* shape, int ndim) {
+  if (!h) { set_error("null handle"); return -1; }
+  h->finalized = false;
+  return store_param(h->params, name, data, shape, ndim);
+}
+
+static const HostTensor* need(const std::map<std::string, HostTensor>& p, const std::string& name, size_t elems) {
+  auto it = p.find(name);
+  if (it == p.end()) { set_error("missing parameter: " + name); return nullptr; }
+  if (it->second.v.size() != elems) {
+    set_error("parameter " + name + " has " + std::to_string(it->second.v.size()) + " elements, expected " +
+              std::to_string(elems));
+    return nullptr;
+  }
+  return &it->second;
+}
+
+extern "C" int gsx_synth_finalize(gsx_synth* h) {
+  if (!h) { set_error("null handle"); return -1; }
+  const int Z = h->cfg.latent_size, L = h->L;
+  const auto& P = h->params;
+  // ---- mapping: weight * (sqrt2/sqrt(in)) * lr_mult, bias * lr_mult   (networks_stylegan.py:507-518, lr_mult .01 :135)
+  for (int i = 0; i < 8; ++i) {
+    const std::string p = "mapping." + std::to_string(2 * i + 1);
+    const HostTensor* w = need(P, p + ".weight", (size_t)Z * Z);
+    const HostTensor* b = need(P, p + ".bias", Z);
+    if (!w || !b) return -1;
+    const float sc = (float)(std::sqrt(2.0) / std::sqrt((double)Z)) * 0.01f;
+    std::vector<float> ws(w->v), bs(b->v);
+    for (auto& x : ws) x *= sc;
+    for (auto& x : bs) x *= 0.01f;
+    cudaFree(h->d_map_w[i]); cudaFree(h->d_map_b[i]);
+    h->d_map_w[i] = dev_upload(ws); h->d_map_b[i] = dev_upload(bs);
+    if (!h->d_map_w[i] || !h->d_map_b[i]) return -2;
+  }
+  // ---- affine (styles): weight / sqrt(512), gain 1 (:244)
+  {
+    std::vector<float> aw((size_t)h->S_total * Z), ab(h->S_total);
+    std::vector<int> ul(h->S_total);
+    for (int l = 0; l < h->nlayers; ++l) {
+      const int r = 2 + l / 2, C = h->nf(r);
+      const std::string p = "net" + std::to_string(r) + ".adain" + std::to_string(1 + (l & 1)) + ".affine";
+      const HostTensor* w = need(P, p + ".weight", (size_t)2 * C * Z);
+      const HostTensor* b = need(P, p + ".bias", (size_t)2 * C);
+      if (!w || !b) return -1;
+      const float sc = (float)(1.0 / std::sqrt((double)Z));
+      for (size_t i = 0; i < w->v.size(); ++i) aw[(size_t)h->style_off[l] * Z + i] = w->v[i] * sc;
+      for (int i = 0; i < 2 * C; ++i) { ab[h->style_off[l] + i] = b->v[i]; ul[h->style_off[l] + i] = l; }
+    }
+    cudaFree(h->d_aff_w); cudaFree(h->d_aff_b); cudaFree(h->d_unit_layer);
+    h->d_aff_w = dev_upload(aw); h->d_aff_b = dev_upload(ab); h->d_unit_layer = dev_upload(ul);
+    if (!h->d_aff_w || !h->d_aff_b || !h->d_unit_layer) return -2;
+  }
+  {
+    const HostTensor* avg = need(P, "latent_avg", Z);
+    const HostTensor* psi = need(P, "truncation_psi", h->nlayers);
+    if (!avg || !psi) return -1;
+    cudaFree(h->d_latent_avg); cudaFree(h->d_psi);
+    h->d_latent_avg = dev_upload(avg->v); h->d_psi = dev_upload(psi->v);
+  }
+  // ---- constant tensor -> blocked bf16 [C/8][1][by][bx][8]
+  {
+    const int C = h->nf(2), by = h->cfg.base_scale_y, bx = h->cfg.base_scale_x;
+    const HostTensor* c = need(P, "constant_tensor", (size_t)C * by * bx);
+    if (!c) return -1;
+    std::vector<bf16> cb((size_t)C * by * bx);
+    for (int ch = 0; ch < C; ++ch)
+      for (int p = 0; p < by * bx; ++p)
+        cb[((size_t)(ch / 8) * by * bx + p) * 8 + (ch & 7)] = __float2bfloat16(c->v[(size_t)ch * by * bx + p]);
+    cudaFree(h->d_const);
+    h->d_const = dev_upload(cb);
+  }
+  // ---- synthesis blocks
+  for (auto& b : h->blocks) {
+    cudaFree(b.conv1.wpack_dev); cudaFree(b.conv2.wpack_dev);
+    cudaFree(b.ns1); cudaFree(b.b1); cudaFree(b.ns2); cudaFree(b.b2);
+  }
+  h->blocks.clear();
+  for (int r = 2; r <= L; ++r) {
+    SynthBlock b;
+    b.r = r; b.C = h->nf(r); b.Cin = r > 2 ? h->nf(r - 1) : b.C;
+    h->hw(r, b.H, b.W);
+    const std::string p = "net" + std::to_string(r);
+    if (r > 2) {
+      const bool deconv = r >= 7;                                            // networks_stylegan.py:154
+      const int k = deconv ? 4 : 3;
+      const HostTensor* w = need(P, p + ".block0.weight", (size_t)b.C * b.Cin * k * k);
+      if (!w) return -1;
+      const float std_ = (float)(std::sqrt(2.0) / std::sqrt((double)k * k * b.Cin));   // :399-403
+      std::vector<float> ws(w->v);
+      for (auto& x : ws) x *= std_;
+      plan_conv(b.conv1, deconv ? DECONV4 : UPCONV3, b.H / 2, b.W / 2, b.Cin, 0, b.C, 0, nullptr);
+      if (*gsx_last_error()) return -1;
+      if (!upload_conv(b.conv1, ws.data())) return -2;
+    }
+    {
+      const HostTensor* w = need(P, p + ".block2.0.weight", (size_t)b.C * b.C * 9);
+      if (!w) return -1;
+      const float std_ = (float)(std::sqrt(2.0) / std::sqrt(9.0 * b.C));
+      std::vector<float> ws(w->v);
+      for (auto& x : ws) x *= std_;
+      set_error("");
+      plan_conv(b.conv2, CONV3, b.H, b.W, b.C, 0, b.C, 0, nullptr);
+      if (*gsx_last_error()) return -1;
+      if (!upload_conv(b.conv2, ws.data())) return -2;
+    }
+    const HostTensor* n1 = need(P, p + ".block1.0.scale_factors", b.C);
+    const HostTensor* b1 = need(P, p + ".block1.1.bias", b.C);
+    const HostTensor* n2 = need(P, p + ".block2.1.scale_factors", b.C);
+    const HostTensor* b2 = need(P, p + ".block2.2.bias", b.C);
+    if (!n1 || !b1 || !n2 || !b2) return -1;
+    b.ns1 = dev_upload(n1->v); b.b1 = dev_upload(b1->v); b.ns2 = dev_upload(n2->v); b.b2 = dev_upload(b2->v);
+    h->blocks.push_back(b);
+  }
+  // ---- ToRGB: 1x1, gain 1 -> std = 1/sqrt(C) (:118-126)
+  {
+    const int C = h->nf(L), nc = h->cfg.channels;
+    const std::string p = "to_rgb" + std::to_string(L) + ".0";
+    const HostTensor* w = need(P, p + ".weight", (size_t)nc * C);
+    const HostTensor* b = need(P, p + ".bias", nc);
+    if (!w || !b) return -1;
+    std::vector<float> ws(w->v);
+    for (auto& x : ws) x *= (float)(1.0 / std::sqrt((double)C));
+    cudaFree(h->d_wrgb); cudaFree(h->d_brgb);
+    h->d_wrgb = dev_upload(ws); h->d_brgb = dev_upload(b->v);
+  }
+  if (!cuda_ok(cudaDeviceSynchronize(), "finalize")) return -2;
+  set_error("");
+  h->finalized = true;
+  return 0;
+}
+
+extern "C" int gsx_synth_workspace_bytes(const gsx_synth* h, int n, size_t* bytes) {
+  if (!h || !bytes || n <= 0) { set_error("bad argument"); return -1; }
+  *bytes = synth_layout(h, n, nullptr).total;
+  return 0;
+}
+extern "C" int gsx_synth_num_layers(const gsx_synth* h) { return h ? h->nlayers : -1; }
+extern "C" int gsx_synth_feature_shape(const gsx_synth* h, int level, int* c, int* hgt, int* wid) {
+  if (!h || level < 0 || level > h->L - 2) { set_error("bad level"); return -1; }
+  *c = h->nf(level + 2);
+  h->hw(level + 2, *hgt, *wid);
+  return 0;
+}
+
+extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const float* psi_host,
+                                 const float* const* noise_dev, uint64_t seed, uint64_t first_sample,
+                                 float* img_f32_dev, uint8_t* img_u8_dev, float* const* feats_f32_dev, void* ws,
+                                 size_t ws_bytes, gsx_stream stream) {
+  if (!h || !h->finalized) { set_error("generator not finalized"); return -1; }
+  if (N <= 0 || !ws) { set_error("bad argument"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SynthWs w = synth_layout(h, N, ws);
+  if (w.total > ws_bytes) { set_error("workspace too small"); return -1; }
+  const int Z = h->cfg.latent_size;
+  set_error("");
+  if (!cuda_ok(cudaMemsetAsync(w.stats, 0, w.stats_bytes, st), "memset stats")) return -2;
+  if (z_dev) {
+    if (!cuda_ok(cudaMemcpyAsync(w.z, z_dev, (size_t)N * Z * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy z")) return -2;
+  } else {
+    launch_fill_latents(w.z, N, Z, seed, first_sample, st); g_launches++;
+  }
+  const float* psi = h->d_psi;
+  if (psi_host) {
+    if (!cuda_ok(cudaMemcpyAsync(w.psi, psi_host, h->nlayers * sizeof(float), cudaMemcpyHostToDevice, st), "copy psi")) return -2;
+    psi = w.psi;
+  }
+  // mapping MLP
+  const float* cur = w.z;
+  for (int i = 0; i < 8; ++i) {
+    DenseArgs d{};
+    d.x = cur; d.W = h->d_map_w[i]; d.b = h->d_map_b[i]; d.y = (i & 1) ? w.wb : w.wa;
+    d.N = N; d.K = Z; d.U = Z; d.lrelu = 1; d.pixelnorm = (i == 0);
+    launch_dense(d, st); g_launches++;
+    cur = d.y;
+  }
+  {   // all style layers at once; truncation folded into the operand load
+    DenseArgs d{};
+    d.x = cur; d.W = h->d_aff_w; d.b = h->d_aff_b; d.y = w.styles;
+    d.N = N; d.K = Z; d.U = h->S_total; d.lrelu = 0; d.pixelnorm = 0;
+    d.latent_avg = h->d_latent_avg; d.psi = psi; d.unit_layer = h->d_unit_layer;
+    launch_dense(d, st); g_launches++;
+  }
+  // noise planes
+  std::vector<const float*> noise(h->nlayers);
+  for (int l = 0; l < h->nlayers; ++l) {
+    if (noise_dev && noise_dev[l]) noise[l] = noise_dev[l];
+    else {
+      int hh, ww;
+      h->hw(2 + l / 2, hh, ww);
+      launch_fill_noise(w.noise[l], (size_t)hh * ww, N, seed, first_sample, l, st); g_launches++;
+      noise[l] = w.noise[l];
+    }
+  }
+  h->last_n = N;
+
+  for (size_t bi = 0; bi < h->blocks.size(); ++bi) {
+    const SynthBlock& b = h->blocks[bi];
+    const int l1 = 2 * (int)bi, l2 = l1 + 1;
+    float* st1 = w.stats + w.stats_off[l1];
+    float* st2 = w.stats + w.stats_off[l2];
+    Pass1Args p1{};
+    p1.out = w.bufB; p1.C = b.C; p1.N = N; p1.H = b.H; p1.W = b.W;
+    p1.nscale = b.ns1; p1.bias = b.b1; p1.noise = noise[l1]; p1.stats = st1;
+    if (b.r == 2) {
+      p1.in = h->d_const; p1.in_broadcast = 1; p1.blur = 0;
+    } else {
+      ConvEpi e{};
+      e.out = w.bufA; e.Ho = b.H; e.Wo = b.W; e.up = 1; e.flags = 0; e.Cout = b.C;
+      if (!run_conv(b.conv1, N, w.feat[bi - 1], nullptr, e, st)) return -2;
+      p1.in = w.bufA; p1.in_broadcast = 0; p1.blur = 1;
+    }
+    launch_pass1(p1, st); g_launches++;
+    ApplyArgs a1{};
+    a1.in = w.bufB; a1.out = w.bufB; a1.C = b.C; a1.N = N; a1.H = b.H; a1.W = b.W;
+    a1.stats = st1; a1.styles = w.styles; a1.style_stride = h->S_total; a1.style_off = h->style_off[l1];
+    launch_apply(a1, st); g_launches++;
+
+    ConvEpi e2{};
+    e2.out = w.bufA; e2.Ho = b.H; e2.Wo = b.W; e2.up = 0; e2.Cout = b.C;
+    e2.bias = b.b2; e2.nscale = b.ns2; e2.noise = noise[l2];
+    const bool fused_stats = b.conv2.g.NB == 1;
+    e2.flags = EPI_LRELU | (fused_stats ? EPI_STATS : 0);
+    e2.stats = fused_stats ? st2 : nullptr;
+    if (!run_conv(b.conv2, N, w.bufB, nullptr, e2, st)) return -2;
+    if (!fused_stats) { launch_stats(w.bufA, st2, b.C, N, b.H * b.W, st); g_launches++; }
+
+    ApplyArgs a2{};
+    a2.in = w.bufA; a2.out = w.feat[bi]; a2.C = b.C; a2.N = N; a2.H = b.H; a2.W = b.W;
+    a2.stats = st2; a2.styles = w.styles; a2.style_stride = h->S_total; a2.style_off = h->style_off[l2];
+    a2.out_nchw_f32 = feats_f32_dev ? feats_f32_dev[bi] : nullptr;
+    if (b.r == h->L) {
+      a2.wrgb = h->d_wrgb; a2.brgb = h->d_brgb; a2.img_f32 = img_f32_dev; a2.img_u8 = img_u8_dev; a2.nc = h->cfg.channels;
+    }
+    launch_apply(a2, st); g_launches++;
+  }
+  if (!cuda_ok(cudaGetLastError(), "synth forward")) return -2;
+  return 0;
+}
+
+extern "C" int gsx_synth_export_noise(gsx_synth* h, int n, int layer, float* out_dev, const void* ws, gsx_stream stream) {
+  if (!h || layer < 0 || layer >= h->nlayers) { set_error("bad layer"); return -1; }
+  SynthWs w = synth_layout(h, n, const_cast<void*>(ws));
+  int hh, ww;
+  h->hw(2 + layer / 2, hh, ww);
+  return cuda_ok(cudaMemcpyAsync(out_dev, w.noise[layer], (size_t)n * hh * ww * sizeof(float), cudaMemcpyDeviceToDevice,
+                                 static_cast<cudaStream_t>(stream)), "export noise") ? 0 : -2;
+}
+extern "C" int gsx_synth_export_latents(gsx_synth* h, int n, float* out_dev, const void* ws, gsx_stream stream) {
+  if (!h) { set_error("null handle"); return -1; }
+  SynthWs w = synth_layout(h, n, const_cast<void*>(ws));
+  return cuda_ok(cudaMemcpyAsync(out_dev, w.z, (size_t)n * h->cfg.latent_size * sizeof(float), cudaMemcpyDeviceToDevice,
+                                 static_cast<cudaStream_t>(stream)), "export z") ? 0 : -2;
+}
+
+// =============================================================================================
+// decoder
+// =============================================================================================
+struct DecLevel {
+  int H, W, cin, f, fnext;
+  ConvLayer cvt, conv_a, conv_b, shortcut, final_;
+  bool has_shortcut = false;
+  float *b_cvt = nullptr, *b_a = nullptr, *b_b = nullptr, *b_sc = nullptr, *b_final = nullptr;
+};
+
+struct gsx_dec {
+  gsx_dec_cfg cfg;
+  int nf, num_classes;
+  std::map<std::string, HostTensor> params;
+  bool finalized = false;
+  std::vector<DecLevel> levels;
+};
+
+struct DecWs {
+  std::vector<bf16*> feat, c, a, sc, prev;     // prev[i] = input "prev" of level i (null at 0)
+  size_t total;
+};
+
+static DecWs dec_layout(const gsx_dec* d, int N, void* base, bool own_feats) {
+  DecWs w;
+  Arena ar(base);
+  const int nf = d->nf;
+  w.feat.assign(nf, nullptr); w.c.assign(nf, nullptr); w.a.assign(nf, nullptr); w.sc.assign(nf, nullptr);
+  w.prev.assign(nf + 1, nullptr);
+  for (int i = 0; i < nf; ++i) {
+    const int H = d->cfg.base_y << i, W = d->cfg.base_x << i;
+    const size_t plane = (size_t)N * H * W;
+    if (own_feats) w.feat[i] = ar.take<bf16>(plane * d->cfg.in_channels[i]);
+    w.c[i] = ar.take<bf16>(plane * d->cfg.features[i]);
+    if (i < nf - 1) {
+      w.a[i] = ar.take<bf16>(plane * 4 * d->cfg.features[i + 1]);
+      w.sc[i] = ar.take<bf16>(plane * d->cfg.features[i + 1]);
+      w.prev[i + 1] = ar.take<bf16>(plane * 4 * d->cfg.features[i + 1]);
+    }
+  }
+  w.total = ar.off;
+  return w;
+}
+
+extern "C" int gsx_dec_create(const gsx_dec_cfg* cfg, gsx_dec** out) {
+  if (!cfg || !out || cfg->num_levels < 1 || cfg->num_levels > 16) { set_error("bad decoder config"); return -1; }
+  int dev;
+  if (!cuda_ok(cudaGetDevice(&dev), "cudaGetDevice (libgsx has no CPU fallback)")) return -2;
+  for (int i = 0; i < cfg->num_levels; ++i)
+    if (cfg->in_channels[i] % 16 || cfg->features[i] % 16) { set_error("decoder channels must be multiples of 16"); return -1; }
+  if (cfg->features[cfg->num_levels] > 16) { set_error("at most 16 classes"); return -1; }
+  gsx_dec* d = new gsx_dec();
+  d->cfg = *cfg;
+  d->nf = cfg->num_levels;
+  d->num_classes = cfg->features[cfg->num_levels];
+  *out = d;
+  return 0;
+}
+
+static void free_level(DecLevel& l) {
+  cudaFree(l.cvt.wpack_dev); cudaFree(l.conv_a.wpack_dev); cudaFree(l.conv_b.wpack_dev);
+  cudaFree(l.shortcut.wpack_dev); cudaFree(l.final_.wpack_dev);
+  cudaFree(l.b_cvt); cudaFree(l.b_a); cudaFree(l.b_b); cudaFree(l.b_sc); cudaFree(l.b_final);
+}
+
+extern "C" void gsx_dec_destroy(gsx_dec* d) {
+  if (!d) return;
+  for (auto& l : d->levels) free_level(l);
+  delete d;
+}
+
+extern "C" int gsx_dec_set_param(gsx_dec* d, const char* name, const float* data, const int64_t* shape, int ndim) {
+  if (!d) { set_error("null handle"); return -1; }
+  d->finalized = false;
+  return store_param(d->params, name, data, shape, ndim);
+}
+
+// conv (+ optional inference BatchNorm fold): w' = w*g, b' = (b - mean)*g + beta, g = gamma/sqrt(var+1e-5)
+static bool fold_conv_bn(const std::map<std::string, HostTensor>& P, const std::string& conv, const std::string& bn,
+                         int cout, size_t per_out, std::vector<float>& w, std::vector<float>& b) {
+  const HostTensor* cw = need(P, conv + ".weight", (size_t)cout * per_out);
+  const HostTensor* cb = need(P, conv + ".bias", cout);
+  if (!cw || !cb) return false;
+  w = cw->v; b = cb->v;
+  if (!bn.empty()) {
+    const HostTensor* ga = need(P, bn + ".gamma", cout);
+    const HostTensor* be = need(P, bn + ".beta", cout);
+    const HostTensor* rm = need(P, bn + ".running_mean", cout);
+    const HostTensor* rv = need(P, bn + ".running_var", cout);
+    if (!ga || !be || !rm || !rv) return false;
+    for (int co = 0; co < cout; ++co) {
+      const float g = ga->v[co] / std::sqrt(rv->v[co] + 1e-5f);
+      for (size_t i = 0; i < per_out; ++i) w[(size_t)co * per_out + i] *= g;
+      b[co] = (b[co] - rm->v[co]) * g + be->v[co];
+    }
+  }
+  return true;
+}
+
+extern "C" int gsx_dec_finalize(gsx_dec* d) {
+  if (!d) { set_error("null handle"); return -1; }
+  for (auto& l : d->levels) free_level(l);
+  d->levels.clear();
+  const auto& P = d->params;
+  const int nf = d->nf;
+  const bool bn = d->cfg.use_bn != 0;
+  for (int i = 0; i < nf; ++i) {
+    DecLevel l;
+    l.H = d->cfg.base_y << i; l.W = d->cfg.base_x << i;
+    l.cin = d->cfg.in_channels[i]; l.f = d->cfg.features[i]; l.fnext = d->cfg.features[i + 1];
+    std::vector<float> w, b;
+    const std::string cv = "cvt_block_" + std::to_string(i);
+    if (!fold_conv_bn(P, cv + ".0", bn ? cv + ".1" : "", l.f, (size_t)l.cin * 9, w, b)) return -1;
+    set_error("");
+    plan_conv(l.cvt, CONV3, l.H, l.W, l.cin, 0, l.f, 0, nullptr);
+    if (*gsx_last_error()) return -1;
+    if (!upload_conv(l.cvt, w.data())) return -2;
+    l.b_cvt = dev_upload(b);
+    const int c0 = i > 0 ? l.f : l.f, c1 = i > 0 ? l.f : 0;          // concat(prev, cvt) (networks_seg.py:108-109)
+    const int cin_main = c0 + c1;
+    if (i < nf - 1) {
+      const std::string mb = "main_block_" + std::to_string(i) + ".1";
+      const int j_b = bn ? 3 : 2;
+      if (!fold_conv_bn(P, mb + ".base_layers.0", bn ? mb + ".base_layers.1" : "", l.fnext, (size_t)cin_main * 9, w, b)) return -1;
+      plan_conv(l.conv_a, UPCONV3, l.H, l.W, c0, c1, l.fnext, 0, nullptr);
+      if (*gsx_last_error()) return -1;
+      if (!upload_conv(l.conv_a, w.data())) return -2;
+      l.b_a = dev_upload(b);
+      if (!fold_conv_bn(P, mb + ".base_layers." + std::to_string(j_b), bn ? mb + ".base_layers." + std::to_string(j_b + 1) : "",
+                        l.fnext, (size_t)l.fnext * 9, w, b)) return -1;
+      plan_conv(l.conv_b, CONV3, l.H * 2, l.W * 2, l.fnext, 0, l.fnext, 0, nullptr);
+      if (*gsx_last_error()) return -1;
+      if (!upload_conv(l.conv_b, w.data())) return -2;
+      l.b_b = dev_upload(b);
+      l.has_shortcut = (l.fnext != cin_main);                        // networks_seg.py:35-41
+      if (l.has_shortcut) {
+        if (!fold_conv_bn(P, mb + ".shortcut.0", "", l.fnext, (size_t)cin_main, w, b)) return -1;
+        plan_conv(l.shortcut, CONV1, l.H, l.W, c0, c1, l.fnext, 0, nullptr);
+        if (*gsx_last_error()) return -1;
+        if (!upload_conv(l.shortcut, w.data())) return -2;
+        l.b_sc = dev_upload(b);
+      } else if (c1 > 0) {
+        set_error("identity shortcut over a concatenated input is not supported");
+        return -1;
+      }
+    } else {
+      const std::string mb = "main_block_" + std::to_string(i) + ".0";
+      if (!fold_conv_bn(P, mb, "", l.fnext, (size_t)cin_main * 9, w, b)) return -1;
+      plan_conv(l.final_, CONV3, l.H, l.W, c0, c1, l.fnext, l.fnext, nullptr);
+      if (*gsx_last_error()) return -1;
+      if (!upload_conv(l.final_, w.data())) return -2;
+      b.resize(16, 0.f);
+      l.b_final = dev_upload(b);
+    }
+    d->levels.push_back(l);
+  }
+  if (!cuda_ok(cudaDeviceSynchronize(), "dec finalize")) return -2;
+  set_error("");
+  d->finalized = true;
+  return 0;
+}
+
+extern "C" int gsx_dec_workspace_bytes(const gsx_dec* d, int n, size_t* bytes) {
+  if (!d || !bytes || n <= 0) { set_error("bad argument"); return -1; }
+  *bytes = dec_layout(d, n, nullptr, true).total;
+  return 0;
+}
+
+extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_dev, const gsx_synth* synth,
+                               const void* synth_ws, float* logits_dev, uint8_t* mask_dev, void* ws, size_t ws_bytes,
+                               gsx_stream stream) {
+  if (!d || !d->finalized) { set_error("decoder not finalized"); return -1; }
+  if (N <= 0 || !ws || !mask_dev) { set_error("bad argument"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nf = d->nf;
+  const bool own = feats_f32_dev != nullptr;
+  DecWs w = dec_layout(d, N, ws, true);
+  if (w.total > ws_bytes) { set_error("decoder workspace too small"); return -1; }
+  std::vector<const bf16*> feat(nf);
+  if (own) {
+    for (int i = 0; i < nf; ++i) {
+      const DecLevel& l = d->levels[i];
+      launch_nchw_to_blocked(feats_f32_dev[i], w.feat[i], l.cin, N, l.H * l.W, st); g_launches++;
+      feat[i] = w.feat[i];
+    }
+  } else {
+    if (!synth || !synth_ws) { set_error("no features given"); return -1; }
+    if ((int)synth->blocks.size() != nf) { set_error("generator/decoder level mismatch"); return -1; }
+    SynthWs sw = synth_layout(synth, N, const_cast<void*>(synth_ws));
+    for (int i = 0; i < nf; ++i) {
+      const DecLevel& l = d->levels[i];
+      const SynthBlock& b = synth->blocks[i];
+      if (b.C != l.cin || b.H != l.H || b.W != l.W) { set_error("generator/decoder feature shape mismatch"); return -1; }
+      feat[i] = sw.feat[i];
+    }
+  }
+  for (int i = 0; i < nf; ++i) {
+    const DecLevel& l = d->levels[i];
+    {
+      ConvEpi e{};
+      e.out = w.c[i]; e.Ho = l.H; e.Wo = l.W; e.flags = EPI_LRELU; e.Cout = l.f; e.bias = l.b_cvt;
+      if (!run_conv(l.cvt, N, feat[i], nullptr, e, st)) return -2;
+    }
+    const bf16* x0 = i > 0 ? w.prev[i] : w.c[i];
+    const bf16* x1 = i > 0 ? w.c[i] : nullptr;
+    if (i < nf - 1) {
+      {
+        ConvEpi e{};
+        e.out = w.a[i]; e.Ho = 2 * l.H; e.Wo = 2 * l.W; e.up = 1; e.flags = EPI_LRELU; e.Cout = l.fnext; e.bias = l.b_a;
+        if (!run_conv(l.conv_a, N, x0, x1, e, st)) return -2;
+      }
+      const bf16* sc = x0;
+      if (l.has_shortcut) {
+        ConvEpi e{};
+        e.out = w.sc[i]; e.Ho = l.H; e.Wo = l.W; e.flags = 0; e.Cout = l.fnext; e.bias = l.b_sc;
+        if (!run_conv(l.shortcut, N, x0, x1, e, st)) return -2;
+        sc = w.sc[i];
+      }
+      {
+        ConvEpi e{};
+        e.out = w.prev[i + 1]; e.Ho = 2 * l.H; e.Wo = 2 * l.W; e.flags = EPI_LRELU; e.Cout = l.fnext; e.bias = l.b_b;
+        e.addsrc = sc;
+        if (!run_conv(l.conv_b, N, w.a[i], nullptr, e, st)) return -2;
+      }
+    } else {
+      ConvEpi e{};
+      e.Ho = l.H; e.Wo = l.W; e.flags = EPI_ARGMAX; e.Cout = l.fnext; e.bias = l.b_final;
+      e.mask = mask_dev; e.logits = logits_dev; e.num_classes = d->num_classes;
+      if (!run_conv(l.final_, N, x0, x1, e, st)) return -2;
+    }
+  }
+  return cuda_ok(cudaGetLastError(), "dec forward") ? 0 : -2;
+}
+
+extern "C" int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z_host, const float* psi_host,
+                                 uint64_t seed, uint64_t first_sample, uint8_t* img_u8_host, uint8_t* mask_host,
+                                 void* synth_ws, size_t synth_ws_bytes, void* dec_ws, size_t dec_ws_bytes,
+                                 void* stage_dev, size_t stage_bytes, gsx_stream stream) {
+  if (!s || !d || !stage_dev) { set_error("bad argument"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int H, W;
+  s->hw(s->L, H, W);
+  const int Z = s->cfg.latent_size, nc = s->cfg.channels;
+  const size_t zb = align_up((size_t)n * Z * sizeof(float), 1024), ib = align_up((size_t)n * H * W * nc, 1024),
+               mb = (size_t)n * H * W;
+  if (stage_bytes < zb + ib + mb) { set_error("staging buffer too small"); return -1; }
+  uint8_t* base = static_cast<uint8_t*>(stage_dev);
+  float* z_dev = reinterpret_cast<float*>(base);
+  uint8_t* img_dev = base + zb;
+  uint8_t* mask_dev = base + zb + ib;
+  if (z_host && !cuda_ok(cudaMemcpyAsync(z_dev, z_host, (size_t)n * Z * sizeof(float), cudaMemcpyHostToDevice, st), "H2D z"))
+    return -2;
+  int rc = gsx_synth_forward(s, n, z_host ? z_dev : nullptr, psi_host, nullptr, seed, first_sample, nullptr, img_dev,
+                             nullptr, synth_ws, synth_ws_bytes, stream);
+  if (rc) return rc;
+  rc = gsx_dec_forward(d, n, nullptr, s, synth_ws, nullptr, mask_dev, dec_ws, dec_ws_bytes, stream);
+  if (rc) return rc;
+  if (img_u8_host && !cuda_ok(cudaMemcpyAsync(img_u8_host, img_dev, (size_t)n * H * W * nc, cudaMemcpyDeviceToHost, st), "D2H img"))
+    return -2;
+  if (mask_host && !cuda_ok(cudaMemcpyAsync(mask_host, mask_dev, mb, cudaMemcpyDeviceToHost, st), "D2H mask")) return -2;
+  return 0;
+}

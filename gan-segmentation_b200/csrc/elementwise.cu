@@ -1,0 +1,343 @@
+// HBM-bound passes of the generate path on the blocked activation layout [C/8][N][H][W][8] bf16.
+// All global accesses are 128-bit, consecutive lanes on consecutive pixels.
+//   pass1 : Blur (networks_stylegan.py:200-236) + AddNoise (:302-304) + Bias (:544) + LeakyReLU(0.2)
+//           (:38-40) + InstanceNorm sum/sumsq (warp-shuffle reduction) in one read + one write.
+//   apply : InstanceNorm finalize + AdaIN modulation (:254-262) [+ ToRGB (:118-126) + the uint8
+//           image transform (image_generator.py:76-84) on the last layer].
+//   layout converters, Philox noise / latent generators, instance-norm statistics.
+#include "gsx_internal.h"
+#include "ptx.cuh"
+
+namespace gsx {
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+    f[2 * k] = __bfloat162float(b2.x);
+    f[2 * k + 1] = __bfloat162float(b2.y);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  __nv_bfloat162 h;
+  h = __floats2bfloat162_rn(f[0], f[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(f[2], f[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(f[4], f[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(f[6], f[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+  return o;
+}
+
+// Block-wide reduction of 16 per-thread values, then one atomicAdd per value per block.
+// dst[i*stride] += sum over the block of v[i].
+template <int NV>
+__device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], float* dst0, float* dst1, int nthreads) {
+  __shared__ float red[32][NV + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[warp][i] = v[i];
+  }
+  __syncthreads();
+  const int nw = nthreads >> 5;
+  if (threadIdx.x < NV) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += red[w][threadIdx.x];
+    // values 0..7 = channel sums, 8..15 = channel sums of squares
+    const int ch = threadIdx.x & 7;
+    atomicAdd((threadIdx.x < 8 ? dst0 : dst1) + ch * 2, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ pass1
+static constexpr int kP1Threads = 256;
+static constexpr int kP1PixPerThread = 4;
+
+__global__ void __launch_bounds__(kP1Threads) pass1_kernel(const Pass1Args a) {
+  const int plane = blockIdx.y;                 // cb * N + n
+  const int cb = plane / a.N, n = plane - cb * a.N;
+  const int HW = a.H * a.W;
+  const bf16* in = a.in + ((size_t)(a.in_broadcast ? cb : plane) * HW) * 8;
+  bf16* out = a.out + ((size_t)plane * HW) * 8;
+  const float* noise = a.noise ? a.noise + (size_t)n * HW : nullptr;
+
+  float ns[8], bs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    ns[i] = a.nscale ? a.nscale[cb * 8 + i] : 0.f;
+    bs[i] = a.bias ? a.bias[cb * 8 + i] : 0.f;
+  }
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+
+  const int base = blockIdx.x * (kP1Threads * kP1PixPerThread);
+#pragma unroll
+  for (int it = 0; it < kP1PixPerThread; ++it) {
+    const int pix = base + it * kP1Threads + threadIdx.x;
+    if (pix < HW) {
+      float v[8];
+      if (a.blur) {
+        const int y = pix / a.W, x = pix - y * a.W;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int yy = y + dy;
+          if (yy < 0 || yy >= a.H) continue;
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= a.W) continue;
+            const float wgt = (dy == 0 ? 2.f : 1.f) * (dx == 0 ? 2.f : 1.f) * (1.f / 16.f);
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(in + ((size_t)yy * a.W + xx) * 8)), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += wgt * f[i];
+          }
+        }
+      } else {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(in + (size_t)pix * 8)), v);
+      }
+      const float nz = noise ? __ldg(noise + pix) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float t = v[i] + ns[i] * nz + bs[i];
+        t = t > 0.f ? t : 0.2f * t;
+        v[i] = t;
+        acc[i] += t;
+        acc[8 + i] += t * t;
+      }
+      *reinterpret_cast<uint4*>(out + (size_t)pix * 8) = pack8(v);
+    }
+  }
+  if (a.stats) {
+    float* st = a.stats + ((size_t)n * a.C + cb * 8) * 2;
+    block_reduce_atomic<16>(acc, st, st + 1, kP1Threads);
+  }
+}
+
+void launch_pass1(const Pass1Args& a, cudaStream_t st) {
+  const int HW = a.H * a.W;
+  dim3 grid((HW + kP1Threads * kP1PixPerThread - 1) / (kP1Threads * kP1PixPerThread), (a.C / 8) * a.N);
+  pass1_kernel<<<grid, kP1Threads, 0, st>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------ stats
+__global__ void __launch_bounds__(256) stats_kernel(const bf16* in, float* stats, int C, int N, int HW) {
+  const int plane = blockIdx.y;
+  const int cb = plane / N, n = plane - cb * N;
+  const bf16* src = in + (size_t)plane * HW * 8;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int pix = blockIdx.x * 256 + threadIdx.x; pix < HW; pix += gridDim.x * 256) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(src + (size_t)pix * 8)), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i] += f[i]; acc[8 + i] += f[i] * f[i]; }
+  }
+  float* st = stats + ((size_t)n * C + cb * 8) * 2;
+  block_reduce_atomic<16>(acc, st, st + 1, 256);
+}
+
+void launch_stats(const bf16* in, float* stats, int C, int N, int HW, cudaStream_t st) {
+  dim3 grid(min(16, (HW + 255) / 256), (C / 8) * N);
+  stats_kernel<<<grid, 256, 0, st>>>(in, stats, C, N, HW);
+}
+
+// ------------------------------------------------------------------------------------------ apply
+__device__ __forceinline__ void adain_coeffs(const ApplyArgs& a, int n, int c, float inv_hw, float& ca, float& cb_) {
+  const float s1 = a.stats[((size_t)n * a.C + c) * 2], s2 = a.stats[((size_t)n * a.C + c) * 2 + 1];
+  const float mean = s1 * inv_hw;
+  const float var = fmaxf(s2 * inv_hw - mean * mean, 0.f);          // biased variance (InstanceNorm)
+  const float rstd = rsqrtf(var + 1e-5f);                           // gluon InstanceNorm eps
+  const float* sty = a.styles + (size_t)n * a.style_stride + a.style_off;
+  ca = rstd * (sty[c] + 1.f);                                       // ys + 1   (networks_stylegan.py:262)
+  cb_ = sty[a.C + c] - mean * ca;                                   // yb
+}
+
+static constexpr int kApThreads = 256;
+static constexpr int kApPixPerThread = 8;
+
+__global__ void __launch_bounds__(kApThreads) apply_kernel(const ApplyArgs a) {
+  const int plane = blockIdx.y;
+  const int cb = plane / a.N, n = plane - cb * a.N;
+  const int HW = a.H * a.W;
+  const float inv_hw = 1.f / (float)HW;
+  float ca[8], cc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) adain_coeffs(a, n, cb * 8 + i, inv_hw, ca[i], cc[i]);
+  const bf16* in = a.in + (size_t)plane * HW * 8;
+  bf16* out = a.out + (size_t)plane * HW * 8;
+  const int base = blockIdx.x * (kApThreads * kApPixPerThread);
+  uint4 r[kApPixPerThread];
+#pragma unroll
+  for (int it = 0; it < kApPixPerThread; ++it) {
+    const int pix = base + it * kApThreads + threadIdx.x;
+    if (pix < HW) r[it] = ldg_nc_u4(in + (size_t)pix * 8);
+  }
+#pragma unroll
+  for (int it = 0; it < kApPixPerThread; ++it) {
+    const int pix = base + it * kApThreads + threadIdx.x;
+    if (pix < HW) {
+      float f[8];
+      unpack8(r[it], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], ca[i], cc[i]);
+      *reinterpret_cast<uint4*>(out + (size_t)pix * 8) = pack8(f);
+      if (a.out_nchw_f32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a.out_nchw_f32[((size_t)n * a.C + cb * 8 + i) * HW + pix] = f[i];
+      }
+    }
+  }
+}
+
+// Last layer: all channels of a pixel are needed for ToRGB, so one thread owns a pixel and walks the channel blocks.
+__global__ void __launch_bounds__(256) apply_rgb_kernel(const ApplyArgs a) {
+  extern __shared__ float sm[];                 // ca[C], cc[C], wrgb[nc*C]
+  float* s_ca = sm;
+  float* s_cc = sm + a.C;
+  float* s_w = sm + 2 * a.C;
+  const int n = blockIdx.y;
+  const int HW = a.H * a.W;
+  const float inv_hw = 1.f / (float)HW;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) adain_coeffs(a, n, c, inv_hw, s_ca[c], s_cc[c]);
+  for (int i = threadIdx.x; i < a.nc * a.C; i += blockDim.x) s_w[i] = a.wrgb[i];
+  __syncthreads();
+  const int CB = a.C / 8;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+    float rgb[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int cb = 0; cb < CB; ++cb) {
+      const size_t off = (((size_t)cb * a.N + n) * HW + pix) * 8;
+      float f[8];
+      unpack8(ldg_nc_u4(a.in + off), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        f[i] = fmaf(f[i], s_ca[cb * 8 + i], s_cc[cb * 8 + i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < a.nc) rgb[k] = fmaf(s_w[k * a.C + cb * 8 + i], f[i], rgb[k]);
+      }
+      *reinterpret_cast<uint4*>(a.out + off) = pack8(f);
+      if (a.out_nchw_f32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a.out_nchw_f32[((size_t)n * a.C + cb * 8 + i) * HW + pix] = f[i];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < a.nc) {
+        const float v = rgb[k] + a.brgb[k];
+        if (a.img_f32) a.img_f32[((size_t)n * a.nc + k) * HW + pix] = v;
+        if (a.img_u8) {
+          // image_generator.py:76-84: (x - (-1)) / 2 -> clip [0,1] -> *255 -> truncate to uint8
+          float u = (v + 1.f) / 2.f;
+          u = fminf(fmaxf(u, 0.f), 1.f);
+          a.img_u8[((size_t)n * HW + pix) * a.nc + k] = (unsigned char)(255.f * u);
+        }
+      }
+    }
+  }
+}
+
+void launch_apply(const ApplyArgs& a, cudaStream_t st) {
+  const int HW = a.H * a.W;
+  if (a.wrgb) {
+    dim3 grid(min((HW + 255) / 256, 4096), a.N);
+    const size_t smem = (size_t)(2 * a.C + a.nc * a.C) * sizeof(float);
+    apply_rgb_kernel<<<grid, 256, smem, st>>>(a);
+  } else {
+    dim3 grid((HW + kApThreads * kApPixPerThread - 1) / (kApThreads * kApPixPerThread), (a.C / 8) * a.N);
+    apply_kernel<<<grid, kApThreads, 0, st>>>(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ layout
+__global__ void blocked_to_nchw_kernel(const bf16* in, float* out, int C, int N, int HW) {
+  const int plane = blockIdx.y;
+  const int cb = plane / N, n = plane - cb * N;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(in + ((size_t)plane * HW + pix) * 8)), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[((size_t)n * C + cb * 8 + i) * HW + pix] = f[i];
+  }
+}
+__global__ void nchw_to_blocked_kernel(const float* in, bf16* out, int C, int N, int HW) {
+  const int plane = blockIdx.y;
+  const int cb = plane / N, n = plane - cb * N;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = __ldg(in + ((size_t)n * C + cb * 8 + i) * HW + pix);
+    *reinterpret_cast<uint4*>(out + ((size_t)plane * HW + pix) * 8) = pack8(f);
+  }
+}
+void launch_blocked_to_nchw(const bf16* in, float* out, int C, int N, int HW, cudaStream_t st) {
+  dim3 grid(min((HW + 255) / 256, 1024), (C / 8) * N);
+  blocked_to_nchw_kernel<<<grid, 256, 0, st>>>(in, out, C, N, HW);
+}
+void launch_nchw_to_blocked(const float* in, bf16* out, int C, int N, int HW, cudaStream_t st) {
+  dim3 grid(min((HW + 255) / 256, 1024), (C / 8) * N);
+  nchw_to_blocked_kernel<<<grid, 256, 0, st>>>(in, out, C, N, HW);
+}
+
+// ------------------------------------------------------------------------------------------ RNG
+// Philox4x32-10 keyed by the seed; counter = (element/4, stream id, global sample index lo, hi).
+// The result depends only on (seed, global sample index, stream, element), never on the batch
+// split or the GPU count.
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;      // (0,1]
+  const float u2 = (float)b * 2.3283064365386963e-10f;               // [0,1)
+  const float r = sqrtf(-2.f * logf(u1));
+  float s, c;
+  sincospif(2.f * u2, &s, &c);
+  z0 = r * c; z1 = r * s;
+}
+__global__ void fill_normal_kernel(float* out, size_t per_sample, int N, uint64_t seed, uint64_t first_sample,
+                                   uint32_t stream_id) {
+  const size_t quads = (per_sample + 3) / 4;
+  const int n = blockIdx.y;
+  const uint64_t gs = first_sample + (uint64_t)n;
+  for (size_t qd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quads; qd += (size_t)gridDim.x * blockDim.x) {
+    uint32_t c[4] = {(uint32_t)qd, stream_id, (uint32_t)gs, (uint32_t)(gs >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float z[4];
+    box_muller(c[0], c[1], z[0], z[1]);
+    box_muller(c[2], c[3], z[2], z[3]);
+    float* dst = out + (size_t)n * per_sample + qd * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (qd * 4 + i < per_sample) dst[i] = z[i];
+  }
+}
+void launch_fill_noise(float* out, size_t plane_elems, int N, uint64_t seed, uint64_t first_sample, int layer,
+                       cudaStream_t st) {
+  const size_t quads = (plane_elems + 3) / 4;
+  dim3 grid((unsigned)min((size_t)1024, (quads + 255) / 256), N);
+  fill_normal_kernel<<<grid, 256, 0, st>>>(out, plane_elems, N, seed, first_sample, (uint32_t)layer);
+}
+void launch_fill_latents(float* z, int N, int Z, uint64_t seed, uint64_t first_sample, cudaStream_t st) {
+  dim3 grid(1, N);
+  fill_normal_kernel<<<grid, 128, 0, st>>>(z, (size_t)Z, N, seed, first_sample, 0xFFFFu);
+}
+
+}  // namespace gsx

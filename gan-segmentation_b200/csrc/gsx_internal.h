@@ -1,0 +1,155 @@
+// Internal declarations shared by the translation units of libgsx (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace gsx {
+
+typedef __nv_bfloat16 bf16;
+
+// ----------------------------------------------------------------------------------------------
+// Activation layout in HBM ("blocked"): [C/8][N][H][W][8] bf16 -- 8 channels of one pixel form one
+// 16-byte vector, pixels of a (channel-block, sample) plane are contiguous.  One TMA box
+// {x, y, n, cb} of this layout lands in shared memory exactly as the K-major, no-swizzle UMMA
+// operand layout (row = pixel, 16 B = 8 channels), and epilogue stores are 16 B per thread with
+// consecutive lanes on consecutive pixels.
+// ----------------------------------------------------------------------------------------------
+
+enum ConvMode {
+  CONV3 = 0,        // 3x3, stride 1, pad 1                      (reference Conv2DW / nn.Conv2D)
+  UPCONV3 = 1,      // nearest x2 then 3x3 pad 1, as 4 phases of 2x2 taps on the low-res input
+  DECONV4 = 2,      // 4x4 stride-2 pad-1 transposed conv, as 4 phases of 2x2 taps
+  CONV1 = 3,        // 1x1
+  UPCONV1 = 4       // nearest x2 then 1x1 == 1x1 at low res (output stays low-res; consumer upsamples)
+};
+
+enum EpiFlags {
+  EPI_LRELU = 1,     // leaky ReLU 0.2
+  EPI_STATS = 2,     // accumulate per-(n,c) sum / sum of squares (InstanceNorm statistics)
+  EPI_ARGMAX = 4     // first-max argmax over num_classes columns -> uint8 mask (+ optional fp32 logits)
+};
+
+static const int kMaxSlots = 16;
+
+struct ConvGeom {
+  int H, W, N;                 // input spatial size, batch
+  int TH, TW, NB;              // tile: rows, cols (input resolution), samples
+  int BH, BW;                  // TMA box rows / cols = tile + 2 halo
+  int tiles_x, tiles_y, tiles_n;
+  int kch0;                    // k-chunks taken from source 0 (rest from source 1)
+  int n_k;                     // k-chunks in total
+  int CBK;                     // 8-channel blocks per k-chunk (even)
+  int n_mtiles;                // 128-row MMA tiles per CTA
+  int N_tile;                  // MMA N (output channels per CTA)
+  int n_ntiles;
+  int n_groups;                // accumulator groups per CTA (4 = all phases in one CTA)
+  int n_slots;                 // filter taps per CTA
+  int phase_grid;              // 1: blockIdx.z selects the phase (wide up-convs)
+  int stages;
+  int cb_stride_bytes;         // NB*BH*BW*16
+  int a_stage_bytes, b_stage_bytes;
+  int tmem_cols;
+  int smem_bytes;
+  short slot_shift[4][kMaxSlots];   // [phase or 0][slot] -> position shift dy*BW+dx inside the box
+  signed char slot_group[kMaxSlots];
+  signed char slot_first[kMaxSlots];  // first tap of its accumulator group (overwrite instead of accumulate)
+};
+
+struct ConvEpi {
+  bf16* out;                   // blocked [Cout/8][N][Ho][Wo][8] (null in argmax mode)
+  int Ho, Wo;                  // output spatial size (2H,2W for the phase modes)
+  int up;                      // 1: phase modes (out pixel = 2*pos + phase)
+  int flags;
+  int Cout;                    // real output channels (N_tile*n_ntiles may be padded above it)
+  const float* bias;           // [Cout] or null
+  const float* nscale;         // [Cout] per-channel noise scale or null
+  const float* noise;          // [N][Ho][Wo] fp32 or null
+  float* stats;                // [N][Cout][2] (sum, sumsq) or null
+  const bf16* addsrc;          // blocked [Cout/8][N][Ho/2][Wo/2][8], added after activation, or null
+  unsigned char* mask;         // [N][Ho][Wo]
+  float* logits;               // [N][num_classes][Ho][Wo] or null
+  int num_classes;
+};
+
+struct ConvParams {
+  CUtensorMap tm[2];
+  ConvGeom g;
+  ConvEpi e;
+  const bf16* wpack;
+};
+
+// A planned + packed convolution layer (host side).
+struct ConvLayer {
+  int mode = CONV3;
+  int cin0 = 0, cin1 = 0, cout = 0;   // channels of the two concatenated sources, real out channels
+  int H = 0, W = 0;                   // input spatial size the layer was planned for
+  ConvGeom g{};                       // geometry with N-independent fields filled
+  bf16* wpack_dev = nullptr;
+  size_t wpack_elems = 0;
+};
+
+struct PlanOverride {
+  int TH, TW, NB, CBK, N_tile, stages, phase_grid;   // 0 / -1 = keep default
+};
+
+// plan.cpp
+void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cout, int argmax_classes,
+               const PlanOverride* ov);
+void finish_geom_for_batch(ConvGeom& g, int N);
+// weights: CONV3/UPCONV3 (Cout,Cin,3,3); DECONV4 (Cin,Cout,4,4); CONV1/UPCONV1 (Cout,Cin,1,1); fp32, already
+// scaled (wscale / BN folded).  Returns packed bf16 host buffer in the order the kernel streams it.
+void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<bf16>& out);
+void make_act_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, int W, int boxW, int boxH, int boxN,
+                        int boxCB);
+
+// launchers (shiftconv.cu / elementwise.cu / styles.cu)
+void launch_shiftconv(const ConvParams& p, cudaStream_t st);
+
+struct Pass1Args {            // blur? + noise + bias + lrelu + stats  (generator, first half of a block)
+  const bf16* in; bf16* out;  // blocked; in may have sample stride 0 (constant tensor)
+  int C, N, H, W;
+  int blur;                   // 1: 3x3 [1,2,1]^2/16 zero-pad blur first
+  int in_broadcast;           // 1: input has a single sample (constant tensor)
+  const float* nscale; const float* bias; const float* noise;   // [C], [C], [N][H][W]
+  float* stats;               // [N][C][2]
+};
+void launch_pass1(const Pass1Args& a, cudaStream_t st);
+
+struct ApplyArgs {            // InstanceNorm + AdaIN: out = (t-mean)*rstd*(scale+1)+shift
+  const bf16* in; bf16* out;  // blocked
+  int C, N, H, W;
+  const float* stats;         // [N][C][2]
+  const float* styles;        // [N][style_stride]; (scale, shift) for this layer at style_off, style_off+C
+  int style_stride, style_off;
+  // optional ToRGB fused on the un-rounded values (last layer): rgb = Wrgb[3][C] x + brgb
+  const float* wrgb; const float* brgb; float* img_f32; unsigned char* img_u8; int nc;
+  float* out_nchw_f32;        // optional fp32 NCHW copy of the feature (drop-in mode)
+};
+void launch_apply(const ApplyArgs& a, cudaStream_t st);
+
+void launch_stats(const bf16* in, float* stats, int C, int N, int HW, cudaStream_t st);
+void launch_blocked_to_nchw(const bf16* in, float* out, int C, int N, int HW, cudaStream_t st);
+void launch_nchw_to_blocked(const float* in, bf16* out, int C, int N, int HW, cudaStream_t st);
+void launch_fill_noise(float* out, size_t plane_elems, int N, uint64_t seed, uint64_t first_sample, int layer,
+                       cudaStream_t st);
+void launch_fill_latents(float* z, int N, int Z, uint64_t seed, uint64_t first_sample, cudaStream_t st);
+
+struct DenseArgs {            // y[n][u] = act( sum_k x'[n][k] W[u][k] + b[u] ), W pre-scaled fp32
+  const float* x; const float* W; const float* b; float* y;
+  int N, K, U;
+  int lrelu;
+  int pixelnorm;              // 1: x' = x * rsqrt(mean(x^2)+1e-8)  (first mapping layer)
+  // styles mode: x' = avg*(1-psi[l]) + x*psi[l] with l = layer of unit u
+  const float* latent_avg; const float* psi; const int* unit_layer;
+  float add_one_first_half;   // unused
+};
+void launch_dense(const DenseArgs& a, cudaStream_t st);
+
+void set_error(const std::string& msg);
+bool cuda_ok(cudaError_t e, const char* what);
+
+}  // namespace gsx

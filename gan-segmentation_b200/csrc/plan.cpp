@@ -1,0 +1,235 @@
+// Host side of the shift-GEMM convolution: tile planning, weight packing into the UMMA B-operand
+// stream, TMA tensor-map encoding.  Compiled by nvcc as C++ (no device code).
+#include "gsx_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace gsx {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error_cstr() { return g_err.c_str(); }
+bool cuda_ok(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  set_error(std::string(what) + ": " + cudaGetErrorString(e));
+  return false;
+}
+
+static const int kSmemLimit = 227 * 1024;
+static const int kHeader = 4096;
+static const int kSlack = 8192;     // garbage-tolerant over-read of the last (partial) MMA tile
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static int pow2_cols(int c) {
+  int p = 32;
+  while (p < c) p <<= 1;
+  return p;
+}
+
+void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cout, int argmax_classes,
+               const PlanOverride* ov) {
+  L.mode = mode; L.H = H; L.W = W; L.cin0 = cin0; L.cin1 = cin1; L.cout = cout;
+  ConvGeom& g = L.g;
+  std::memset(&g, 0, sizeof(g));
+  g.H = H; g.W = W;
+  const bool up = (mode == UPCONV3 || mode == DECONV4);
+  const int cb0 = cin0 / 8, cb1 = cin1 / 8, cbt = cb0 + cb1;
+
+  int N_tile = argmax_classes > 0 ? 16 : std::min(cout, 128);
+  if (ov && ov->N_tile > 0) N_tile = ov->N_tile;
+  int phase_grid = (up && cout > 64) ? 1 : 0;
+  if (ov && ov->phase_grid >= 0 && up) phase_grid = ov->phase_grid;
+  const int G = (up && !phase_grid) ? 4 : 1;
+  const bool thin = (cin0 + cin1) <= 64 && cout <= 64;
+  int budget_cols = thin ? 256 : 512;
+  int max_mt = std::max(1, budget_cols / (G * N_tile));
+  max_mt = std::min(max_mt, 32);
+
+  int TW = (W <= 126) ? W : ((W % 64 == 0) ? 64 : 126);
+  if (ov && ov->TW > 0) TW = ov->TW;
+  const int BW = TW + 2;
+  const int cap = max_mt * 128;
+  int NB = 1, TH;
+  if (TW == W && (H + 2) * BW * 2 <= cap) {
+    TH = H;
+    NB = std::min(cap / ((H + 2) * BW), 64);
+  } else {
+    int th_max = (cap - TW) / BW + 1;
+    th_max = std::max(1, std::min(th_max, std::min(H, 254)));
+    const int ty = ceil_div(H, th_max);
+    TH = ceil_div(H, ty);
+  }
+  if (ov && ov->TH > 0) TH = ov->TH;
+  if (ov && ov->NB > 0) NB = ov->NB;
+
+  const int n_slots = (mode == CONV3) ? 9 : (mode == CONV1 ? 1 : (phase_grid ? 4 : 16));
+
+  // k-chunk depth and pipeline stages under the shared-memory limit
+  int CBK = 0, stages = 0;
+  for (;;) {
+    const int BH = TH + 2;
+    int cbs[4] = {8, 4, 2, 0};
+    if (ov && ov->CBK > 0) { cbs[0] = ov->CBK; cbs[1] = 0; }
+    bool found = false;
+    const long lim = thin ? 110 * 1024 : kSmemLimit;      // thin layers: leave room for 2 CTAs per SM
+    for (int ci = 0; cbs[ci] && !found; ++ci) {
+      const int c = cbs[ci];
+      if (c > cbt || cb0 % c || (cb1 && cb1 % c)) continue;
+      const int n_k = cbt / c;
+      const long a_st = (long)NB * BH * BW * 16 * c;
+      const long b_st = (long)n_slots * (c / 2) * N_tile * 32;
+      if (a_st / c >= (1 << 18)) continue;                 // LBO field is 14 bits of 16-byte units
+      const int s_hi = (ov && ov->stages > 0) ? ov->stages : std::min(n_k, thin ? 2 : 4);
+      const int s_lo = (ov && ov->stages > 0) ? ov->stages : std::min(n_k, 2);
+      for (int s = s_hi; s >= s_lo && s >= 1; --s) {
+        if (kHeader + s * (a_st + b_st) + kSlack <= lim) { CBK = c; stages = s; found = true; break; }
+      }
+    }
+    if (found) break;
+    if (NB > 1) { NB = std::max(1, NB / 2); continue; }
+    if (TH > 1) { const int t2 = ceil_div(H, ceil_div(H, TH) + 1); TH = (t2 < TH) ? t2 : TH - 1; continue; }
+    set_error("plan_conv: no feasible tiling");
+    return;
+  }
+
+  g.TH = TH; g.TW = TW; g.NB = NB; g.BH = TH + 2; g.BW = BW;
+  g.tiles_x = ceil_div(W, TW); g.tiles_y = ceil_div(H, TH);
+  g.CBK = CBK; g.kch0 = cb0 / CBK; g.n_k = cbt / CBK;
+  g.N_tile = N_tile; g.n_ntiles = ceil_div(argmax_classes > 0 ? argmax_classes : cout, N_tile);
+  g.n_groups = G; g.n_slots = n_slots; g.phase_grid = phase_grid; g.stages = stages;
+  g.n_mtiles = ceil_div(((NB - 1) * g.BH + TH - 1) * BW + TW, 128);
+  g.cb_stride_bytes = NB * g.BH * BW * 16;
+  g.a_stage_bytes = g.cb_stride_bytes * CBK;
+  g.b_stage_bytes = n_slots * (CBK / 2) * N_tile * 32;
+  g.tmem_cols = pow2_cols(G * g.n_mtiles * N_tile);
+  g.smem_bytes = kHeader + stages * (g.a_stage_bytes + g.b_stage_bytes) + kSlack;
+  if (g.tmem_cols > 512) { set_error("plan_conv: TMEM budget exceeded"); return; }
+
+  for (int ph = 0; ph < 4; ++ph)
+    for (int s = 0; s < kMaxSlots; ++s) g.slot_shift[ph][s] = 0;
+  if (mode == CONV3) {
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int s = ky * 3 + kx;
+        g.slot_shift[0][s] = (short)(ky * BW + kx); g.slot_group[s] = 0; g.slot_first[s] = (s == 0);
+      }
+  } else if (mode == CONV1) {
+    g.slot_shift[0][0] = (short)(BW + 1); g.slot_group[0] = 0; g.slot_first[0] = 1;
+  } else {
+    for (int ph = 0; ph < 4; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          const short sh = (short)((py + a) * BW + (px + b));
+          if (phase_grid) {
+            const int s = a * 2 + b;
+            g.slot_shift[ph][s] = sh; g.slot_group[s] = 0; g.slot_first[s] = (s == 0);
+          } else {
+            const int s = ph * 4 + a * 2 + b;
+            g.slot_shift[0][s] = sh; g.slot_group[s] = (signed char)ph; g.slot_first[s] = (a == 0 && b == 0);
+          }
+        }
+    }
+  }
+}
+
+void finish_geom_for_batch(ConvGeom& g, int N) {
+  g.N = N;
+  g.tiles_n = ceil_div(N, g.NB);
+}
+
+// Tap sets of the nearest-x2 + 3x3 conv folded onto the low-res grid:
+// output row 2y+py reads upsampled rows 2y+py+ky-1 = low-res row y + (py-1+a).
+static void up3_taps(int p, int a, int* k, int* nk) {
+  if (p == 0) { if (a == 0) { k[0] = 0; *nk = 1; } else { k[0] = 1; k[1] = 2; *nk = 2; } }
+  else        { if (a == 0) { k[0] = 0; k[1] = 1; *nk = 2; } else { k[0] = 2; *nk = 1; } }
+}
+
+void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<bf16>& out) {
+  const ConvGeom& g = L.g;
+  const int cin = L.cin0 + L.cin1, cout = L.cout;
+  const int nz = g.phase_grid ? 4 : 1;
+  const int k16pc = g.CBK / 2;
+  const size_t tile = (size_t)g.N_tile * 16;
+  out.assign((size_t)nz * g.n_ntiles * g.n_k * g.n_slots * k16pc * tile, __float2bfloat16(0.f));
+  const bool up = (L.mode == UPCONV3 || L.mode == DECONV4);
+
+  auto wval = [&](int z, int slot, int co, int ci) -> float {
+    if (L.mode == CONV3) { const int ky = slot / 3, kx = slot % 3; return w[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx]; }
+    if (L.mode == CONV1) return w[(size_t)co * cin + ci];
+    int ph, a, b;
+    if (g.phase_grid) { ph = z; a = slot >> 1; b = slot & 1; }
+    else { ph = slot >> 2; a = (slot >> 1) & 1; b = slot & 1; }
+    const int py = ph >> 1, px = ph & 1;
+    if (L.mode == UPCONV3) {
+      int ky[2], kx[2], nky, nkx;
+      up3_taps(py, a, ky, &nky); up3_taps(px, b, kx, &nkx);
+      float s = 0.f;
+      for (int i = 0; i < nky; ++i)
+        for (int j = 0; j < nkx; ++j) s += w[(((size_t)co * cin + ci) * 3 + ky[i]) * 3 + kx[j]];
+      return s;
+    }
+    // DECONV4: weight (Cin, Cout, 4, 4); out[2y'+py] gathers in[y'+py-1+a] with ky = 3-py (a=0) / 1-py (a=1)
+    const int ky = a == 0 ? 3 - py : 1 - py, kx = b == 0 ? 3 - px : 1 - px;
+    return w[(((size_t)ci * cout + co) * 4 + ky) * 4 + kx];
+  };
+  (void)up;
+  size_t base = 0;
+  for (int z = 0; z < nz; ++z)
+    for (int nt = 0; nt < g.n_ntiles; ++nt)
+      for (int kc = 0; kc < g.n_k; ++kc)
+        for (int slot = 0; slot < g.n_slots; ++slot)
+          for (int j = 0; j < k16pc; ++j, base += tile)
+            for (int nr = 0; nr < g.N_tile; ++nr) {
+              const int co = nt * g.N_tile + nr;
+              if (co >= cout) continue;
+              for (int k = 0; k < 16; ++k) {
+                const int ci = (kc * g.CBK + 2 * j) * 8 + k;
+                out[base + (size_t)(k >> 3) * (g.N_tile * 8) + (size_t)nr * 8 + (k & 7)] =
+                    __float2bfloat16(wval(z, slot, co, ci));
+              }
+            }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+void make_act_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, int W, int boxW, int boxH, int boxN,
+                        int boxCB) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return; }
+  // dim0 counts 8-byte units (2 per pixel) so that a 256-element box row spans 128 pixels
+  const cuuint64_t dims[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)(C / 8)};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)N * H * W * 16};
+  const cuuint32_t box[4] = {(cuuint32_t)boxW * 2, (cuuint32_t)boxH, (cuuint32_t)boxN, (cuuint32_t)boxCB};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (%d) C=%d N=%d H=%d W=%d box=%dx%dx%dx%d", (int)r, C, N, H,
+             W, boxW, boxH, boxN, boxCB);
+    set_error(buf);
+  }
+}
+
+}  // namespace gsx

@@ -1,0 +1,129 @@
+/* libgsx -- C ABI of the B200-native generate hot path (StyleGAN-v1 synthesis + segmentation decoder).
+ *
+ * The reference (author-hidden-name/GAN-segmentation) is pure Python over MXNet and defines no FFI;
+ * its boundary for this path is the Python surface of Generator / Decoder / ImageGenerator / SegSolver.
+ * Each entry point below states the reference interface it replaces (file:line relative to the
+ * reference tree).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions: every function returns 0 on success, <0 on error (gsx_last_error() returns a
+ * thread-local message).  Handles are opaque, one per GPU (the current CUDA device at create time),
+ * not thread-safe per handle.  Device pointers and workspaces are caller-owned (torch tensors on the
+ * Python side); forward calls only enqueue work on the caller's stream and never synchronise.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef GSX_H_
+#define GSX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gsx_synth gsx_synth;
+typedef struct gsx_dec gsx_dec;
+typedef void* gsx_stream;                 /* cudaStream_t */
+
+/* Generator hyper-parameters: the keys of ImageGenerator._get_config (image_generator.py:46-74)
+ * that Generator.__init__ reads (networks_stylegan.py:81-91). */
+typedef struct {
+  int max_res_log2;
+  int base_scale_y, base_scale_x;
+  int fmap_base;
+  float fmap_decay;
+  int fmap_max;
+  int latent_size;
+  int channels;
+} gsx_synth_cfg;
+
+/* Decoder hyper-parameters: cfg['in_channels'], cfg['features'] (incl. the trailing num_classes),
+ * cfg['use_bn'] of SegSolver.get_config (seg_solver.py:83-132); base = spatial size of level 0. */
+typedef struct {
+  int num_levels;
+  int in_channels[16];
+  int features[17];
+  int use_bn;
+  int base_y, base_x;
+} gsx_dec_cfg;
+
+typedef struct {
+  int TH, TW, NB, CBK, N_tile, stages, phase_grid;     /* 0 (phase_grid: -1) keeps the planner's choice */
+} gsx_plan_override;
+
+const char* gsx_last_error(void);
+int gsx_abi_version(void);
+/* Number of kernels this library has launched in the calling process (all handles); bench.py reports it. */
+uint64_t gsx_launch_count(void);
+
+/* ---- generator: replaces Generator(config) / load_parameters / __call__
+ *      (networks_stylegan.py:76-197, image_generator.py:20-22, :99) ---- */
+int gsx_synth_create(const gsx_synth_cfg* cfg, gsx_synth** out);
+void gsx_synth_destroy(gsx_synth* h);
+/* Parameter by reference name (structural 'net4.block2.0.weight' or legacy '16_conv_2_weight'),
+ * float32 host data in the reference's shape.  Unknown names are ignored (ignore_extra=True,
+ * image_generator.py:22) and reported with return value 1. */
+int gsx_synth_set_param(gsx_synth* h, const char* name, const float* data, const int64_t* shape, int ndim);
+/* Folds wscale/lr_mult, packs bf16 tensor-core operands, uploads.  Fails if a parameter is missing. */
+int gsx_synth_finalize(gsx_synth* h);
+int gsx_synth_workspace_bytes(const gsx_synth* h, int n, size_t* bytes);
+int gsx_synth_num_layers(const gsx_synth* h);                       /* 2*(max_res_log2-1) */
+int gsx_synth_feature_shape(const gsx_synth* h, int level, int* c, int* hgt, int* wid);
+/* z_dev [n,latent] fp32 or NULL (Philox(seed, first_sample+i)).  psi_host: NULL -> truncation_psi
+ * parameter, else num_layers floats.  noise_dev: NULL -> Philox, else num_layers device pointers to
+ * [n,1,h,w] fp32 (the planes AddNoise samples at networks_stylegan.py:300).  Outputs (each nullable):
+ * img_f32_dev [n,3,H,W], img_u8_dev [n,H,W,3] (image_generator.py:76-84), feats_f32_dev[level] [n,C,h,w].
+ * Blocked bf16 features stay in the workspace for gsx_dec_forward. */
+int gsx_synth_forward(gsx_synth* h, int n, const float* z_dev, const float* psi_host,
+                      const float* const* noise_dev, uint64_t seed, uint64_t first_sample, float* img_f32_dev,
+                      uint8_t* img_u8_dev, float* const* feats_f32_dev, void* ws, size_t ws_bytes,
+                      gsx_stream stream);
+/* Copies the noise plane / latents the last forward used (for parity dumps). */
+int gsx_synth_export_noise(gsx_synth* h, int n, int layer, float* out_dev, const void* ws, gsx_stream stream);
+int gsx_synth_export_latents(gsx_synth* h, int n, float* out_dev, const void* ws, gsx_stream stream);
+
+/* ---- decoder: replaces Decoder(cfg)(*features) + argmax of SegSolver.predict
+ *      (networks_seg.py:49-113, seg_solver.py:307-329) ---- */
+int gsx_dec_create(const gsx_dec_cfg* cfg, gsx_dec** out);
+void gsx_dec_destroy(gsx_dec* h);
+int gsx_dec_set_param(gsx_dec* h, const char* name, const float* data, const int64_t* shape, int ndim);
+int gsx_dec_finalize(gsx_dec* h);                                   /* folds BatchNorm (inference) */
+int gsx_dec_workspace_bytes(const gsx_dec* h, int n, size_t* bytes);
+/* Features either as fp32 NCHW device arrays (feats_f32_dev[level], the reference's predict() input)
+ * or, when feats_f32_dev is NULL, taken from the workspace of the last gsx_synth_forward(synth, n, ...).
+ * mask_dev [n,H,W] uint8 class ids (first maximum wins); logits_dev [n,classes,H,W] fp32 or NULL. */
+int gsx_dec_forward(gsx_dec* h, int n, const float* const* feats_f32_dev, const gsx_synth* synth,
+                    const void* synth_ws, float* logits_dev, uint8_t* mask_dev, void* ws, size_t ws_bytes,
+                    gsx_stream stream);
+
+/* ---- whole generate step with HOST buffers (main.py:97-99 per batch): z_host (or NULL) in,
+ *      uint8 image + uint8 mask out; H2D/D2H copies are enqueued on the stream inside the call.
+ *      stage_dev: n*(latent*4 + H*W*4) bytes of device scratch. ---- */
+int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z_host, const float* psi_host, uint64_t seed,
+                      uint64_t first_sample, uint8_t* img_u8_host, uint8_t* mask_host, void* synth_ws,
+                      size_t synth_ws_bytes, void* dec_ws, size_t dec_ws_bytes, void* stage_dev,
+                      size_t stage_bytes, gsx_stream stream);
+
+/* ---- single-operator hooks (tests / tuning; fp32 NCHW device tensors in and out, temporaries
+ *      are allocated inside, so not for the hot path) ---- */
+int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, int cout, const float* x0_dev,
+                const float* x1_dev, const float* w_host, const float* bias_dev, const float* nscale_dev,
+                const float* noise_dev, int flags, const float* addsrc_dev, float* out_dev, float* stats_dev,
+                uint8_t* mask_dev, float* logits_dev, int num_classes, const gsx_plan_override* ov,
+                int* plan_out /* 16 ints */, int repeat, float* ms_out, gsx_stream stream);
+/* Planner only (no GPU needed): the tiling gsx_op_conv / the forward passes would use. */
+int gsx_plan_query(int mode, int h, int w, int cin0, int cin1, int cout, int num_classes,
+                   const gsx_plan_override* ov, int* plan_out /* 16 ints */);
+int gsx_op_pass1(int n, int c, int h, int w, const float* x_dev, int blur, int in_broadcast,
+                 const float* nscale_dev, const float* bias_dev, const float* noise_dev, float* out_dev,
+                 float* stats_dev, gsx_stream stream);
+int gsx_op_apply(int n, int c, int h, int w, const float* x_dev, const float* stats_dev, const float* styles_dev,
+                 const float* wrgb_dev, const float* brgb_dev, int nc, float* out_dev, float* img_f32_dev,
+                 uint8_t* img_u8_dev, gsx_stream stream);
+int gsx_op_fill_normal(float* out_dev, size_t per_sample, int n, uint64_t seed, uint64_t first_sample,
+                       int stream_id, gsx_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSX_H_ */
