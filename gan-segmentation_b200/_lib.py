@@ -7,7 +7,11 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libgsx.so')
+# One shared library per 16-bit storage / tensor-core operand type (csrc/Makefile):
+#   fp16 -> libgsx.so (default: meets the image tolerance), bf16 -> libgsx_bf16.so (the north star's type)
+LIB_PATHS = {'fp16': os.path.join(_HERE, 'libgsx.so'), 'bf16': os.path.join(_HERE, 'libgsx_bf16.so')}
+LIB_PATH = LIB_PATHS['fp16']
+DEFAULT_DTYPE = os.environ.get('GSX_DTYPE', 'fp16')
 CSRC = os.path.join(_HERE, 'csrc')
 
 # enums of gsx_internal.h / gsx.h
@@ -46,7 +50,7 @@ def build(verbose=False):
     return LIB_PATH
 
 
-_lib = None
+_libs = {}
 
 _vp, _fp, _i, _u64, _sz = C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_size_t
 
@@ -82,27 +86,35 @@ _SIGS = {
 EXPORTS = tuple(_SIGS)
 
 
-def lib():
-    """Load libgsx.so (once).  Raises GsxError when it is missing -- there is no fallback."""
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise GsxError(f'{LIB_PATH} not found: run __graft_entry__.build() (make -C {CSRC}); '
+def lib(dtype=None):
+    """Load the library for ``dtype`` (once).  Raises GsxError when it is missing -- there is no fallback."""
+    dtype = dtype or DEFAULT_DTYPE
+    if dtype not in LIB_PATHS:
+        raise GsxError(f'unknown dtype {dtype!r} (fp16 or bf16)')
+    if dtype not in _libs:
+        path = LIB_PATHS[dtype]
+        if not os.path.exists(path):
+            raise GsxError(f'{path} not found: run __graft_entry__.build() (make -C {CSRC}); '
                            'the generate path has no CPU fallback')
-        l = C.CDLL(LIB_PATH)
+        l = C.CDLL(path)
         for name, (res, args) in _SIGS.items():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        _lib = l
-    return _lib
+        _libs[dtype] = l
+    return _libs[dtype]
 
 
-def check(rc, what=''):
+def check(rc, what='', dtype=None):
     if rc < 0:
-        msg = lib().gsx_last_error()
+        msg = lib(dtype).gsx_last_error()
         raise GsxError(f'{what}: {msg.decode() if msg else rc}')
     return rc
+
+
+def launch_count():
+    """Kernels launched by every loaded library in this process."""
+    return sum(int(l.gsx_launch_count()) for l in _libs.values())
 
 
 def ptr(t):

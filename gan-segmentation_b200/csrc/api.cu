@@ -78,7 +78,7 @@ struct Arena {              // carves a caller-owned workspace
 };
 
 // Runs one planned conv layer: builds the tensor maps for this batch / these buffers and launches.
-static bool run_conv(const ConvLayer& L, int N, const bf16* x0, const bf16* x1, const ConvEpi& epi, cudaStream_t st) {
+static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1, const ConvEpi& epi, cudaStream_t st) {
   ConvParams p;
   p.g = L.g;
   finish_geom_for_batch(p.g, N);
@@ -95,7 +95,7 @@ static bool run_conv(const ConvLayer& L, int N, const bf16* x0, const bf16* x1, 
 }
 
 static bool upload_conv(ConvLayer& L, const float* w) {
-  std::vector<bf16> packed;
+  std::vector<act_t> packed;
   pack_conv_weights(L, w, packed);
   L.wpack_elems = packed.size();
   L.wpack_dev = dev_upload(packed);
@@ -127,7 +127,7 @@ struct gsx_synth {
   float *d_aff_w = nullptr, *d_aff_b = nullptr;
   int* d_unit_layer = nullptr;
   float *d_latent_avg = nullptr, *d_psi = nullptr, *d_wrgb = nullptr, *d_brgb = nullptr;
-  bf16* d_const = nullptr;
+  act_t* d_const = nullptr;
   int last_n = 0;
 
   int nf(int r) const {
@@ -138,13 +138,18 @@ struct gsx_synth {
 };
 
 struct SynthWs {
-  float *z, *wa, *wb, *styles, *stats, *psi;
+  float *z, *wa, *wb, *styles, *psi;
   std::vector<float*> noise;
-  std::vector<bf16*> feat;
-  bf16 *bufA, *bufB;
-  size_t stats_bytes, total;
-  std::vector<size_t> stats_off;          // floats, per style layer
+  std::vector<float*> partial;            // per style layer: per-tile (sum, sumsq) partials [N][T][C][2]
+  std::vector<float*> coef;               // per style layer: AdaIN coefficients [N][C][2]
+  std::vector<int> stats_T;
+  std::vector<act_t*> feat;
+  act_t *bufA, *bufB;
+  size_t total;
 };
+
+// Tiles per sample the statistics of style layer l arrive in (must match what the producers write).
+static int synth_stats_tiles(const gsx_synth* h, int l);
 
 static SynthWs synth_layout(const gsx_synth* h, int N, void* base) {
   SynthWs w;
@@ -155,13 +160,12 @@ static SynthWs synth_layout(const gsx_synth* h, int N, void* base) {
   w.wb = a.take<float>((size_t)N * Z);
   w.styles = a.take<float>((size_t)N * h->S_total);
   w.psi = a.take<float>(h->nlayers);
-  size_t so = 0;
   for (int l = 0; l < h->nlayers; ++l) {
-    w.stats_off.push_back(so);
-    so += (size_t)N * h->nf(2 + l / 2) * 2;
+    const int C = h->nf(2 + l / 2), T = synth_stats_tiles(h, l);
+    w.stats_T.push_back(T);
+    w.partial.push_back(a.take<float>((size_t)N * T * C * 2));
+    w.coef.push_back(a.take<float>((size_t)N * C * 2));
   }
-  w.stats = a.take<float>(so);
-  w.stats_bytes = so * sizeof(float);
   size_t maxact = 0;
   for (int r = 2; r <= h->L; ++r) {
     int hh, ww;
@@ -169,13 +173,24 @@ static SynthWs synth_layout(const gsx_synth* h, int N, void* base) {
     const size_t plane = (size_t)N * hh * ww;
     w.noise.push_back(a.take<float>(plane));
     w.noise.push_back(a.take<float>(plane));
-    w.feat.push_back(a.take<bf16>(plane * h->nf(r)));
+    w.feat.push_back(a.take<act_t>(plane * h->nf(r)));
     maxact = std::max(maxact, plane * h->nf(r));
   }
-  w.bufA = a.take<bf16>(maxact);
-  w.bufB = a.take<bf16>(maxact);
+  w.bufA = a.take<act_t>(maxact);
+  w.bufB = a.take<act_t>(maxact);
   w.total = a.off;
   return w;
+}
+
+static int synth_stats_tiles(const gsx_synth* h, int l) {
+  int hh, ww;
+  h->hw(2 + l / 2, hh, ww);
+  if ((l & 1) == 0) return pass1_tiles(hh * ww);
+  if ((size_t)(l / 2) < h->blocks.size()) {
+    const ConvGeom& g = h->blocks[l / 2].conv2.g;
+    if (g.NB == 1) return g.tiles_x * g.tiles_y;
+  }
+  return stats_tiles(hh * ww);
 }
 
 extern "C" const char* gsx_last_error(void) { return last_error_cstr(); }
@@ -289,15 +304,15 @@ extern "C" int gsx_synth_finalize(gsx_synth* h) {
     cudaFree(h->d_latent_avg); cudaFree(h->d_psi);
     h->d_latent_avg = dev_upload(avg->v); h->d_psi = dev_upload(psi->v);
   }
-  // ---- constant tensor -> blocked bf16 [C/8][1][by][bx][8]
+  // ---- constant tensor -> blocked act_t [C/8][1][by][bx][8]
   {
     const int C = h->nf(2), by = h->cfg.base_scale_y, bx = h->cfg.base_scale_x;
     const HostTensor* c = need(P, "constant_tensor", (size_t)C * by * bx);
     if (!c) return -1;
-    std::vector<bf16> cb((size_t)C * by * bx);
+    std::vector<act_t> cb((size_t)C * by * bx);
     for (int ch = 0; ch < C; ++ch)
       for (int p = 0; p < by * bx; ++p)
-        cb[((size_t)(ch / 8) * by * bx + p) * 8 + (ch & 7)] = __float2bfloat16(c->v[(size_t)ch * by * bx + p]);
+        cb[((size_t)(ch / 8) * by * bx + p) * 8 + (ch & 7)] = to_act(c->v[(size_t)ch * by * bx + p]);
     cudaFree(h->d_const);
     h->d_const = dev_upload(cb);
   }
@@ -385,7 +400,6 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
   if (w.total > ws_bytes) { set_error("workspace too small"); return -1; }
   const int Z = h->cfg.latent_size;
   set_error("");
-  if (!cuda_ok(cudaMemsetAsync(w.stats, 0, w.stats_bytes, st), "memset stats")) return -2;
   if (z_dev) {
     if (!cuda_ok(cudaMemcpyAsync(w.z, z_dev, (size_t)N * Z * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy z")) return -2;
   } else {
@@ -428,8 +442,8 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
   for (size_t bi = 0; bi < h->blocks.size(); ++bi) {
     const SynthBlock& b = h->blocks[bi];
     const int l1 = 2 * (int)bi, l2 = l1 + 1;
-    float* st1 = w.stats + w.stats_off[l1];
-    float* st2 = w.stats + w.stats_off[l2];
+    float* st1 = w.partial[l1];
+    float* st2 = w.partial[l2];
     Pass1Args p1{};
     p1.out = w.bufB; p1.C = b.C; p1.N = N; p1.H = b.H; p1.W = b.W;
     p1.nscale = b.ns1; p1.bias = b.b1; p1.noise = noise[l1]; p1.stats = st1;
@@ -442,9 +456,11 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
       p1.in = w.bufA; p1.in_broadcast = 0; p1.blur = 1;
     }
     launch_pass1(p1, st); g_launches++;
+    launch_finalize(st1, w.stats_T[l1], N, b.C, b.H * b.W, w.styles, h->S_total, h->style_off[l1], w.coef[l1], st);
+    g_launches++;
     ApplyArgs a1{};
     a1.in = w.bufB; a1.out = w.bufB; a1.C = b.C; a1.N = N; a1.H = b.H; a1.W = b.W;
-    a1.stats = st1; a1.styles = w.styles; a1.style_stride = h->S_total; a1.style_off = h->style_off[l1];
+    a1.coef = w.coef[l1];
     launch_apply(a1, st); g_launches++;
 
     ConvEpi e2{};
@@ -453,12 +469,15 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     const bool fused_stats = b.conv2.g.NB == 1;
     e2.flags = EPI_LRELU | (fused_stats ? EPI_STATS : 0);
     e2.stats = fused_stats ? st2 : nullptr;
+    e2.stats_T = w.stats_T[l2];
     if (!run_conv(b.conv2, N, w.bufB, nullptr, e2, st)) return -2;
     if (!fused_stats) { launch_stats(w.bufA, st2, b.C, N, b.H * b.W, st); g_launches++; }
+    launch_finalize(st2, w.stats_T[l2], N, b.C, b.H * b.W, w.styles, h->S_total, h->style_off[l2], w.coef[l2], st);
+    g_launches++;
 
     ApplyArgs a2{};
     a2.in = w.bufA; a2.out = w.feat[bi]; a2.C = b.C; a2.N = N; a2.H = b.H; a2.W = b.W;
-    a2.stats = st2; a2.styles = w.styles; a2.style_stride = h->S_total; a2.style_off = h->style_off[l2];
+    a2.coef = w.coef[l2];
     a2.out_nchw_f32 = feats_f32_dev ? feats_f32_dev[bi] : nullptr;
     if (b.r == h->L) {
       a2.wrgb = h->d_wrgb; a2.brgb = h->d_brgb; a2.img_f32 = img_f32_dev; a2.img_u8 = img_u8_dev; a2.nc = h->cfg.channels;
@@ -503,7 +522,7 @@ struct gsx_dec {
 };
 
 struct DecWs {
-  std::vector<bf16*> feat, c, a, sc, prev;     // prev[i] = input "prev" of level i (null at 0)
+  std::vector<act_t*> feat, c, a, sc, prev;     // prev[i] = input "prev" of level i (null at 0)
   size_t total;
 };
 
@@ -516,12 +535,12 @@ static DecWs dec_layout(const gsx_dec* d, int N, void* base, bool own_feats) {
   for (int i = 0; i < nf; ++i) {
     const int H = d->cfg.base_y << i, W = d->cfg.base_x << i;
     const size_t plane = (size_t)N * H * W;
-    if (own_feats) w.feat[i] = ar.take<bf16>(plane * d->cfg.in_channels[i]);
-    w.c[i] = ar.take<bf16>(plane * d->cfg.features[i]);
+    if (own_feats) w.feat[i] = ar.take<act_t>(plane * d->cfg.in_channels[i]);
+    w.c[i] = ar.take<act_t>(plane * d->cfg.features[i]);
     if (i < nf - 1) {
-      w.a[i] = ar.take<bf16>(plane * 4 * d->cfg.features[i + 1]);
-      w.sc[i] = ar.take<bf16>(plane * d->cfg.features[i + 1]);
-      w.prev[i + 1] = ar.take<bf16>(plane * 4 * d->cfg.features[i + 1]);
+      w.a[i] = ar.take<act_t>(plane * 4 * d->cfg.features[i + 1]);
+      w.sc[i] = ar.take<act_t>(plane * d->cfg.features[i + 1]);
+      w.prev[i + 1] = ar.take<act_t>(plane * 4 * d->cfg.features[i + 1]);
     }
   }
   w.total = ar.off;
@@ -662,7 +681,7 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
   const bool own = feats_f32_dev != nullptr;
   DecWs w = dec_layout(d, N, ws, true);
   if (w.total > ws_bytes) { set_error("decoder workspace too small"); return -1; }
-  std::vector<const bf16*> feat(nf);
+  std::vector<const act_t*> feat(nf);
   if (own) {
     for (int i = 0; i < nf; ++i) {
       const DecLevel& l = d->levels[i];
@@ -687,15 +706,15 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
       e.out = w.c[i]; e.Ho = l.H; e.Wo = l.W; e.flags = EPI_LRELU; e.Cout = l.f; e.bias = l.b_cvt;
       if (!run_conv(l.cvt, N, feat[i], nullptr, e, st)) return -2;
     }
-    const bf16* x0 = i > 0 ? w.prev[i] : w.c[i];
-    const bf16* x1 = i > 0 ? w.c[i] : nullptr;
+    const act_t* x0 = i > 0 ? w.prev[i] : w.c[i];
+    const act_t* x1 = i > 0 ? w.c[i] : nullptr;
     if (i < nf - 1) {
       {
         ConvEpi e{};
         e.out = w.a[i]; e.Ho = 2 * l.H; e.Wo = 2 * l.W; e.up = 1; e.flags = EPI_LRELU; e.Cout = l.fnext; e.bias = l.b_a;
         if (!run_conv(l.conv_a, N, x0, x1, e, st)) return -2;
       }
-      const bf16* sc = x0;
+      const act_t* sc = x0;
       if (l.has_shortcut) {
         ConvEpi e{};
         e.out = w.sc[i]; e.Ho = l.H; e.Wo = l.W; e.flags = 0; e.Cout = l.fnext; e.bias = l.b_sc;

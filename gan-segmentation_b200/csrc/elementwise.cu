@@ -1,4 +1,4 @@
-// HBM-bound passes of the generate path on the blocked activation layout [C/8][N][H][W][8] bf16.
+// HBM-bound passes of the generate path on the blocked activation layout [C/8][N][H][W][8] act_t.
 // All global accesses are 128-bit, consecutive lanes on consecutive pixels.
 //   pass1 : Blur (networks_stylegan.py:200-236) + AddNoise (:302-304) + Bias (:544) + LeakyReLU(0.2)
 //           (:38-40) + InstanceNorm sum/sumsq (warp-shuffle reduction) in one read + one write.
@@ -14,25 +14,35 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-    f[2 * k] = __bfloat162float(b2.x);
-    f[2 * k + 1] = __bfloat162float(b2.y);
+#if GSX_FP16
+    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+#else
+    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+#endif
+    f[2 * k] = v.x;
+    f[2 * k + 1] = v.y;
   }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+#if GSX_FP16
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  __half2 h = __floats2half2_rn(a, b);
+#else
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+#endif
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 o;
-  __nv_bfloat162 h;
-  h = __floats2bfloat162_rn(f[0], f[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
-  h = __floats2bfloat162_rn(f[2], f[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
-  h = __floats2bfloat162_rn(f[4], f[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
-  h = __floats2bfloat162_rn(f[6], f[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+  o.x = pack2(f[0], f[1]); o.y = pack2(f[2], f[3]); o.z = pack2(f[4], f[5]); o.w = pack2(f[6], f[7]);
   return o;
 }
 
-// Block-wide reduction of 16 per-thread values, then one atomicAdd per value per block.
-// dst[i*stride] += sum over the block of v[i].
+// Block-wide reduction of 16 per-thread values (8 channel sums, 8 sums of squares) in a fixed order,
+// then one plain store per value: dst[ch*2 + which] = block total.  No atomics -> bit-reproducible.
 template <int NV>
-__device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], float* dst0, float* dst1, int nthreads) {
+__device__ __forceinline__ void block_reduce_store(float (&v)[NV], float* dst0, float* dst1, int nthreads) {
   __shared__ float red[32][NV + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -51,7 +61,7 @@ __device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], float* dst0,
     for (int w = 0; w < nw; ++w) s += red[w][threadIdx.x];
     // values 0..7 = channel sums, 8..15 = channel sums of squares
     const int ch = threadIdx.x & 7;
-    atomicAdd((threadIdx.x < 8 ? dst0 : dst1) + ch * 2, s);
+    ((threadIdx.x < 8 ? dst0 : dst1) + ch * 2)[0] = s;
   }
 }
 
@@ -63,8 +73,8 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(const Pass1Args a) {
   const int plane = blockIdx.y;                 // cb * N + n
   const int cb = plane / a.N, n = plane - cb * a.N;
   const int HW = a.H * a.W;
-  const bf16* in = a.in + ((size_t)(a.in_broadcast ? cb : plane) * HW) * 8;
-  bf16* out = a.out + ((size_t)plane * HW) * 8;
+  const act_t* in = a.in + ((size_t)(a.in_broadcast ? cb : plane) * HW) * 8;
+  act_t* out = a.out + ((size_t)plane * HW) * 8;
   const float* noise = a.noise ? a.noise + (size_t)n * HW : nullptr;
 
   float ns[8], bs[8];
@@ -118,22 +128,24 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(const Pass1Args a) {
     }
   }
   if (a.stats) {
-    float* st = a.stats + ((size_t)n * a.C + cb * 8) * 2;
-    block_reduce_atomic<16>(acc, st, st + 1, kP1Threads);
+    float* st = a.stats + (((size_t)n * gridDim.x + blockIdx.x) * a.C + cb * 8) * 2;
+    block_reduce_store<16>(acc, st, st + 1, kP1Threads);
   }
 }
 
+int pass1_tiles(int HW) { return (HW + kP1Threads * kP1PixPerThread - 1) / (kP1Threads * kP1PixPerThread); }
+
 void launch_pass1(const Pass1Args& a, cudaStream_t st) {
   const int HW = a.H * a.W;
-  dim3 grid((HW + kP1Threads * kP1PixPerThread - 1) / (kP1Threads * kP1PixPerThread), (a.C / 8) * a.N);
+  dim3 grid(pass1_tiles(HW), (a.C / 8) * a.N);
   pass1_kernel<<<grid, kP1Threads, 0, st>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------ stats
-__global__ void __launch_bounds__(256) stats_kernel(const bf16* in, float* stats, int C, int N, int HW) {
+__global__ void __launch_bounds__(256) stats_kernel(const act_t* in, float* stats, int C, int N, int HW) {
   const int plane = blockIdx.y;
   const int cb = plane / N, n = plane - cb * N;
-  const bf16* src = in + (size_t)plane * HW * 8;
+  const act_t* src = in + (size_t)plane * HW * 8;
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
@@ -143,24 +155,51 @@ __global__ void __launch_bounds__(256) stats_kernel(const bf16* in, float* stats
 #pragma unroll
     for (int i = 0; i < 8; ++i) { acc[i] += f[i]; acc[8 + i] += f[i] * f[i]; }
   }
-  float* st = stats + ((size_t)n * C + cb * 8) * 2;
-  block_reduce_atomic<16>(acc, st, st + 1, 256);
+  float* st = stats + (((size_t)n * gridDim.x + blockIdx.x) * C + cb * 8) * 2;
+  block_reduce_store<16>(acc, st, st + 1, 256);
 }
 
-void launch_stats(const bf16* in, float* stats, int C, int N, int HW, cudaStream_t st) {
-  dim3 grid(min(16, (HW + 255) / 256), (C / 8) * N);
-  stats_kernel<<<grid, 256, 0, st>>>(in, stats, C, N, HW);
+int stats_tiles(int HW) { return min(16, (HW + 255) / 256); }
+
+void launch_stats(const act_t* in, float* stats_partial, int C, int N, int HW, cudaStream_t st) {
+  dim3 grid(stats_tiles(HW), (C / 8) * N);
+  stats_kernel<<<grid, 256, 0, st>>>(in, stats_partial, C, N, HW);
+}
+
+// ------------------------------------------------------------------------------------------ finalize
+__global__ void finalize_kernel(const float* __restrict__ partial, int T, int N, int C, float inv_hw,
+                                const float* __restrict__ styles, int style_stride, int style_off,
+                                float* __restrict__ coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // (n, c)
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C;
+  float s1 = 0.f, s2 = 0.f;
+  const float* p = partial + ((size_t)n * T * C + c) * 2;
+  for (int t = 0; t < T; ++t) {                             // fixed order
+    s1 += p[(size_t)t * C * 2];
+    s2 += p[(size_t)t * C * 2 + 1];
+  }
+  if (!styles) { coef[(size_t)i * 2] = s1; coef[(size_t)i * 2 + 1] = s2; return; }
+  const float mean = s1 * inv_hw;
+  const float var = fmaxf(s2 * inv_hw - mean * mean, 0.f);  // biased variance (InstanceNorm)
+  const float rstd = rsqrtf(var + 1e-5f);                   // gluon InstanceNorm eps
+  const float* sty = styles + (size_t)n * style_stride + style_off;
+  const float a = rstd * (sty[c] + 1.f);                    // ys + 1   (networks_stylegan.py:262)
+  coef[(size_t)i * 2] = a;
+  coef[(size_t)i * 2 + 1] = sty[C + c] - mean * a;          // yb
+}
+
+void launch_finalize(const float* partial, int T, int N, int C, int HW, const float* styles, int style_stride,
+                     int style_off, float* coef, cudaStream_t st) {
+  finalize_kernel<<<(N * C + 127) / 128, 128, 0, st>>>(partial, T, N, C, 1.f / (float)HW, styles, style_stride,
+                                                        style_off, coef);
 }
 
 // ------------------------------------------------------------------------------------------ apply
-__device__ __forceinline__ void adain_coeffs(const ApplyArgs& a, int n, int c, float inv_hw, float& ca, float& cb_) {
-  const float s1 = a.stats[((size_t)n * a.C + c) * 2], s2 = a.stats[((size_t)n * a.C + c) * 2 + 1];
-  const float mean = s1 * inv_hw;
-  const float var = fmaxf(s2 * inv_hw - mean * mean, 0.f);          // biased variance (InstanceNorm)
-  const float rstd = rsqrtf(var + 1e-5f);                           // gluon InstanceNorm eps
-  const float* sty = a.styles + (size_t)n * a.style_stride + a.style_off;
-  ca = rstd * (sty[c] + 1.f);                                       // ys + 1   (networks_stylegan.py:262)
-  cb_ = sty[a.C + c] - mean * ca;                                   // yb
+__device__ __forceinline__ void adain_coeffs(const ApplyArgs& a, int n, int c, float /*inv_hw*/, float& ca, float& cb_) {
+  const float2 v = *reinterpret_cast<const float2*>(a.coef + ((size_t)n * a.C + c) * 2);
+  ca = v.x;
+  cb_ = v.y;
 }
 
 static constexpr int kApThreads = 256;
@@ -174,8 +213,8 @@ __global__ void __launch_bounds__(kApThreads) apply_kernel(const ApplyArgs a) {
   float ca[8], cc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) adain_coeffs(a, n, cb * 8 + i, inv_hw, ca[i], cc[i]);
-  const bf16* in = a.in + (size_t)plane * HW * 8;
-  bf16* out = a.out + (size_t)plane * HW * 8;
+  const act_t* in = a.in + (size_t)plane * HW * 8;
+  act_t* out = a.out + (size_t)plane * HW * 8;
   const int base = blockIdx.x * (kApThreads * kApPixPerThread);
   uint4 r[kApPixPerThread];
 #pragma unroll
@@ -261,7 +300,7 @@ void launch_apply(const ApplyArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------ layout
-__global__ void blocked_to_nchw_kernel(const bf16* in, float* out, int C, int N, int HW) {
+__global__ void blocked_to_nchw_kernel(const act_t* in, float* out, int C, int N, int HW) {
   const int plane = blockIdx.y;
   const int cb = plane / N, n = plane - cb * N;
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
@@ -271,7 +310,7 @@ __global__ void blocked_to_nchw_kernel(const bf16* in, float* out, int C, int N,
     for (int i = 0; i < 8; ++i) out[((size_t)n * C + cb * 8 + i) * HW + pix] = f[i];
   }
 }
-__global__ void nchw_to_blocked_kernel(const float* in, bf16* out, int C, int N, int HW) {
+__global__ void nchw_to_blocked_kernel(const float* in, act_t* out, int C, int N, int HW) {
   const int plane = blockIdx.y;
   const int cb = plane / N, n = plane - cb * N;
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
@@ -281,11 +320,11 @@ __global__ void nchw_to_blocked_kernel(const float* in, bf16* out, int C, int N,
     *reinterpret_cast<uint4*>(out + ((size_t)plane * HW + pix) * 8) = pack8(f);
   }
 }
-void launch_blocked_to_nchw(const bf16* in, float* out, int C, int N, int HW, cudaStream_t st) {
+void launch_blocked_to_nchw(const act_t* in, float* out, int C, int N, int HW, cudaStream_t st) {
   dim3 grid(min((HW + 255) / 256, 1024), (C / 8) * N);
   blocked_to_nchw_kernel<<<grid, 256, 0, st>>>(in, out, C, N, HW);
 }
-void launch_nchw_to_blocked(const float* in, bf16* out, int C, int N, int HW, cudaStream_t st) {
+void launch_nchw_to_blocked(const float* in, act_t* out, int C, int N, int HW, cudaStream_t st) {
   dim3 grid(min((HW + 255) / 256, 1024), (C / 8) * N);
   nchw_to_blocked_kernel<<<grid, 256, 0, st>>>(in, out, C, N, HW);
 }

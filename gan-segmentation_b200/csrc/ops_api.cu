@@ -1,5 +1,5 @@
 // Single-operator entry points of the C ABI (tests and tuning sweeps).  fp32 NCHW device tensors in
-// and out; blocked bf16 temporaries are allocated per call, so these are not hot-path functions.
+// and out; blocked act_t temporaries are allocated per call, so these are not hot-path functions.
 #include "../../include/gsx.h"
 #include "gsx_internal.h"
 
@@ -40,15 +40,15 @@ extern "C" int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, in
   if (ov) { po.TH = ov->TH; po.TW = ov->TW; po.NB = ov->NB; po.CBK = ov->CBK; po.N_tile = ov->N_tile; po.stages = ov->stages; po.phase_grid = ov->phase_grid; }
   plan_conv(L, mode, h, w, cin0, cin1, cout, argmax ? num_classes : 0, ov ? &po : nullptr);
   if (*last_error_cstr()) return -1;
-  std::vector<bf16> packed;
+  std::vector<act_t> packed;
   pack_conv_weights(L, w_host, packed);
-  bf16* wp = tmp.get<bf16>(packed.size());
-  bf16* xb0 = tmp.get<bf16>((size_t)n * cin0 * h * w);
-  bf16* xb1 = cin1 ? tmp.get<bf16>((size_t)n * cin1 * h * w) : nullptr;
-  bf16* ob = argmax ? nullptr : tmp.get<bf16>((size_t)n * cout * Ho * Wo);
-  bf16* ab = addsrc_dev ? tmp.get<bf16>((size_t)n * cout * (Ho / 2) * (Wo / 2)) : nullptr;
+  act_t* wp = tmp.get<act_t>(packed.size());
+  act_t* xb0 = tmp.get<act_t>((size_t)n * cin0 * h * w);
+  act_t* xb1 = cin1 ? tmp.get<act_t>((size_t)n * cin1 * h * w) : nullptr;
+  act_t* ob = argmax ? nullptr : tmp.get<act_t>((size_t)n * cout * Ho * Wo);
+  act_t* ab = addsrc_dev ? tmp.get<act_t>((size_t)n * cout * (Ho / 2) * (Wo / 2)) : nullptr;
   if (!wp || !xb0 || (cin1 && !xb1) || (!argmax && !ob) || (addsrc_dev && !ab)) { set_error("cudaMalloc failed"); return -2; }
-  if (!cuda_ok(cudaMemcpyAsync(wp, packed.data(), packed.size() * sizeof(bf16), cudaMemcpyHostToDevice, st), "H2D weights")) return -2;
+  if (!cuda_ok(cudaMemcpyAsync(wp, packed.data(), packed.size() * sizeof(act_t), cudaMemcpyHostToDevice, st), "H2D weights")) return -2;
   launch_nchw_to_blocked(x0_dev, xb0, cin0, n, h * w, st);
   if (cin1) launch_nchw_to_blocked(x1_dev, xb1, cin1, n, h * w, st);
   if (addsrc_dev) launch_nchw_to_blocked(addsrc_dev, ab, cout, n, (Ho / 2) * (Wo / 2), st);
@@ -65,7 +65,11 @@ extern "C" int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, in
   const bool want_stats = (flags & EPI_STATS) != 0;
   const bool fused_stats = want_stats && p.g.NB == 1;
   if (want_stats && !fused_stats) e.flags &= ~EPI_STATS;
-  e.stats = fused_stats ? stats_dev : nullptr;
+  const int stats_T = fused_stats ? p.g.tiles_x * p.g.tiles_y : stats_tiles(Ho * Wo);
+  float* partial = want_stats ? tmp.get<float>((size_t)n * stats_T * cout * 2) : nullptr;
+  if (want_stats && !partial) { set_error("cudaMalloc failed"); return -2; }
+  e.stats = fused_stats ? partial : nullptr;
+  e.stats_T = stats_T;
   p.e = e;
   make_act_tensormap(&p.tm[0], xb0, cin0, n, h, w, p.g.BW, p.g.BH, p.g.NB, p.g.CBK);
   if (cin1) make_act_tensormap(&p.tm[1], xb1, cin1, n, h, w, p.g.BW, p.g.BH, p.g.NB, p.g.CBK);
@@ -77,10 +81,10 @@ extern "C" int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, in
                           g.smem_bytes, g.tiles_x * g.tiles_y * g.tiles_n, g.n_ntiles, g.n_groups, g.n_slots, g.BW};
     for (int i = 0; i < 16; ++i) plan_out[i] = vals[i];
   }
-  if (want_stats) cudaMemsetAsync(stats_dev, 0, (size_t)n * cout * 2 * sizeof(float), st);
   launch_shiftconv(p, st); g_launches++;
   if (!cuda_ok(cudaGetLastError(), "shiftconv launch")) return -2;
-  if (want_stats && !fused_stats) launch_stats(ob, stats_dev, cout, n, Ho * Wo, st);
+  if (want_stats && !fused_stats) launch_stats(ob, partial, cout, n, Ho * Wo, st);
+  if (want_stats) launch_finalize(partial, stats_T, n, cout, Ho * Wo, nullptr, 0, 0, stats_dev, st);
   if (!argmax && out_dev) launch_blocked_to_nchw(ob, out_dev, cout, n, Ho * Wo, st);
   if (!cuda_ok(cudaStreamSynchronize(st), "gsx_op_conv")) return -2;
   if (repeat > 0 && ms_out) {
@@ -121,15 +125,17 @@ extern "C" int gsx_op_pass1(int n, int c, int h, int w, const float* x_dev, int 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Tmp tmp;
   const int nin = in_broadcast ? 1 : n;
-  bf16* xb = tmp.get<bf16>((size_t)nin * c * h * w);
-  bf16* ob = tmp.get<bf16>((size_t)n * c * h * w);
+  act_t* xb = tmp.get<act_t>((size_t)nin * c * h * w);
+  act_t* ob = tmp.get<act_t>((size_t)n * c * h * w);
   if (!xb || !ob) { set_error("cudaMalloc failed"); return -2; }
   launch_nchw_to_blocked(x_dev, xb, c, nin, h * w, st);
-  if (stats_dev) cudaMemsetAsync(stats_dev, 0, (size_t)n * c * 2 * sizeof(float), st);
+  const int T = pass1_tiles(h * w);
+  float* partial = stats_dev ? tmp.get<float>((size_t)n * T * c * 2) : nullptr;
   Pass1Args a{};
   a.in = xb; a.out = ob; a.C = c; a.N = n; a.H = h; a.W = w; a.blur = blur; a.in_broadcast = in_broadcast;
-  a.nscale = nscale_dev; a.bias = bias_dev; a.noise = noise_dev; a.stats = stats_dev;
+  a.nscale = nscale_dev; a.bias = bias_dev; a.noise = noise_dev; a.stats = partial;
   launch_pass1(a, st); g_launches++;
+  if (stats_dev) launch_finalize(partial, T, n, c, h * w, nullptr, 0, 0, stats_dev, st);
   launch_blocked_to_nchw(ob, out_dev, c, n, h * w, st);
   return cuda_ok(cudaStreamSynchronize(st), "gsx_op_pass1") ? 0 : -2;
 }
@@ -139,13 +145,16 @@ extern "C" int gsx_op_apply(int n, int c, int h, int w, const float* x_dev, cons
                             float* img_f32_dev, uint8_t* img_u8_dev, gsx_stream stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Tmp tmp;
-  bf16* xb = tmp.get<bf16>((size_t)n * c * h * w);
-  bf16* ob = tmp.get<bf16>((size_t)n * c * h * w);
+  act_t* xb = tmp.get<act_t>((size_t)n * c * h * w);
+  act_t* ob = tmp.get<act_t>((size_t)n * c * h * w);
   if (!xb || !ob) { set_error("cudaMalloc failed"); return -2; }
   launch_nchw_to_blocked(x_dev, xb, c, n, h * w, st);
+  float* coef = tmp.get<float>((size_t)n * c * 2);
+  if (!coef) { set_error("cudaMalloc failed"); return -2; }
+  launch_finalize(stats_dev, 1, n, c, h * w, styles_dev, 2 * c, 0, coef, st);
   ApplyArgs a{};
-  a.in = xb; a.out = ob; a.C = c; a.N = n; a.H = h; a.W = w; a.stats = stats_dev; a.styles = styles_dev;
-  a.style_stride = 2 * c; a.style_off = 0; a.wrgb = wrgb_dev; a.brgb = brgb_dev; a.nc = nc;
+  a.in = xb; a.out = ob; a.C = c; a.N = n; a.H = h; a.W = w; a.coef = coef;
+  a.wrgb = wrgb_dev; a.brgb = brgb_dev; a.nc = nc;
   a.img_f32 = img_f32_dev; a.img_u8 = img_u8_dev;
   launch_apply(a, st); g_launches++;
   launch_blocked_to_nchw(ob, out_dev, c, n, h * w, st);

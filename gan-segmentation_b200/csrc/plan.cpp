@@ -20,7 +20,7 @@ bool cuda_ok(cudaError_t e, const char* what) {
 }
 
 static const int kSmemLimit = 227 * 1024;
-static const int kHeader = 4096;
+static const int kHeader = kConvHeaderBytes;
 static const int kSlack = 8192;     // garbage-tolerant over-read of the last (partial) MMA tile
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -80,9 +80,9 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
       const int c = cbs[ci];
       if (c > cbt || cb0 % c || (cb1 && cb1 % c)) continue;
       const int n_k = cbt / c;
-      const long a_st = (long)NB * BH * BW * 16 * c;
+      const long a_st = ((long)NB * BH * BW * 16 * c + 127) / 128 * 128;   // TMA smem destinations are 128-B aligned
       const long b_st = (long)n_slots * (c / 2) * N_tile * 32;
-      if (a_st / c >= (1 << 18)) continue;                 // LBO field is 14 bits of 16-byte units
+      if ((long)NB * BH * BW * 16 >= (1 << 18)) continue;                 // LBO field is 14 bits of 16-byte units
       const int s_hi = (ov && ov->stages > 0) ? ov->stages : std::min(n_k, thin ? 2 : 4);
       const int s_lo = (ov && ov->stages > 0) ? ov->stages : std::min(n_k, 2);
       for (int s = s_hi; s >= s_lo && s >= 1; --s) {
@@ -104,9 +104,10 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   g.n_mtiles = ceil_div(((NB - 1) * g.BH + TH - 1) * BW + TW, 128);
   g.cb_stride_bytes = NB * g.BH * BW * 16;
   g.a_stage_bytes = g.cb_stride_bytes * CBK;
+  g.a_stage_stride = (g.a_stage_bytes + 127) / 128 * 128;
   g.b_stage_bytes = n_slots * (CBK / 2) * N_tile * 32;
   g.tmem_cols = pow2_cols(G * g.n_mtiles * N_tile);
-  g.smem_bytes = kHeader + stages * (g.a_stage_bytes + g.b_stage_bytes) + kSlack;
+  g.smem_bytes = kHeader + stages * (g.a_stage_stride + g.b_stage_bytes) + kSlack;
   if (g.tmem_cols > 512) { set_error("plan_conv: TMEM budget exceeded"); return; }
 
   for (int ph = 0; ph < 4; ++ph)
@@ -149,13 +150,13 @@ static void up3_taps(int p, int a, int* k, int* nk) {
   else        { if (a == 0) { k[0] = 0; k[1] = 1; *nk = 2; } else { k[0] = 2; *nk = 1; } }
 }
 
-void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<bf16>& out) {
+void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& out) {
   const ConvGeom& g = L.g;
   const int cin = L.cin0 + L.cin1, cout = L.cout;
   const int nz = g.phase_grid ? 4 : 1;
   const int k16pc = g.CBK / 2;
   const size_t tile = (size_t)g.N_tile * 16;
-  out.assign((size_t)nz * g.n_ntiles * g.n_k * g.n_slots * k16pc * tile, __float2bfloat16(0.f));
+  out.assign((size_t)nz * g.n_ntiles * g.n_k * g.n_slots * k16pc * tile, to_act(0.f));
   const bool up = (L.mode == UPCONV3 || L.mode == DECONV4);
 
   auto wval = [&](int z, int slot, int co, int ci) -> float {
@@ -190,7 +191,7 @@ void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<bf16>& ou
               for (int k = 0; k < 16; ++k) {
                 const int ci = (kc * g.CBK + 2 * j) * 8 + k;
                 out[base + (size_t)(k >> 3) * (g.N_tile * 8) + (size_t)nr * 8 + (k & 7)] =
-                    __float2bfloat16(wval(z, slot, co, ci));
+                    to_act(wval(z, slot, co, ci));
               }
             }
 }

@@ -42,7 +42,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 24)) __trap();
   }
 }
 
@@ -85,8 +85,8 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]; bf16 x bf16 -> fp32, issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc]; 16-bit x 16-bit -> fp32 (kind::f16), issued by ONE thread.
+__device__ __forceinline__ void umma_f16kind(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -126,12 +126,12 @@ __device__ __forceinline__ uint64_t umma_desc_hi(uint32_t lbo_bytes, uint32_t sb
 __device__ __forceinline__ uint64_t umma_desc(uint64_t hi, uint32_t smem_addr) {
   return hi | static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
 }
-// Instruction descriptor: D=F32, A=B=BF16, both K-major, M=128, N runtime.
-__host__ __device__ inline uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
+// Instruction descriptor: D=F32, A=B=F16 (fmt 0) or BF16 (fmt 1), both K-major, N runtime.
+__host__ __device__ inline uint32_t umma_idesc_16bit(uint32_t M, uint32_t N, uint32_t fmt) {
   uint32_t d = 0;
   d |= 1u << 4;           // c_format F32
-  d |= 1u << 7;           // a_format BF16
-  d |= 1u << 10;          // b_format BF16
+  d |= fmt << 7;          // a_format
+  d |= fmt << 10;         // b_format
   d |= (N >> 3) << 17;    // n_dim
   d |= (M >> 4) << 24;    // m_dim
   return d;

@@ -17,7 +17,7 @@
 //   * accumulators live in TMEM (128 lanes x N_tile fp32 columns per 128-pixel MMA tile); one
 //     thread issues tcgen05.mma, tcgen05.commit releases smem stages / publishes the accumulators.
 //   * 4 epilogue warps read TMEM (tcgen05.ld 32x32b), fuse noise*scale + bias + leaky-ReLU
-//     (+ residual add, + InstanceNorm sum/sumsq, or + argmax) and store bf16 with 16 B per thread.
+//     (+ residual add, + InstanceNorm sum/sumsq, or + argmax) and store 16-bit activations with 16 B per thread.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
 #include "gsx_internal.h"
@@ -26,7 +26,7 @@
 namespace gsx {
 
 static constexpr int kThreads = 192;
-static constexpr int kHeaderBytes = 4096;   // barriers + tmem slot + stats scratch
+static constexpr int kHeaderBytes = kConvHeaderBytes;   // barriers + tmem slot + stats scratch
 static constexpr int kMaxStages = 8;
 
 struct __align__(16) SmemHeader {
@@ -35,15 +35,28 @@ struct __align__(16) SmemHeader {
   uint64_t accum_full;
   uint32_t tmem_base;
   uint32_t pad;
-  float stats[2 * 256];        // [channel in N_tile][sum, sumsq]
+  float stats[4][2 * 256];     // [epilogue warp][channel in N_tile][sum, sumsq] -- one slot per warp, no atomics
 };
 static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+__device__ __forceinline__ uint32_t pack_x2(float a, float b) {
+#if GSX_FP16
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  __half2 h = __floats2half2_rn(a, b);
+#else
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+#endif
   return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_x2(uint32_t w) {
+#if GSX_FP16
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+#else
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+#endif
 }
 
 __global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_constant__ ConvParams p) {
@@ -51,7 +64,7 @@ __global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_con
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
   uint8_t* a_base = smem + kHeaderBytes;
   const ConvGeom& g = p.g;
-  uint8_t* b_base = a_base + (size_t)g.stages * g.a_stage_bytes;
+  uint8_t* b_base = a_base + (size_t)g.stages * g.a_stage_stride;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -75,7 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_con
     tma_prefetch_desc(&p.tm[0]);
     if (g.kch0 < g.n_k) tma_prefetch_desc(&p.tm[1]);
   }
-  for (int i = threadIdx.x; i < 2 * 256; i += kThreads) hdr->stats[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * 2 * 256; i += kThreads) (&hdr->stats[0][0])[i] = 0.f;
   if (warp == 1) {
     tmem_alloc(&hdr->tmem_base, (uint32_t)g.tmem_cols);
     tmem_relinquish();
@@ -89,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_con
     // ================================ TMA producer =================================
     if (lane == 0) {
       const uint32_t stage_bytes = (uint32_t)(g.a_stage_bytes + g.b_stage_bytes);
-      const bf16* wsrc = p.wpack + ((size_t)(phase_z * g.n_ntiles + ntile) * g.n_k) * (size_t)(g.b_stage_bytes / 2);
+      const act_t* wsrc = p.wpack + ((size_t)(phase_z * g.n_ntiles + ntile) * g.n_k) * (size_t)(g.b_stage_bytes / 2);
       for (int kc = 0; kc < g.n_k; ++kc) {
         const int s = kc % g.stages;
         const int it = kc / g.stages;
@@ -98,14 +111,14 @@ __global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_con
         const int src = kc < g.kch0 ? 0 : 1;
         const int cb0 = (src ? kc - g.kch0 : kc) * g.CBK;
         // dim0 is in 8-byte units (2 per pixel) so that the inner box extent reaches 128 pixels
-        tma_load_4d(a_base + (size_t)s * g.a_stage_bytes, &p.tm[src], &hdr->full[s], (x0 - 1) * 2, y0 - 1, n0, cb0);
+        tma_load_4d(a_base + (size_t)s * g.a_stage_stride, &p.tm[src], &hdr->full[s], (x0 - 1) * 2, y0 - 1, n0, cb0);
         bulk_load(b_base + (size_t)s * g.b_stage_bytes, wsrc + (size_t)kc * (g.b_stage_bytes / 2),
                   (uint32_t)g.b_stage_bytes, &hdr->full[s]);
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ===================================
-    const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)g.N_tile);
+    const uint32_t idesc = umma_idesc_16bit(128, (uint32_t)g.N_tile, GSX_FP16 ? 0u : 1u);
     const uint64_t a_hi = umma_desc_hi((uint32_t)g.cb_stride_bytes, 128);
     const uint64_t b_hi = umma_desc_hi((uint32_t)g.N_tile * 16, 128);
     const int k16_per_chunk = g.CBK >> 1;
@@ -116,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_con
       mbar_wait(&hdr->full[s], (uint32_t)(it & 1));
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t a_addr = smem_u32(a_base + (size_t)s * g.a_stage_bytes);
+        const uint32_t a_addr = smem_u32(a_base + (size_t)s * g.a_stage_stride);
         const uint32_t b_addr = smem_u32(b_base + (size_t)s * g.b_stage_bytes);
         for (int slot = 0; slot < g.n_slots; ++slot) {
           const int grp = g.slot_group[slot];
@@ -127,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_con
             const uint32_t a_k = a_addr + (uint32_t)(2 * j) * (uint32_t)g.cb_stride_bytes + shift_bytes;
             for (int mt = 0; mt < g.n_mtiles; ++mt) {
               const uint64_t adesc = umma_desc(a_hi, a_k + (uint32_t)mt * 2048u);
-              umma_bf16(tmem_base + (uint32_t)((grp * g.n_mtiles + mt) * g.N_tile), adesc, bdesc, idesc, acc);
+              umma_f16kind(tmem_base + (uint32_t)((grp * g.n_mtiles + mt) * g.N_tile), adesc, bdesc, idesc, acc);
             }
           }
         }
@@ -224,9 +237,9 @@ __global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_con
                   const uint32_t w4[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[k]);
-                    f[h * 8 + 2 * k] += __bfloat162float(b2.x);
-                    f[h * 8 + 2 * k + 1] += __bfloat162float(b2.y);
+                    const float2 b2 = unpack_x2(w4[k]);
+                    f[h * 8 + 2 * k] += b2.x;
+                    f[h * 8 + 2 * k + 1] += b2.y;
                   }
                 }
               }
@@ -238,10 +251,10 @@ __global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_con
               for (int h = 0; h < 2; ++h) {
                 if (c0 + h * 8 < e.Cout) {
                   uint4 o;
-                  o.x = pack_bf16x2(f[h * 8 + 0], f[h * 8 + 1]);
-                  o.y = pack_bf16x2(f[h * 8 + 2], f[h * 8 + 3]);
-                  o.z = pack_bf16x2(f[h * 8 + 4], f[h * 8 + 5]);
-                  o.w = pack_bf16x2(f[h * 8 + 6], f[h * 8 + 7]);
+                  o.x = pack_x2(f[h * 8 + 0], f[h * 8 + 1]);
+                  o.y = pack_x2(f[h * 8 + 2], f[h * 8 + 3]);
+                  o.z = pack_x2(f[h * 8 + 4], f[h * 8 + 5]);
+                  o.w = pack_x2(f[h * 8 + 6], f[h * 8 + 7]);
                   *reinterpret_cast<uint4*>(e.out + (((size_t)((c0 >> 3) + h) * g.N + n) * plane_out + pix) * 8) = o;
                 }
               }
@@ -268,16 +281,19 @@ __global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_con
           // lane's bits (16,8,4,2,1) selected halves successively -> value index = lane
           const int vi = lane;                                 // 0..15 sums, 16..31 sumsq
           const int ch = cc * 16 + (vi & 15);
-          atomicAdd(&hdr->stats[ch * 2 + (vi >> 4)], vals[0]);
+          hdr->stats[warp - 2][ch * 2 + (vi >> 4)] += vals[0];     // this warp's own slot: plain add
         }
       }
       if (do_stats) {
         named_bar_sync(1, 128);                                // the 4 epilogue warps
         const int tid = threadIdx.x - 64;
-        // fused stats need a single sample per CTA (NB == 1); enforced by the planner
+        // fused stats need a single sample per CTA (NB == 1); enforced by the callers.  Fixed summation
+        // order + one partial per (sample, tile): bit-reproducible, finalize_kernel adds the tiles up.
+        const int tile_in_sample = ty * g.tiles_x + tx;
         for (int i = tid; i < g.N_tile * 2; i += 128) {
           const int ch = ntile * g.N_tile + (i >> 1);
-          if (ch < e.Cout) atomicAdd(e.stats + ((size_t)n0 * e.Cout + ch) * 2 + (i & 1), hdr->stats[i]);
+          const float s = (hdr->stats[0][i] + hdr->stats[1][i]) + (hdr->stats[2][i] + hdr->stats[3][i]);
+          if (ch < e.Cout) e.stats[(((size_t)n0 * e.stats_T + tile_in_sample) * e.Cout + ch) * 2 + (i & 1)] = s;
         }
       }
     }

@@ -18,10 +18,10 @@ def _stream():
 
 
 def conv(mode, x0, weight, x1=None, bias=None, nscale=None, noise=None, flags=0, addsrc=None,
-         num_classes=0, override=None, repeat=0):
+         num_classes=0, override=None, repeat=0, dtype=None):
     """Run one shift-GEMM convolution.  x0/x1: [N,C,H,W] fp32 cuda; weight: fp32 (numpy or cpu tensor) in
     the reference layout of the mode.  Returns dict(out, stats, mask, logits, plan, ms)."""
-    lib = L.lib()
+    lib = L.lib(dtype)
     n, cin0, h, w = x0.shape
     cin1 = 0 if x1 is None else x1.shape[1]
     wnp = np.ascontiguousarray(np.asarray(weight, np.float32))
@@ -49,23 +49,23 @@ def conv(mode, x0, weight, x1=None, bias=None, nscale=None, noise=None, flags=0,
     rc = lib.gsx_op_conv(mode, n, h, w, cin0, cin1, cout, L.ptr(x0), L.ptr(x1), L.np_ptr(wnp), L.ptr(bias),
                          L.ptr(nscale), L.ptr(noise), flags, L.ptr(addsrc), L.ptr(out), L.ptr(stats), L.ptr(mask),
                          L.ptr(logits), num_classes, C.byref(ov) if ov else None, plan, repeat, C.byref(ms), _stream())
-    L.check(rc, 'gsx_op_conv')
+    L.check(rc, 'gsx_op_conv', dtype)
     return dict(out=out, stats=stats, mask=mask, logits=logits, plan=dict(zip(PLAN_FIELDS, list(plan))), ms=ms.value)
 
 
-def pass1(x, n, blur, nscale, bias, noise, in_broadcast=False, want_stats=True):
-    lib = L.lib()
+def pass1(x, n, blur, nscale, bias, noise, in_broadcast=False, want_stats=True, dtype=None):
+    lib = L.lib(dtype)
     _, c, h, w = x.shape
     out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
     stats = torch.zeros((n, c, 2), dtype=torch.float32, device=x.device) if want_stats else None
     rc = lib.gsx_op_pass1(n, c, h, w, L.ptr(x.contiguous()), int(blur), int(in_broadcast), L.ptr(nscale), L.ptr(bias),
                           L.ptr(noise), L.ptr(out), L.ptr(stats), _stream())
-    L.check(rc, 'gsx_op_pass1')
+    L.check(rc, 'gsx_op_pass1', dtype)
     return out, stats
 
 
-def apply(x, stats, styles, wrgb=None, brgb=None):
-    lib = L.lib()
+def apply(x, stats, styles, wrgb=None, brgb=None, dtype=None):
+    lib = L.lib(dtype)
     n, c, h, w = x.shape
     out = torch.empty_like(x)
     nc = 0 if wrgb is None else wrgb.shape[0]
@@ -73,7 +73,7 @@ def apply(x, stats, styles, wrgb=None, brgb=None):
     u8 = torch.empty((n, h, w, nc), dtype=torch.uint8, device=x.device) if nc else None
     rc = lib.gsx_op_apply(n, c, h, w, L.ptr(x.contiguous()), L.ptr(stats), L.ptr(styles), L.ptr(wrgb), L.ptr(brgb), nc,
                           L.ptr(out), L.ptr(img), L.ptr(u8), _stream())
-    L.check(rc, 'gsx_op_apply')
+    L.check(rc, 'gsx_op_apply', dtype)
     return out, img, u8
 
 

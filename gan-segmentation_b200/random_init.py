@@ -46,6 +46,8 @@ def init_generator_params(cfg, seed=0, mode='nondegenerate', psi=None):
       StyleGAN's 1/lrmul init, so the effective mapping weight is He-scaled N(0,1));
       mapping bias ~ N(0,10^2) (effective N(0,0.1^2) after lr_mult);  affine bias, Bias layers,
       to_rgb bias ~ N(0,0.1^2);  noise scale_factors ~ N(0,0.2^2);  latent_avg ~ N(0,0.1^2);
+      to_rgb weight ~ N(0,0.3^2) so the image fills the [-1,1] range like a trained generator's output
+      (std ~0.5) instead of saturating;
       constant_tensor ~ N(0,1);  truncation_psi = 0.7 on the first 8 layers and 1.0 after
       (truncation_cutoff=8 convention) unless ``psi`` is given.
     """
@@ -78,6 +80,8 @@ def init_generator_params(cfg, seed=0, mode='nondegenerate', psi=None):
             w = rng.randn(*shape).astype(np.float32)
             if name.startswith('mapping.') and mode == 'nondegenerate':
                 w = w * 100.0
+            if name.startswith('to_rgb') and mode == 'nondegenerate':
+                w = w * 0.3
             out[name] = w
         elif name.endswith('scale_factors'):
             out[name] = (0.2 * rng.randn(*shape)).astype(np.float32) if mode == 'nondegenerate' \

@@ -1,0 +1,133 @@
+"""Drop-in mirror of the predict half of the reference's SegSolver (seg_solver.py:16-132, 307-349)."""
+from __future__ import annotations
+
+import os
+from os.path import join
+
+import numpy as np
+import torch
+
+from .config import decoder_config
+from .networks import Decoder
+from .random_init import init_decoder_params
+
+
+def list_params_files(base_dir):
+    """utils.list_files_with_ext(dir, ['.params']) (utils.py:18-37): sorted os.walk order."""
+    out = []
+    if not os.path.isdir(base_dir):
+        return out
+    for root, _, fnames in sorted(os.walk(base_dir)):
+        rel = os.path.relpath(root, base_dir)
+        for fn in fnames:
+            if os.path.splitext(fn.lower())[1] == '.params' and os.path.isfile(join(root, fn)):
+                out.append(fn if rel == '.' else join(rel, fn))
+    return out
+
+
+class SegSolver:
+    """``SegSolver(max_res_log2, path_to_data, checkpoints_dir, gpu_ids, keep_weights)`` (seg_solver.py:17).
+
+    The generate path needs ``predict`` / ``load`` / ``save`` and the attributes callers read
+    (``is_trained``, ``net``, ``cfg``, ``ctx``, ``params_file``).  ``fit`` / ``evaluate`` (decoder training,
+    seg_solver.py:222-305, 351-465) are outside this round's scope and raise NotImplementedError.
+    """
+
+    def __init__(self, max_res_log2, path_to_data, checkpoints_dir, gpu_ids, keep_weights=True, *, base_hw=(4, 4),
+                 verbose=True):
+        self.path_to_data = path_to_data
+        self.checkpoints_dir = checkpoints_dir
+        self.keep_weights = keep_weights
+        if len(gpu_ids) == 0:
+            raise RuntimeError('SegSolver needs at least one GPU id: the B200 path has no CPU fallback')
+        self.ctx = [torch.device('cuda', i) for i in gpu_ids]
+        self.is_trained = False
+        self.params_file = None
+        self.base_hw = base_hw
+        self.verbose = verbose
+        self.cfg = self.get_config(max_res_log2=max_res_log2)
+        self.net = self.init_net()
+        self.is_trained = self.load()
+
+    def get_config(self, max_res_log2=9):
+        return decoder_config(max_res_log2)
+
+    def init_net(self):
+        """Decoder + Xavier('in', 2.34) init, fresh BatchNorm statistics (seg_solver.py:36-49)."""
+        params = init_decoder_params(self.cfg, seed=self.cfg['seed'], mode='reference')
+        self.nets = [Decoder(self.cfg, num_devices=len(self.ctx), base_hw=self.base_hw, device=d) for d in self.ctx]
+        for net in self.nets:
+            net.set_parameters(params)
+        if self.verbose:
+            self.print_params(params, 'decoder')
+        return self.nets[0]
+
+    def print_params(self, params, title):
+        """Same table as seg_solver.py:60-81."""
+        row = '{:<36}{:<16}{:<24}{:<16}'
+        print(row.format(title, 'params', 'weight shape', 'dtype'))
+        print(row.format('---', '---', '---', '---'))
+        total = 0
+        for name, p in params.items():
+            n = int(np.prod(p.shape))
+            total += n
+            print(row.format(name, n, str(tuple(p.shape)), 'np.float32'))
+        print(row.format('---', '---', '---', '---'))
+        print('{:<36}{:<16}'.format('total', total))
+        print('{:<36}{:<16}'.format('---', '---'))
+
+    def set_parameters(self, params):
+        for net in self.nets:
+            net.set_parameters(params)
+
+    def predict(self, features=None, *, generator=None, device_outputs=False):
+        """seg_solver.py:307-329: list of [C,H,W] / [N,C,H,W] features -> float32 [N,H,W,1] class ids.
+        ``generator=`` takes the features the given Generator's last forward left in HBM instead."""
+        if features is None:
+            out = self.net.forward(None, generator=generator, return_logits=False)
+            mask = out['mask']
+        else:
+            feats = []
+            for f in features:
+                t = torch.as_tensor(f, dtype=torch.float32)
+                if t.dim() == 3:
+                    t = t.unsqueeze(0)
+                feats.append(t)
+            n = feats[0].shape[0]
+            k = len(self.nets)
+            if n % k and k > 1:
+                raise ValueError('batch must divide the number of devices (split_and_load even_split, :317)')
+            per = n // k if k > 1 else n
+            masks = []
+            for i, net in enumerate(self.nets):
+                sl = slice(i * per, (i + 1) * per)
+                masks.append(net.forward([f[sl] for f in feats], return_logits=False)['mask'])
+            for d in self.ctx:
+                torch.cuda.synchronize(d)
+            mask = torch.cat([m.to(self.ctx[0]) for m in masks], 0)
+        if device_outputs:
+            return mask
+        return mask.cpu().numpy().astype(np.float32)[:, :, :, None]
+
+    def save(self, suffix=None):
+        param_name = 'checkpoint_last.params' if suffix is None else f'checkpoint_{suffix}.params'
+        self.params_file = param_name
+        os.makedirs(self.checkpoints_dir, exist_ok=True)
+        self.net.save_parameters(join(self.checkpoints_dir, param_name))
+
+    def load(self):
+        files = list_params_files(self.checkpoints_dir)
+        if len(files) > 0:
+            params_file = files[0]
+            print(f'loading checkpoint: {params_file}')
+            self.params_file = params_file
+            from .params_io import load_params
+            self.set_parameters(load_params(join(self.checkpoints_dir, params_file)))
+            return True
+        return False
+
+    def fit(self, epoch_end_callback=None):
+        raise NotImplementedError('decoder training (seg_solver.py:351-465) is not part of the generate hot path yet')
+
+    def evaluate(self, input_dir, output_dir=None):
+        raise NotImplementedError('evaluation (seg_solver.py:222-305) is not part of the generate hot path yet')

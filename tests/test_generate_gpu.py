@@ -1,0 +1,125 @@
+"""Whole-path parity on the GPU: C-ABI generator + decoder against the CPU oracle on identical latents,
+noise and random-init weights (BASELINE.json configs 1 and 3 at test size)."""
+import numpy as np
+import pytest
+import torch
+
+from parity_util import make_case, psnr, rel_rms, first_max_argmax, IMG_PSNR_DB, TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(max_res_log2, n, base=(4, 4), seed=0, psi=None, dtype='fp16'):
+    from gan_segmentation_b200.networks import Generator, Decoder
+    from oracle import generate_oracle as O
+    gc, dc, gp, dp, z, noise = make_case(max_res_log2, n, base, seed)
+    ref = O.generate(gp, gc, dp, dc, z, noise, psi=psi)
+    G = Generator(gc, dtype=dtype)
+    G.set_parameters(gp)
+    D = Decoder(dc, base_hw=base, dtype=dtype)
+    D.set_parameters(dp)
+    out = G.forward(z, psi=psi, noise=noise, return_u8=True)
+    dec = D.forward(generator=G)
+    torch.cuda.synchronize()
+    return ref, out, dec, (G, D, gc, dc, gp, dp, z, noise)
+
+
+def check(ref, out, dec, label, dtype='fp16'):
+    tol = TOL[dtype]
+    img = out['img'].cpu().numpy()
+    a = np.clip(img, -1, 1)
+    b = np.clip(ref['img_f32'], -1, 1)
+    maxabs = float(np.abs(a - b).max())
+    p = psnr(a, b)
+    errs = [rel_rms(f.cpu().numpy(), r) for f, r in zip(out['features'], ref['features'])]
+    lg = dec['logits'].cpu().numpy()
+    mask = dec['mask'].cpu().numpy()
+    agree = float((mask == ref['mask'][..., 0].astype(np.uint8)).mean())
+    du8 = np.abs(out['img_u8'].cpu().numpy().astype(np.int32) - ref['img_u8'].astype(np.int32))
+    print(f'\n[{label}] img max-abs {maxabs:.4f} psnr {p:.1f} dB | feature rel-rms {["%.4f" % e for e in errs]} | '
+          f'logits rel-rms {rel_rms(lg, ref["logits"]):.4f} | mask agreement {agree:.5f} | u8 max diff {du8.max()}')
+    assert np.isfinite(img).all()
+    assert max(errs) < tol['feat'], errs
+    assert p >= tol['psnr'], p
+    assert maxabs <= tol['max_abs'], maxabs
+    assert agree >= tol['mask'], agree
+    # argmax is bit-exact given identical logits (first-max tie rule)
+    assert np.array_equal(mask, first_max_argmax(lg))
+    assert du8.max() <= tol['u8']
+
+
+def test_config1_bedrooms_256_batch1(dtype):
+    """BASELINE config 1: StyleGAN-bedrooms 256^2 generator + decoder, batch 1, psi from the parameters."""
+    ref, out, dec, _ = run_both(8, 1, dtype=dtype)
+    check(ref, out, dec, f'bedrooms256 n=1 {dtype}', dtype)
+
+
+def test_bedrooms_256_batch3_psi07(dtype):
+    ref, out, dec, _ = run_both(8, 3, seed=3, psi=0.7, dtype=dtype)
+    check(ref, out, dec, f'bedrooms256 n=3 psi=.7 {dtype}', dtype)
+
+
+def test_nonsquare_base_3x4(dtype):
+    """BASELINE config 3's non-square synthesis path (base 3x4) at max_res_log2=7 -> 96x128."""
+    ref, out, dec, _ = run_both(7, 2, base=(3, 4), seed=5, dtype=dtype)
+    check(ref, out, dec, f'base3x4 res7 n=2 {dtype}', dtype)
+
+
+def test_run_to_run_bit_reproducible():
+    """No float atomics anywhere on the path: two runs on the same inputs are bit-identical."""
+    ref, out, dec, (G, D, gc, dc, gp, dp, z, noise) = run_both(6, 3, seed=9)
+    a_img, a_mask = out['img'].clone(), dec['mask'].clone()
+    out2 = G.forward(z, noise=noise)
+    dec2 = D.forward(generator=G)
+    torch.cuda.synchronize()
+    assert torch.equal(out2['img'], a_img) and torch.equal(dec2['mask'], a_mask)
+
+
+def test_decoder_from_host_features_matches_device_path():
+    """Drop-in predict(): fp32 NCHW features in (the reference's interface) == device-resident path."""
+    ref, out, dec, (G, D, *_rest) = run_both(6, 2, seed=7)
+    dec2 = D.forward([f.cpu().numpy() for f in out['features']])
+    torch.cuda.synchronize()
+    # features handed over in fp32 are the bf16 values the device path used, so the result is identical
+    assert torch.equal(dec2['mask'], dec['mask'])
+    assert torch.equal(dec2['logits'], dec['logits'])
+
+
+def test_device_rng_path_matches_oracle_on_exported_noise():
+    """Philox noise / latents generated on the device: export them and replay through the oracle."""
+    from gan_segmentation_b200.networks import Generator
+    from oracle import generate_oracle as O
+    gc, dc, gp, dp, _, _ = make_case(6, 2, seed=11)
+    G = Generator(gc)
+    G.set_parameters(gp)
+    out = G.forward(None, n=2, seed=1234, first_sample=40)
+    z = G.export_latents(2).cpu().numpy()
+    noise = [p.cpu().numpy() for p in G.export_noise(2)]
+    out_b = G.forward(None, n=1, seed=1234, first_sample=41)        # sample 41 alone == row 1 of the pair
+    torch.cuda.synchronize()
+    assert torch.equal(out_b['img'][0], out['img'][1])
+    with torch.no_grad():
+        img, _ = O.generator_forward(gp, gc, z, noise)
+    a, b = np.clip(out['img'].cpu().numpy(), -1, 1), np.clip(img.numpy(), -1, 1)
+    assert psnr(a, b) >= IMG_PSNR_DB
+    assert abs(z.mean()) < 0.1 and abs(z.std() - 1) < 0.1
+
+
+def test_scope_kats_on_device():
+    """Reference invariants checked on the CUDA path: zero noise scale => output independent
+    of noise; psi=0 => output independent of z."""
+    from gan_segmentation_b200.networks import Generator
+    gc, dc, gp, dp, z, noise = make_case(5, 2, seed=13)
+    gp0 = dict(gp)
+    for k in gp0:
+        if k.endswith('scale_factors'):
+            gp0[k] = np.zeros_like(gp0[k])
+    G = Generator(gc)
+    G.set_parameters(gp0)
+    a = G.forward(z, noise=noise)['img'].clone()
+    b = G.forward(z, noise=[2 * p + 1 for p in noise])['img'].clone()
+    assert torch.equal(a, b)
+    G.set_parameters(gp)
+    c = G.forward(z, noise=noise, psi=0.0)['img'].clone()
+    d = G.forward(z[::-1].copy(), noise=noise, psi=0.0)['img'].clone()
+    assert torch.equal(c, d)

@@ -8,11 +8,24 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
+_DT = 'fp16'     # set per test from the ``dtype`` fixture
+
+
+def use(dtype):
+    global _DT
+    _DT = dtype
+
+
 def bf(x):
-    return x.to(torch.bfloat16).to(torch.float32)
+    """Round to the 16-bit storage type of the library under test."""
+    return x.to(torch.bfloat16 if _DT == 'bf16' else torch.float16).to(torch.float32)
 
 
-def close(out, ref, what, rel=2.0 ** -7, abs_frac=2e-3):
+def close(out, ref, what, rel=None, abs_frac=None):
+    if rel is None:
+        rel = 2.0 ** -7 if _DT == 'bf16' else 2.0 ** -10
+    if abs_frac is None:
+        abs_frac = 2e-3 if _DT == 'bf16' else 3e-4
     scale = ref.abs().max().item() + 1e-6
     err = (out - ref).abs()
     tol = rel * ref.abs() + abs_frac * scale
@@ -64,7 +77,8 @@ CASES = [
 
 
 @pytest.mark.parametrize('case', CASES, ids=lambda c: '-'.join(map(str, c)))
-def test_conv_raw(gsx_lib, case):
+def test_conv_raw(gsx_lib, dtype, case):
+    use(dtype)
     from gan_segmentation_b200 import _lib as L, ops
     mname, n, cin0, cin1, cout, h, w = case
     mode = getattr(L, mname)
@@ -73,13 +87,14 @@ def test_conv_raw(gsx_lib, case):
     x = bf(torch.randn((n, cin, h, w), generator=g))
     wt = make_w(mode, cin, cout, g)
     xd = x.cuda()
-    r = ops.conv(mode, xd[:, :cin0], wt.numpy(), x1=xd[:, cin0:] if cin1 else None)
+    r = ops.conv(mode, xd[:, :cin0], wt.numpy(), x1=xd[:, cin0:] if cin1 else None, dtype=dtype)
     ref = ref_conv(mode, xd, wt.cuda())
     close(r['out'], ref, f'{case} plan={r["plan"]}')
 
 
-def test_conv_generator_epilogue(gsx_lib):
+def test_conv_generator_epilogue(gsx_lib, dtype):
     """conv_2 epilogue of a synthesis block: + scale*noise + bias, LeakyReLU(0.2), InstanceNorm sums."""
+    use(dtype)
     from gan_segmentation_b200 import _lib as L, ops
     g = torch.Generator().manual_seed(5)
     for (n, c, h, w) in [(2, 32, 64, 64), (2, 512, 8, 8), (1, 128, 32, 32), (4, 512, 4, 4)]:
@@ -88,18 +103,22 @@ def test_conv_generator_epilogue(gsx_lib):
         ns = torch.randn(c, generator=g).cuda() * 0.3
         b = torch.randn(c, generator=g).cuda() * 0.2
         nz = torch.randn((n, 1, h, w), generator=g).cuda()
-        r = ops.conv(L.CONV3, x, wt.numpy(), bias=b, nscale=ns, noise=nz, flags=L.EPI_LRELU | L.EPI_STATS)
+        r = ops.conv(L.CONV3, x, wt.numpy(), bias=b, nscale=ns, noise=nz, flags=L.EPI_LRELU | L.EPI_STATS, dtype=dtype)
         v = F.conv2d(x, wt.cuda(), None, 1, 1) + ns.view(1, -1, 1, 1) * nz + b.view(1, -1, 1, 1)
         v = F.leaky_relu(v, 0.2)
         close(r['out'], v, f'epilogue {n, c, h, w}')
         s1 = v.sum(dim=(2, 3))
         s2 = (v * v).sum(dim=(2, 3))
-        assert torch.allclose(r['stats'][:, :, 0], s1, rtol=2e-3, atol=2e-3 * s2.sqrt().max().item()), r['plan']
-        assert torch.allclose(r['stats'][:, :, 1], s2, rtol=2e-3), r['plan']
+        # multi-sample tiles (tiny images) take the statistics from the bf16-rounded output instead of the
+        # fp32 accumulators, hence the looser bound there
+        rt = 2e-3 if r['plan']['NB'] == 1 else 8e-3
+        assert torch.allclose(r['stats'][:, :, 0], s1, rtol=rt, atol=rt * s2.sqrt().max().item()), r['plan']
+        assert torch.allclose(r['stats'][:, :, 1], s2, rtol=rt), r['plan']
 
 
-def test_conv_decoder_residual(gsx_lib):
+def test_conv_decoder_residual(gsx_lib, dtype):
     """conv_b of a DecoderResBlock: bias, LeakyReLU, + nearest-upsampled shortcut (networks_seg.py:44-46)."""
+    use(dtype)
     from gan_segmentation_b200 import _lib as L, ops
     g = torch.Generator().manual_seed(6)
     n, c, h, w = 2, 32, 32, 48
@@ -107,14 +126,15 @@ def test_conv_decoder_residual(gsx_lib):
     sc = bf(torch.randn((n, c, h // 2, w // 2), generator=g)).cuda()
     wt = make_w(L.CONV3, c, c, g)
     b = torch.randn(c, generator=g).cuda() * 0.2
-    r = ops.conv(L.CONV3, x, wt.numpy(), bias=b, flags=L.EPI_LRELU, addsrc=sc)
+    r = ops.conv(L.CONV3, x, wt.numpy(), bias=b, flags=L.EPI_LRELU, addsrc=sc, dtype=dtype)
     ref = F.leaky_relu(F.conv2d(x, wt.cuda(), b, 1, 1), 0.2) + F.interpolate(sc, scale_factor=2, mode='nearest')
     close(r['out'], ref, 'residual')
 
 
-def test_conv_argmax(gsx_lib):
+def test_conv_argmax(gsx_lib, dtype):
     """Final decoder conv + argmax: the mask must equal the first-max argmax of the logits the kernel
     itself produced (bit-exact), and the logits must match the fp32 reference."""
+    use(dtype)
     from gan_segmentation_b200 import _lib as L, ops
     g = torch.Generator().manual_seed(7)
     for nc in (2, 5):
@@ -124,7 +144,7 @@ def test_conv_argmax(gsx_lib):
         b = torch.randn(nc, generator=g) * 0.1
         b16 = torch.zeros(16)
         b16[:nc] = b
-        r = ops.conv(L.CONV3, x[:, :c0], wt.numpy(), x1=x[:, c0:], bias=b16.cuda(), flags=L.EPI_ARGMAX, num_classes=nc)
+        r = ops.conv(L.CONV3, x[:, :c0], wt.numpy(), x1=x[:, c0:], bias=b16.cuda(), flags=L.EPI_ARGMAX, num_classes=nc, dtype=dtype)
         ref = F.conv2d(x, wt.cuda(), b.cuda(), 1, 1)
         close(r['logits'], ref, 'logits', rel=1e-4, abs_frac=1e-4)
         lg = r['logits'].cpu().numpy()
@@ -137,17 +157,19 @@ def test_conv_argmax(gsx_lib):
         assert np.array_equal(r['mask'].cpu().numpy(), idx)
 
 
-def test_argmax_ties_first_max(gsx_lib):
+def test_argmax_ties_first_max(gsx_lib, dtype):
     """All-zero weights + equal biases: every logit ties, class 0 must win (seg_solver.py:326)."""
+    use(dtype)
     from gan_segmentation_b200 import _lib as L, ops
     x = torch.randn((1, 32, 16, 16)).cuda()
     wt = np.zeros((3, 32, 3, 3), np.float32)
     b16 = torch.zeros(16).cuda()
-    r = ops.conv(L.CONV3, x[:, :16], wt, x1=x[:, 16:], bias=b16, flags=L.EPI_ARGMAX, num_classes=3)
+    r = ops.conv(L.CONV3, x[:, :16], wt, x1=x[:, 16:], bias=b16, flags=L.EPI_ARGMAX, num_classes=3, dtype=dtype)
     assert int(r['mask'].max()) == 0
 
 
-def test_pass1_and_apply(gsx_lib):
+def test_pass1_and_apply(gsx_lib, dtype):
+    use(dtype)
     from gan_segmentation_b200 import ops
     g = torch.Generator().manual_seed(8)
     for (n, c, h, w, blur) in [(2, 16, 64, 64, True), (3, 64, 12, 16, True), (2, 512, 4, 4, False), (1, 32, 96, 128, True)]:
@@ -155,7 +177,7 @@ def test_pass1_and_apply(gsx_lib):
         ns = torch.randn(c, generator=g).cuda() * 0.3
         b = torch.randn(c, generator=g).cuda() * 0.2
         nz = torch.randn((n, 1, h, w), generator=g).cuda()
-        out, stats = ops.pass1(x, n, blur, ns, b, nz)
+        out, stats = ops.pass1(x, n, blur, ns, b, nz, dtype=dtype)
         v = x
         if blur:
             k = torch.tensor([1., 2., 1.])
@@ -169,12 +191,13 @@ def test_pass1_and_apply(gsx_lib):
         t = bf(v)
         st = torch.stack([t.sum(dim=(2, 3)), (t * t).sum(dim=(2, 3))], dim=2).contiguous()
         sty = torch.randn((n, 2 * c), generator=g).cuda()
-        o2, _, _ = ops.apply(t, st, sty)
+        o2, _, _ = ops.apply(t, st, sty, dtype=dtype)
         ref = F.instance_norm(t, eps=1e-5) * (sty[:, :c].view(n, c, 1, 1) + 1) + sty[:, c:].view(n, c, 1, 1)
         close(o2, ref, f'apply {n, c, h, w}', rel=2.0 ** -7, abs_frac=4e-3)
 
 
-def test_pass1_broadcast_const(gsx_lib):
+def test_pass1_broadcast_const(gsx_lib, dtype):
+    use(dtype)
     from gan_segmentation_b200 import ops
     g = torch.Generator().manual_seed(9)
     n, c, h, w = 3, 512, 4, 4
@@ -182,14 +205,15 @@ def test_pass1_broadcast_const(gsx_lib):
     ns = torch.randn(c, generator=g).cuda() * 0.3
     b = torch.randn(c, generator=g).cuda() * 0.2
     nz = torch.randn((n, 1, h, w), generator=g).cuda()
-    out, _ = ops.pass1(x, n, False, ns, b, nz, in_broadcast=True)
+    out, _ = ops.pass1(x, n, False, ns, b, nz, in_broadcast=True, dtype=dtype)
     v = F.leaky_relu(x + ns.view(1, -1, 1, 1) * nz + b.view(1, -1, 1, 1), 0.2)
     close(out, v, 'pass1 broadcast')
 
 
-def test_apply_rgb_u8(gsx_lib):
+def test_apply_rgb_u8(gsx_lib, dtype):
     """ToRGB + uint8 transform fused in the last apply pass; uint8 must equal the reference transform
     (image_generator.py:76-84) of the fp32 image the same kernel wrote (bit-exact)."""
+    use(dtype)
     from gan_segmentation_b200 import ops
     g = torch.Generator().manual_seed(10)
     n, c, h, w = 2, 16, 64, 64
@@ -198,7 +222,7 @@ def test_apply_rgb_u8(gsx_lib):
     sty = torch.randn((n, 2 * c), generator=g).cuda() * 0.5
     wr = (torch.randn((3, c), generator=g) / 4).cuda()
     br = (torch.randn(3, generator=g) * 0.1).cuda()
-    o, img, u8 = ops.apply(t, st, sty, wr, br)
+    o, img, u8 = ops.apply(t, st, sty, wr, br, dtype=dtype)
     ref = F.instance_norm(t, eps=1e-5) * (sty[:, :c].view(n, c, 1, 1) + 1) + sty[:, c:].view(n, c, 1, 1)
     close(o, ref, 'apply rgb feature', abs_frac=4e-3)
     ref_img = F.conv2d(ref, wr.view(3, c, 1, 1), br)
@@ -209,7 +233,8 @@ def test_apply_rgb_u8(gsx_lib):
     assert np.array_equal(u8.cpu().numpy(), a)
 
 
-def test_philox_normal(gsx_lib):
+def test_philox_normal(gsx_lib, dtype):
+    use(dtype)
     from gan_segmentation_b200 import ops
     a = ops.fill_normal(1 << 16, 4, 123, 10, 3)
     b = ops.fill_normal(1 << 16, 2, 123, 12, 3)       # samples 12,13 == rows 2,3 of a: split-invariant
