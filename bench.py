@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the generate hot path: image+mask samples/sec, StyleGAN-FFHQ 1024^2 generator + decoder.
+
+  python bench.py --gpus N --steps K --warmup W             (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                      (CPU baseline arm: the oracle on host cores)
+
+One step = one batch of 32 latents per GPU -> uint8 image [1024,1024,3] + uint8 mask [1024,1024] per
+latent (BASELINE.json configs[1]).  Latents are index-sharded over the ranks, no collective on the
+data path (weak scaling).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'image+mask samples/sec'
+UNIT = 'samples/s'
+WORKLOADS = {
+    'ffhq1024': dict(gan='ffhq', max_res_log2=10, base=(4, 4), batch=32, psi=0.7,
+                     name='StyleGAN-FFHQ 1024^2 generator + hair decoder forward, batch 32/GPU, psi=0.7 (BASELINE configs[1])'),
+    'cars512x384': dict(gan='cars', max_res_log2=9, base=(3, 4), batch=64, psi=0.7,
+                        name='StyleGAN-cars 512x384 generator + decoder forward, batch 64/GPU (BASELINE configs[2])'),
+    'bedrooms256': dict(gan='bedrooms', max_res_log2=8, base=(4, 4), batch=1, psi=1.0,
+                        name='StyleGAN-bedrooms 256^2 generator + decoder forward, batch 1 (BASELINE configs[0])'),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d['hbm_gbs']), tensor=float(d.get('bf16_tflops_sustained', d['bf16_tflops'])), src='measured')
+    return dict(hbm=6650.0, tensor=1400.0, src='fallback')      # B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '50', '-i', str(gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.06)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def build_models(wl, dtype, device):
+    import gan_segmentation_b200  # noqa: F401
+    from gan_segmentation_b200.config import generator_config, decoder_config
+    from gan_segmentation_b200.random_init import init_generator_params, init_decoder_params
+    from gan_segmentation_b200.networks import Generator, Decoder
+    gc = generator_config(wl['max_res_log2'], *wl['base'])
+    dc = decoder_config(wl['max_res_log2'])
+    gp = init_generator_params(gc, seed=0)
+    dp = init_decoder_params(dc, seed=2)
+    G = Generator(gc, device=device, dtype=dtype)
+    G.set_parameters(gp)
+    D = Decoder(dc, base_hw=wl['base'], device=device, dtype=dtype)
+    D.set_parameters(dp)
+    return gc, dc, gp, dp, G, D
+
+
+def cpu_oracle_rate(wl, n_samples, warm=1):
+    """The oracle (PyTorch-CPU restatement of the reference; MXNet itself is not installable offline) on the
+    host cores: image+mask samples/s at batch 1 (main.py:97-99 decodes one sample at a time)."""
+    import numpy as np
+    import torch
+    from gan_segmentation_b200.config import generator_config, decoder_config, noise_shapes
+    from gan_segmentation_b200.random_init import init_generator_params, init_decoder_params
+    from oracle import generate_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gc = generator_config(wl['max_res_log2'], *wl['base'])
+    dc = decoder_config(wl['max_res_log2'])
+    gp = init_generator_params(gc, seed=0)
+    dp = init_decoder_params(dc, seed=2)
+    rs = np.random.RandomState(0)
+    times = []
+    for i in range(warm + n_samples):
+        z = rs.randn(1, 512).astype(np.float32)
+        noise = [rs.randn(*s).astype(np.float32) for s in noise_shapes(gc, 1)]
+        t0 = time.perf_counter()
+        O.generate(gp, gc, dp, dc, z, noise, psi=wl['psi'])
+        t = time.perf_counter() - t0
+        if i >= warm:
+            times.append(t)
+    return dict(value=1.0 / statistics.median(times), unit=UNIT, cores=cores, kind='port',
+                sample=f'{n_samples} latents at batch 1 after {warm} warm-up (median), oracle/generate_oracle.py '
+                       f'(PyTorch CPU fp32, {cores} threads); the MXNet reference is not installable offline'), times
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    steps = min(steps, 8)                                  # bounded: ~2 s per 1024^2 sample on 8 cores
+    base, times = cpu_oracle_rate(wl, steps, warm=min(warm, 1))
+    ms = 1e3 * statistics.mean(times)
+    line = dict(metric=METRIC, value=base['value'], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=min(warm, 1),
+                ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                impl='reference', config=dict(workload=wl['name'], step='1 latent (bounded sample of the batch)'),
+                cpu_baseline=dict(base), gpu_launches=0,
+                e2e=dict(value=base['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='ffhq1024', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=0)
+    ap.add_argument('--dtype', default=os.environ.get('GSX_DTYPE', 'fp16'), choices=['fp16', 'bf16'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--layers-out', default='', help='write the per-layer roofline table (TSV) here')
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl['batch'] = args.batch
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, wl, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from gan_segmentation_b200 import _lib as L
+    from gan_segmentation_b200.networks import GeneratePipeline
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the generate path has no CPU fallback')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    B = wl['batch']
+    gc, dc, gp, dp, G, D = build_models(wl, args.dtype, device)
+    pipe = GeneratePipeline(G, D, B)
+    lib = G._lib
+    H, W = G.out_hw
+    img_dev = torch.empty((B, H, W, 3), dtype=torch.uint8, device=device)
+    mask_dev = torch.empty((B, H, W), dtype=torch.uint8, device=device)
+    z_dev = torch.randn((B, 512), generator=torch.Generator(device=device).manual_seed(1234 + rank), device=device)
+    psi = np.full((G.num_layers,), wl['psi'], np.float32)
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def step_device(i):
+        # latents already resident in HBM; noise from the on-device Philox stream of the global sample index
+        first = (i * world + rank) * B
+        L.check(lib.gsx_synth_forward(G._h, B, L.ptr(z_dev), L.np_ptr(psi), None, 7, first, None, L.ptr(img_dev), None,
+                                      L.ptr(pipe.gws), pipe.gws.numel(), sp), 'synth', args.dtype)
+        L.check(lib.gsx_dec_forward(D._h, B, None, G._h, L.ptr(pipe.gws), None, L.ptr(mask_dev), L.ptr(pipe.dws),
+                                    pipe.dws.numel(), sp), 'dec', args.dtype)
+
+    z_host = np.random.RandomState(99 + rank).randn(B, 512).astype(np.float32)
+
+    def step_host(i):
+        pipe.run(z_host, psi=psi, seed=7, first_sample=(i * world + rank) * B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for i in range(warm):
+            fn(i)
+        barrier()
+        n0 = L.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(warm + i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = L.launch_count() - n0
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, launches = timed(step_device)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _ = timed(step_host)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = steps * B * world / (ms_total * 1e-3)
+    e2e_value = steps * B * world / (ms_e2e * 1e-3)
+
+    # ---- per-layer profile of one step (outside the timed region) -> dominant kernel + roofline
+    pk = peaks()
+    lib.gsx_profile_enable(1)
+    step_device(0)
+    buf = C.create_string_buffer(1 << 20)
+    L.check(lib.gsx_profile_dump(buf, len(buf)), 'profile_dump', args.dtype)
+    lib.gsx_profile_enable(0)
+    rows = []
+    for ln in buf.value.decode().strip().split('\n'):
+        lab, ms, by, fl = ln.split('\t')
+        rows.append(dict(label=lab, ms=float(ms), bytes=float(by), flops=float(fl)))
+    agg = {}
+    for r in rows:
+        a = agg.setdefault(r['label'], dict(label=r['label'], ms=0.0, bytes=0.0, flops=0.0, launches=0))
+        a['ms'] += r['ms']; a['bytes'] += r['bytes']; a['flops'] += r['flops']; a['launches'] += 1
+    ridge = pk['tensor'] * 1e12 / (pk['hbm'] * 1e9)
+    table = []
+    for a in agg.values():
+        if a['ms'] <= 0:
+            continue
+        ai = a['flops'] / a['bytes'] if a['bytes'] else 0.0
+        bound = 'tensor' if ai > ridge else 'hbm'
+        ach = a['flops'] / (a['ms'] * 1e-3) / 1e12 if bound == 'tensor' else a['bytes'] / (a['ms'] * 1e-3) / 1e9
+        peak = pk['tensor'] if bound == 'tensor' else pk['hbm']
+        table.append(dict(a, bound=bound, achieved=ach, peak=peak, frac=ach / peak,
+                          unit='TFLOP/s' if bound == 'tensor' else 'GB/s'))
+    table.sort(key=lambda t: -t['ms'])
+    step_ms_profiled = sum(t['ms'] for t in table)
+    if args.layers_out:
+        with open(args.layers_out, 'w') as f:
+            f.write('label\tlaunches\tms\tshare\tbound\talg_GB\talg_GFLOP\tachieved\tunit\tfrac_of_%s_peak\n' % pk['src'])
+            for t in table:
+                f.write(f"{t['label']}\t{t['launches']}\t{t['ms']:.4f}\t{t['ms'] / step_ms_profiled:.4f}\t{t['bound']}\t"
+                        f"{t['bytes'] / 1e9:.4f}\t{t['flops'] / 1e9:.2f}\t{t['achieved']:.1f}\t{t['unit']}\t{t['frac']:.3f}\n")
+    top = table[0]
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get(top['label'])
+    roofline = dict(kernel=f"shiftconv_kernel [{top['label']}]" if '.conv' in top['label'] or 'cvt' in top['label'] or
+                    'final' in top['label'] or 'shortcut' in top['label'] else top['label'],
+                    bound=top['bound'], achieved=top['achieved'], peak=top['peak'], unit=top['unit'], frac=top['frac'],
+                    traffic=traffic, peak_source=pk['src'], share_of_step=top['ms'] / step_ms_profiled,
+                    whole_step=dict(hbm_frac=sum(t['bytes'] for t in table if t['bound'] == 'hbm') / 1e9 /
+                                    (sum(t['ms'] for t in table if t['bound'] == 'hbm') * 1e-3 + 1e-12) / pk['hbm'],
+                                    tensor_frac=sum(t['flops'] for t in table if t['bound'] == 'tensor') / 1e12 /
+                                    (sum(t['ms'] for t in table if t['bound'] == 'tensor') * 1e-3 + 1e-12) / pk['tensor']))
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu, _ = cpu_oracle_rate(wl, 5 if wl['max_res_log2'] >= 10 else 10)
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=steps, warmup=warm,
+                ms_per_step=ms_total / steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype=args.dtype, data='synthetic',
+                config=dict(workload=wl['name'], batch_per_gpu=B, global_batch=B * world, psi=wl['psi'],
+                            noise='on-device Philox4x32-10 keyed by (seed, global sample index, layer)',
+                            weights='random init of the named architecture (seed 0 / 2), pretrained .params unavailable offline',
+                            parallelism=f'latent-index sharding over {world} GPU(s), no collective',
+                            l2='per-step working set (~%.1f GiB) exceeds the 126 MB L2' % ((pipe.gws.numel() + pipe.dws.numel()) / 2 ** 30)),
+                clocks=clocks, gpu_launches=launches * world,
+                e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=ms_e2e / steps, h2d_bytes_per_step=pipe.h2d_bytes * world,
+                         d2h_bytes_per_step=pipe.d2h_bytes * world,
+                         api='gsx_generate_host (pinned host z in, uint8 image + mask out)'),
+                roofline=roofline, cpu_baseline=cpu)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

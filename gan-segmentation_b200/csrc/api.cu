@@ -67,6 +67,23 @@ static T* dev_upload(const std::vector<T>& h) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Optional per-launch timing (bench.py's per-layer roofline table): CUDA events around every launch
+// of a forward pass, on the caller's stream.  Off on the hot path.
+struct ProfRec { std::string label; double bytes, flops; cudaEvent_t e0, e1; };
+static std::vector<ProfRec> g_prof;
+static bool g_prof_on = false;
+struct ProfScope {
+  cudaStream_t st; bool on;
+  ProfScope(const std::string& label, double bytes, double flops, cudaStream_t s) : st(s), on(g_prof_on) {
+    if (!on) return;
+    ProfRec r{label, bytes, flops, nullptr, nullptr};
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    g_prof.push_back(r);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(g_prof.back().e1, st); }
+};
+
 struct Arena {              // carves a caller-owned workspace
   uint8_t* base; size_t off = 0;
   explicit Arena(void* b) : base(static_cast<uint8_t*>(b)) {}
@@ -78,7 +95,17 @@ struct Arena {              // carves a caller-owned workspace
 };
 
 // Runs one planned conv layer: builds the tensor maps for this batch / these buffers and launches.
-static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1, const ConvEpi& epi, cudaStream_t st) {
+static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1, const ConvEpi& epi, cudaStream_t st,
+                     const char* label = "conv") {
+  // algorithmic work of this layer: 2 B x (input + output elements), upsample/concat folded,
+  // +4 B x noise plane, uint8 mask; dense FLOPs of the reference formulation
+  const double in_el = (double)N * (L.cin0 + L.cin1) * L.H * L.W, out_px = (double)N * epi.Ho * epi.Wo;
+  double bytes = 2.0 * in_el + ((epi.flags & EPI_ARGMAX) ? out_px : 2.0 * out_px * L.cout);
+  if (epi.noise) bytes += 4.0 * out_px;
+  if (epi.addsrc) bytes += 2.0 * out_px / 4 * L.cout;
+  const double taps = L.mode == CONV1 ? 1 : (L.mode == DECONV4 ? 4 : 9);    // per OUTPUT pixel
+  const double flops = 2.0 * out_px * taps * (L.cin0 + L.cin1) * L.cout;
+  ProfScope ps(label, bytes, flops, st);
   ConvParams p;
   p.g = L.g;
   finish_geom_for_batch(p.g, N);
@@ -403,6 +430,7 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
   if (z_dev) {
     if (!cuda_ok(cudaMemcpyAsync(w.z, z_dev, (size_t)N * Z * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy z")) return -2;
   } else {
+    ProfScope ps("latents", 4.0 * N * Z, 0, st);
     launch_fill_latents(w.z, N, Z, seed, first_sample, st); g_launches++;
   }
   const float* psi = h->d_psi;
@@ -416,7 +444,7 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     DenseArgs d{};
     d.x = cur; d.W = h->d_map_w[i]; d.b = h->d_map_b[i]; d.y = (i & 1) ? w.wb : w.wa;
     d.N = N; d.K = Z; d.U = Z; d.lrelu = 1; d.pixelnorm = (i == 0);
-    launch_dense(d, st); g_launches++;
+    { ProfScope ps("map.dense", 4.0 * Z * Z + 8.0 * N * Z, 2.0 * N * Z * Z, st); launch_dense(d, st); g_launches++; }
     cur = d.y;
   }
   {   // all style layers at once; truncation folded into the operand load
@@ -424,6 +452,7 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     d.x = cur; d.W = h->d_aff_w; d.b = h->d_aff_b; d.y = w.styles;
     d.N = N; d.K = Z; d.U = h->S_total; d.lrelu = 0; d.pixelnorm = 0;
     d.latent_avg = h->d_latent_avg; d.psi = psi; d.unit_layer = h->d_unit_layer;
+    ProfScope ps("styles", 4.0 * h->S_total * Z + 4.0 * N * (Z + h->S_total), 2.0 * N * Z * h->S_total, st);
     launch_dense(d, st); g_launches++;
   }
   // noise planes
@@ -433,6 +462,7 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     else {
       int hh, ww;
       h->hw(2 + l / 2, hh, ww);
+      ProfScope ps("noise", 4.0 * N * hh * ww, 0, st);
       launch_fill_noise(w.noise[l], (size_t)hh * ww, N, seed, first_sample, l, st); g_launches++;
       noise[l] = w.noise[l];
     }
@@ -442,6 +472,8 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
   for (size_t bi = 0; bi < h->blocks.size(); ++bi) {
     const SynthBlock& b = h->blocks[bi];
     const int l1 = 2 * (int)bi, l2 = l1 + 1;
+    const std::string tag = "g" + std::to_string(b.r) + ".";
+    const double act_bytes = 2.0 * N * b.C * b.H * b.W, plane_bytes = 4.0 * N * b.H * b.W;
     float* st1 = w.partial[l1];
     float* st2 = w.partial[l2];
     Pass1Args p1{};
@@ -452,16 +484,17 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     } else {
       ConvEpi e{};
       e.out = w.bufA; e.Ho = b.H; e.Wo = b.W; e.up = 1; e.flags = 0; e.Cout = b.C;
-      if (!run_conv(b.conv1, N, w.feat[bi - 1], nullptr, e, st)) return -2;
+      if (!run_conv(b.conv1, N, w.feat[bi - 1], nullptr, e, st, (tag + (b.r >= 7 ? "deconv" : "upconv")).c_str())) return -2;
       p1.in = w.bufA; p1.in_broadcast = 0; p1.blur = 1;
     }
-    launch_pass1(p1, st); g_launches++;
-    launch_finalize(st1, w.stats_T[l1], N, b.C, b.H * b.W, w.styles, h->S_total, h->style_off[l1], w.coef[l1], st);
-    g_launches++;
+    { ProfScope ps(tag + "pass1", (b.r == 2 ? 1.0 : 2.0) * act_bytes + plane_bytes, 0, st); launch_pass1(p1, st); g_launches++; }
+    { ProfScope ps(tag + "finalize", 0, 0, st);
+      launch_finalize(st1, w.stats_T[l1], N, b.C, b.H * b.W, w.styles, h->S_total, h->style_off[l1], w.coef[l1], st);
+      g_launches++; }
     ApplyArgs a1{};
     a1.in = w.bufB; a1.out = w.bufB; a1.C = b.C; a1.N = N; a1.H = b.H; a1.W = b.W;
     a1.coef = w.coef[l1];
-    launch_apply(a1, st); g_launches++;
+    { ProfScope ps(tag + "apply1", 2.0 * act_bytes, 0, st); launch_apply(a1, st); g_launches++; }
 
     ConvEpi e2{};
     e2.out = w.bufA; e2.Ho = b.H; e2.Wo = b.W; e2.up = 0; e2.Cout = b.C;
@@ -470,10 +503,11 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     e2.flags = EPI_LRELU | (fused_stats ? EPI_STATS : 0);
     e2.stats = fused_stats ? st2 : nullptr;
     e2.stats_T = w.stats_T[l2];
-    if (!run_conv(b.conv2, N, w.bufB, nullptr, e2, st)) return -2;
-    if (!fused_stats) { launch_stats(w.bufA, st2, b.C, N, b.H * b.W, st); g_launches++; }
-    launch_finalize(st2, w.stats_T[l2], N, b.C, b.H * b.W, w.styles, h->S_total, h->style_off[l2], w.coef[l2], st);
-    g_launches++;
+    if (!run_conv(b.conv2, N, w.bufB, nullptr, e2, st, (tag + "conv2").c_str())) return -2;
+    if (!fused_stats) { ProfScope ps(tag + "stats", act_bytes, 0, st); launch_stats(w.bufA, st2, b.C, N, b.H * b.W, st); g_launches++; }
+    { ProfScope ps(tag + "finalize", 0, 0, st);
+      launch_finalize(st2, w.stats_T[l2], N, b.C, b.H * b.W, w.styles, h->S_total, h->style_off[l2], w.coef[l2], st);
+      g_launches++; }
 
     ApplyArgs a2{};
     a2.in = w.bufA; a2.out = w.feat[bi]; a2.C = b.C; a2.N = N; a2.H = b.H; a2.W = b.W;
@@ -482,7 +516,13 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     if (b.r == h->L) {
       a2.wrgb = h->d_wrgb; a2.brgb = h->d_brgb; a2.img_f32 = img_f32_dev; a2.img_u8 = img_u8_dev; a2.nc = h->cfg.channels;
     }
-    launch_apply(a2, st); g_launches++;
+    {
+      double by = 2.0 * act_bytes;
+      if (b.r == h->L) by += (img_u8_dev ? 1.0 : 0.0) * N * b.H * b.W * h->cfg.channels + (img_f32_dev ? 4.0 : 0.0) * N * b.H * b.W * h->cfg.channels;
+      if (a2.out_nchw_f32) by += 2.0 * act_bytes;
+      ProfScope ps(tag + (b.r == h->L ? "apply2+rgb" : "apply2"), by, b.r == h->L ? 2.0 * N * b.H * b.W * b.C * h->cfg.channels : 0, st);
+      launch_apply(a2, st); g_launches++;
+    }
   }
   if (!cuda_ok(cudaGetLastError(), "synth forward")) return -2;
   return 0;
@@ -685,6 +725,7 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
   if (own) {
     for (int i = 0; i < nf; ++i) {
       const DecLevel& l = d->levels[i];
+      ProfScope ps("d" + std::to_string(i) + ".to_blocked", 6.0 * N * l.cin * l.H * l.W, 0, st);
       launch_nchw_to_blocked(feats_f32_dev[i], w.feat[i], l.cin, N, l.H * l.W, st); g_launches++;
       feat[i] = w.feat[i];
     }
@@ -704,7 +745,7 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
     {
       ConvEpi e{};
       e.out = w.c[i]; e.Ho = l.H; e.Wo = l.W; e.flags = EPI_LRELU; e.Cout = l.f; e.bias = l.b_cvt;
-      if (!run_conv(l.cvt, N, feat[i], nullptr, e, st)) return -2;
+      if (!run_conv(l.cvt, N, feat[i], nullptr, e, st, ("d" + std::to_string(i) + ".cvt").c_str())) return -2;
     }
     const act_t* x0 = i > 0 ? w.prev[i] : w.c[i];
     const act_t* x1 = i > 0 ? w.c[i] : nullptr;
@@ -712,26 +753,26 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
       {
         ConvEpi e{};
         e.out = w.a[i]; e.Ho = 2 * l.H; e.Wo = 2 * l.W; e.up = 1; e.flags = EPI_LRELU; e.Cout = l.fnext; e.bias = l.b_a;
-        if (!run_conv(l.conv_a, N, x0, x1, e, st)) return -2;
+        if (!run_conv(l.conv_a, N, x0, x1, e, st, ("d" + std::to_string(i) + ".conv_a").c_str())) return -2;
       }
       const act_t* sc = x0;
       if (l.has_shortcut) {
         ConvEpi e{};
         e.out = w.sc[i]; e.Ho = l.H; e.Wo = l.W; e.flags = 0; e.Cout = l.fnext; e.bias = l.b_sc;
-        if (!run_conv(l.shortcut, N, x0, x1, e, st)) return -2;
+        if (!run_conv(l.shortcut, N, x0, x1, e, st, ("d" + std::to_string(i) + ".shortcut").c_str())) return -2;
         sc = w.sc[i];
       }
       {
         ConvEpi e{};
         e.out = w.prev[i + 1]; e.Ho = 2 * l.H; e.Wo = 2 * l.W; e.flags = EPI_LRELU; e.Cout = l.fnext; e.bias = l.b_b;
         e.addsrc = sc;
-        if (!run_conv(l.conv_b, N, w.a[i], nullptr, e, st)) return -2;
+        if (!run_conv(l.conv_b, N, w.a[i], nullptr, e, st, ("d" + std::to_string(i) + ".conv_b").c_str())) return -2;
       }
     } else {
       ConvEpi e{};
       e.Ho = l.H; e.Wo = l.W; e.flags = EPI_ARGMAX; e.Cout = l.fnext; e.bias = l.b_final;
       e.mask = mask_dev; e.logits = logits_dev; e.num_classes = d->num_classes;
-      if (!run_conv(l.final_, N, x0, x1, e, st)) return -2;
+      if (!run_conv(l.final_, N, x0, x1, e, st, ("d" + std::to_string(i) + ".final+argmax").c_str())) return -2;
     }
   }
   return cuda_ok(cudaGetLastError(), "dec forward") ? 0 : -2;
@@ -764,4 +805,31 @@ extern "C" int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z
     return -2;
   if (mask_host && !cuda_ok(cudaMemcpyAsync(mask_host, mask_dev, mb, cudaMemcpyDeviceToHost, st), "D2H mask")) return -2;
   return 0;
+}
+
+// =============================================================================================
+// per-launch profile (bench.py's per-layer table)
+// =============================================================================================
+extern "C" int gsx_profile_enable(int on) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_prof_on = on != 0;
+  return 0;
+}
+
+extern "C" int gsx_profile_dump(char* buf, size_t cap) {
+  if (!buf || cap == 0) { set_error("bad argument"); return -1; }
+  if (!cuda_ok(cudaDeviceSynchronize(), "profile dump")) return -2;
+  size_t off = 0;
+  buf[0] = 0;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    const int n = snprintf(buf + off, cap - off, "%s\t%.6f\t%.0f\t%.0f\n", r.label.c_str(), ms, r.bytes, r.flops);
+    if (n < 0 || (size_t)n >= cap - off) break;
+    off += (size_t)n;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  return (int)off;
 }

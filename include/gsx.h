@@ -104,6 +104,11 @@ int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z_host, cons
                       size_t synth_ws_bytes, void* dec_ws, size_t dec_ws_bytes, void* stage_dev,
                       size_t stage_bytes, gsx_stream stream);
 
+/* ---- per-launch timing of the forward passes (bench.py's per-layer roofline table): enable, run a
+ *      forward, dump "label\tms\talgorithmic_bytes\talgorithmic_flops\n" lines.  Off by default. ---- */
+int gsx_profile_enable(int on);
+int gsx_profile_dump(char* buf, size_t cap);
+
 /* ---- single-operator hooks (tests / tuning; fp32 NCHW device tensors in and out, temporaries
  *      are allocated inside, so not for the hot path) ---- */
 int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, int cout, const float* x0_dev,
