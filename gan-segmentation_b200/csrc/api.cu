@@ -111,6 +111,7 @@ static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1
   finish_geom_for_batch(p.g, N);
   p.e = epi;
   p.wpack = L.wpack_dev;
+  p.taps = L.taps_dev;
   set_error("");
   make_act_tensormap(&p.tm[0], x0, L.cin0, N, L.H, L.W, p.g.BW, p.g.BH, p.g.NB, p.g.CBK);
   if (L.cin1 > 0) make_act_tensormap(&p.tm[1], x1, L.cin1, N, L.H, L.W, p.g.BW, p.g.BH, p.g.NB, p.g.CBK);
@@ -126,7 +127,10 @@ static bool upload_conv(ConvLayer& L, const float* w) {
   pack_conv_weights(L, w, packed);
   L.wpack_elems = packed.size();
   L.wpack_dev = dev_upload(packed);
-  return L.wpack_dev != nullptr;
+  std::vector<int4> taps(4 * kMaxSlots);
+  build_tap_table(L.g, taps.data());
+  L.taps_dev = dev_upload(taps);
+  return L.wpack_dev != nullptr && L.taps_dev != nullptr;
 }
 
 }  // namespace gsx
@@ -255,6 +259,7 @@ extern "C" void gsx_synth_destroy(gsx_synth* h) {
   cudaFree(h->d_psi); cudaFree(h->d_wrgb); cudaFree(h->d_brgb); cudaFree(h->d_const);
   for (auto& b : h->blocks) {
     cudaFree(b.conv1.wpack_dev); cudaFree(b.conv2.wpack_dev);
+    cudaFree(b.conv1.taps_dev); cudaFree(b.conv2.taps_dev);
     cudaFree(b.ns1); cudaFree(b.b1); cudaFree(b.ns2); cudaFree(b.b2);
   }
   delete h;
@@ -346,6 +351,7 @@ extern "C" int gsx_synth_finalize(gsx_synth* h) {
   // ---- synthesis blocks
   for (auto& b : h->blocks) {
     cudaFree(b.conv1.wpack_dev); cudaFree(b.conv2.wpack_dev);
+    cudaFree(b.conv1.taps_dev); cudaFree(b.conv2.taps_dev);
     cudaFree(b.ns1); cudaFree(b.b1); cudaFree(b.ns2); cudaFree(b.b2);
   }
   h->blocks.clear();
@@ -605,6 +611,8 @@ extern "C" int gsx_dec_create(const gsx_dec_cfg* cfg, gsx_dec** out) {
 static void free_level(DecLevel& l) {
   cudaFree(l.cvt.wpack_dev); cudaFree(l.conv_a.wpack_dev); cudaFree(l.conv_b.wpack_dev);
   cudaFree(l.shortcut.wpack_dev); cudaFree(l.final_.wpack_dev);
+  cudaFree(l.cvt.taps_dev); cudaFree(l.conv_a.taps_dev); cudaFree(l.conv_b.taps_dev);
+  cudaFree(l.shortcut.taps_dev); cudaFree(l.final_.taps_dev);
   cudaFree(l.b_cvt); cudaFree(l.b_a); cudaFree(l.b_b); cudaFree(l.b_sc); cudaFree(l.b_final);
 }
 

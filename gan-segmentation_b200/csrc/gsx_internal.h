@@ -37,7 +37,7 @@ __host__ __device__ inline act_t to_act(float v) {
 #endif
 }
 
-static const int kConvHeaderBytes = 10240;   // shiftconv smem header: barriers + tmem slot + per-warp stats scratch
+static const int kConvHeaderBytes = 2048;    // shiftconv smem header: mbarriers + tmem slot
 
 // ----------------------------------------------------------------------------------------------
 // Activation layout in HBM ("blocked"): [C/8][N][H][W][8] act_t -- 8 channels of one pixel form one
@@ -81,7 +81,13 @@ struct ConvGeom {
   int cb_stride_bytes;         // NB*BH*BW*16
   int a_stage_bytes, b_stage_bytes;
   int a_stage_stride;          // a_stage_bytes rounded up to 128 (TMA destination alignment)
-  int tmem_cols;
+  int a_off;                   // byte offset of the A stages in dynamic smem (after header + stats slots)
+  int tmem_cols;               // allocated TMEM columns (power of two) = acc_bufs * n_groups*n_mtiles*N_tile rounded up
+  int acc_bufs;                // 2: accumulators double buffered (MMA of tile i+1 overlaps epilogue of tile i)
+  int b_resident;              // 1: the whole packed weight set is loaded once per CTA and stays in smem
+  int epi_groups;              // G: epilogue warps per TMEM lane quarter (CTA has 2 + 4G warps)
+  int ctas_per_sm;             // persistent grid = min(work items, SMs * ctas_per_sm)
+  unsigned magic_box, magic_bw;  // ceil(2^32 / (BH*BW)), ceil(2^32 / BW): division by multiply-high
   int smem_bytes;
   short slot_shift[4][kMaxSlots];   // [phase or 0][slot] -> position shift dy*BW+dx inside the box
   signed char slot_group[kMaxSlots];
@@ -110,6 +116,10 @@ struct ConvParams {
   ConvGeom g;
   ConvEpi e;
   const act_t* wpack;
+  // per (phase, slot) tap table in device memory: {A shift in bytes, accumulator group, first-of-group, 0}.
+  // (Indexing the by-value parameter arrays dynamically would make the compiler copy the whole parameter
+  //  block to local memory and turn every field access of the MMA issue loop into a local load.)
+  const int4* taps;
 };
 
 // A planned + packed convolution layer (host side).
@@ -120,10 +130,13 @@ struct ConvLayer {
   ConvGeom g{};                       // geometry with N-independent fields filled
   act_t* wpack_dev = nullptr;
   size_t wpack_elems = 0;
+  int4* taps_dev = nullptr;           // 4 * kMaxSlots entries
 };
+void build_tap_table(const ConvGeom& g, int4* out /* 4*kMaxSlots */);
 
 struct PlanOverride {
   int TH, TW, NB, CBK, N_tile, stages, phase_grid;   // 0 / -1 = keep default
+  int epi_groups, acc_bufs, max_mtiles;              // 0 = keep default
 };
 
 // plan.cpp

@@ -37,7 +37,7 @@ extern "C" int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, in
   set_error("");
   ConvLayer L;
   PlanOverride po{};
-  if (ov) { po.TH = ov->TH; po.TW = ov->TW; po.NB = ov->NB; po.CBK = ov->CBK; po.N_tile = ov->N_tile; po.stages = ov->stages; po.phase_grid = ov->phase_grid; }
+  if (ov) { po.TH = ov->TH; po.TW = ov->TW; po.NB = ov->NB; po.CBK = ov->CBK; po.N_tile = ov->N_tile; po.stages = ov->stages; po.phase_grid = ov->phase_grid; po.epi_groups = ov->epi_groups; po.acc_bufs = ov->acc_bufs; po.max_mtiles = ov->max_mtiles; }
   plan_conv(L, mode, h, w, cin0, cin1, cout, argmax ? num_classes : 0, ov ? &po : nullptr);
   if (*last_error_cstr()) return -1;
   std::vector<act_t> packed;
@@ -53,11 +53,17 @@ extern "C" int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, in
   if (cin1) launch_nchw_to_blocked(x1_dev, xb1, cin1, n, h * w, st);
   if (addsrc_dev) launch_nchw_to_blocked(addsrc_dev, ab, cout, n, (Ho / 2) * (Wo / 2), st);
   L.wpack_dev = wp;
+  std::vector<int4> taps_h(4 * kMaxSlots);
+  build_tap_table(L.g, taps_h.data());
+  int4* taps_d = tmp.get<int4>(taps_h.size());
+  if (!taps_d) { set_error("cudaMalloc failed"); return -2; }
+  cudaMemcpyAsync(taps_d, taps_h.data(), taps_h.size() * sizeof(int4), cudaMemcpyHostToDevice, st);
 
   ConvParams p;
   p.g = L.g;
   finish_geom_for_batch(p.g, n);
   p.wpack = wp;
+  p.taps = taps_d;
   ConvEpi e{};
   e.out = ob; e.Ho = Ho; e.Wo = Wo; e.up = up ? 1 : 0; e.flags = flags; e.Cout = cout;
   e.bias = bias_dev; e.nscale = nscale_dev; e.noise = noise_dev; e.addsrc = ab;
@@ -78,7 +84,7 @@ extern "C" int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, in
   if (plan_out) {
     const ConvGeom& g = p.g;
     const int vals[16] = {g.TH, g.TW, g.NB, g.CBK, g.N_tile, g.stages, g.phase_grid, g.n_mtiles, g.n_k, g.tmem_cols,
-                          g.smem_bytes, g.tiles_x * g.tiles_y * g.tiles_n, g.n_ntiles, g.n_groups, g.n_slots, g.BW};
+                          g.smem_bytes, g.tiles_x * g.tiles_y * g.tiles_n, g.n_ntiles, g.n_groups * 100 + g.acc_bufs * 10 + g.epi_groups, g.n_slots, g.BW};
     for (int i = 0; i < 16; ++i) plan_out[i] = vals[i];
   }
   launch_shiftconv(p, st); g_launches++;
@@ -109,12 +115,12 @@ extern "C" int gsx_plan_query(int mode, int h, int w, int cin0, int cin1, int co
   set_error("");
   ConvLayer L;
   PlanOverride po{};
-  if (ov) { po.TH = ov->TH; po.TW = ov->TW; po.NB = ov->NB; po.CBK = ov->CBK; po.N_tile = ov->N_tile; po.stages = ov->stages; po.phase_grid = ov->phase_grid; }
+  if (ov) { po.TH = ov->TH; po.TW = ov->TW; po.NB = ov->NB; po.CBK = ov->CBK; po.N_tile = ov->N_tile; po.stages = ov->stages; po.phase_grid = ov->phase_grid; po.epi_groups = ov->epi_groups; po.acc_bufs = ov->acc_bufs; po.max_mtiles = ov->max_mtiles; }
   plan_conv(L, mode, h, w, cin0, cin1, cout, num_classes, ov ? &po : nullptr);
   if (*last_error_cstr()) return -1;
   const ConvGeom& g = L.g;
   const int vals[16] = {g.TH, g.TW, g.NB, g.CBK, g.N_tile, g.stages, g.phase_grid, g.n_mtiles, g.n_k, g.tmem_cols,
-                        g.smem_bytes, g.tiles_x * g.tiles_y, g.n_ntiles, g.n_groups, g.n_slots, g.BW};
+                        g.smem_bytes, g.tiles_x * g.tiles_y, g.n_ntiles, g.n_groups * 100 + g.acc_bufs * 10 + g.epi_groups, g.n_slots, g.BW};
   for (int i = 0; i < 16; ++i) plan_out[i] = vals[i];
   return 0;
 }

@@ -45,9 +45,19 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   if (ov && ov->phase_grid >= 0 && up) phase_grid = ov->phase_grid;
   const int G = (up && !phase_grid) ? 4 : 1;
   const bool thin = (cin0 + cin1) <= 64 && cout <= 64;
+  // thin layers: 256 columns per accumulator buffer so that two buffers fit (MMA / epilogue overlap);
+  // wide layers: all 512 columns for one buffer (more MMA rows per weight load; the epilogue is a small
+  // fraction of the k-loop there)
   int budget_cols = thin ? 256 : 512;
+  if (ov && ov->acc_bufs == 1) budget_cols = 512;
+  if (ov && ov->acc_bufs == 2) budget_cols = 256;
   int max_mt = std::max(1, budget_cols / (G * N_tile));
   max_mt = std::min(max_mt, 32);
+  if (ov && ov->max_mtiles > 0) max_mt = std::min(max_mt, ov->max_mtiles);
+  int epi_groups = (N_tile <= 32) ? 4 : 2;
+  if (ov && ov->epi_groups > 0) epi_groups = ov->epi_groups;
+  const int stats_bytes = (2 * 4 * epi_groups * 2 * N_tile * 4 + 1023) / 1024 * 1024;
+  const int hdr_bytes = kHeader + stats_bytes;
 
   int TW = (W <= 126) ? W : ((W % 64 == 0) ? 64 : 126);
   if (ov && ov->TW > 0) TW = ov->TW;
@@ -75,7 +85,7 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
     int cbs[4] = {8, 4, 2, 0};
     if (ov && ov->CBK > 0) { cbs[0] = ov->CBK; cbs[1] = 0; }
     bool found = false;
-    const long lim = thin ? 110 * 1024 : kSmemLimit;      // thin layers: leave room for 2 CTAs per SM
+    const long lim = kSmemLimit;                          // one persistent CTA per SM
     for (int ci = 0; cbs[ci] && !found; ++ci) {
       const int c = cbs[ci];
       if (c > cbt || cb0 % c || (cb1 && cb1 % c)) continue;
@@ -83,10 +93,13 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
       const long a_st = ((long)NB * BH * BW * 16 * c + 127) / 128 * 128;   // TMA smem destinations are 128-B aligned
       const long b_st = (long)n_slots * (c / 2) * N_tile * 32;
       if ((long)NB * BH * BW * 16 >= (1 << 18)) continue;                 // LBO field is 14 bits of 16-byte units
-      const int s_hi = (ov && ov->stages > 0) ? ov->stages : std::min(n_k, thin ? 2 : 4);
-      const int s_lo = (ov && ov->stages > 0) ? ov->stages : std::min(n_k, 2);
+      // the stage ring runs across work items, so even single-chunk layers want >= 2 stages
+      const bool bres = (n_k == 1) && !phase_grid && (argmax_classes > 0 || cout <= N_tile);
+      const int s_hi = (ov && ov->stages > 0) ? ov->stages : (n_k == 1 ? 3 : 4);
+      const int s_lo = (ov && ov->stages > 0) ? ov->stages : 2;
       for (int s = s_hi; s >= s_lo && s >= 1; --s) {
-        if (kHeader + s * (a_st + b_st) + kSlack <= lim) { CBK = c; stages = s; found = true; break; }
+        const long tot = hdr_bytes + (bres ? s * a_st + b_st : s * (a_st + b_st)) + kSlack;
+        if (tot <= lim) { CBK = c; stages = s; found = true; break; }
       }
     }
     if (found) break;
@@ -106,9 +119,18 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   g.a_stage_bytes = g.cb_stride_bytes * CBK;
   g.a_stage_stride = (g.a_stage_bytes + 127) / 128 * 128;
   g.b_stage_bytes = n_slots * (CBK / 2) * N_tile * 32;
-  g.tmem_cols = pow2_cols(G * g.n_mtiles * N_tile);
-  g.smem_bytes = kHeader + stages * (g.a_stage_stride + g.b_stage_bytes) + kSlack;
-  if (g.tmem_cols > 512) { set_error("plan_conv: TMEM budget exceeded"); return; }
+  const int cols = G * g.n_mtiles * N_tile;
+  g.acc_bufs = (2 * cols <= 512) ? 2 : 1;
+  if (ov && ov->acc_bufs == 1) g.acc_bufs = 1;
+  g.tmem_cols = pow2_cols(g.acc_bufs * cols);
+  if (cols > 512) { set_error("plan_conv: TMEM budget exceeded"); return; }
+  g.b_resident = (g.n_k == 1 && g.n_ntiles == 1 && !phase_grid) ? 1 : 0;
+  g.epi_groups = epi_groups;
+  g.ctas_per_sm = 1;
+  g.a_off = hdr_bytes;
+  g.magic_box = (unsigned)((0x100000000ULL + (unsigned long long)(g.BH * BW) - 1) / (unsigned long long)(g.BH * BW));
+  g.magic_bw = (unsigned)((0x100000000ULL + (unsigned long long)BW - 1) / (unsigned long long)BW);
+  g.smem_bytes = hdr_bytes + stages * g.a_stage_stride + (g.b_resident ? 1 : stages) * g.b_stage_bytes + kSlack;
 
   for (int ph = 0; ph < 4; ++ph)
     for (int s = 0; s < kMaxSlots; ++s) g.slot_shift[ph][s] = 0;
@@ -136,6 +158,12 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
         }
     }
   }
+}
+
+void build_tap_table(const ConvGeom& g, int4* out) {
+  for (int ph = 0; ph < 4; ++ph)
+    for (int s = 0; s < kMaxSlots; ++s)
+      out[ph * kMaxSlots + s] = make_int4(g.slot_shift[ph][s] * 16, g.slot_group[s], g.slot_first[s], 0);
 }
 
 void finish_geom_for_batch(ConvGeom& g, int N) {

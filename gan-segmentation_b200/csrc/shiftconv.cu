@@ -1,4 +1,4 @@
-// Shift-GEMM convolution on tcgen05 tensor cores (sm_100a).
+// Shift-GEMM convolution on tcgen05 tensor cores (sm_100a), persistent and warp-specialized.
 //
 // Every convolution on the generate path -- the generator's 3x3 convs (reference
 // networks_stylegan.py:446-457 used at :24,:46), the nearest-x2 + 3x3 conv (:27 + :24), the 4x4
@@ -13,43 +13,45 @@
 //     address is shifted by (dy*BW+dx)*16 B -- no im2col copy, each input byte is staged once.
 //   * nearest-x2+conv and the transposed conv are four output phases of 2x2 taps on the low-res
 //     input (16 tap/phase pairs); the phases either share one CTA (thin layers; 4 accumulator
-//     groups) or are spread over blockIdx.z (wide layers).
-//   * accumulators live in TMEM (128 lanes x N_tile fp32 columns per 128-pixel MMA tile); one
-//     thread issues tcgen05.mma, tcgen05.commit releases smem stages / publishes the accumulators.
-//   * 4 epilogue warps read TMEM (tcgen05.ld 32x32b), fuse noise*scale + bias + leaky-ReLU
-//     (+ residual add, + InstanceNorm sum/sumsq, or + argmax) and store 16-bit activations with 16 B per thread.
+//     groups) or are separate work items (wide layers).
+//   * accumulators live in TMEM (128 lanes x N_tile fp32 columns per 128-pixel MMA tile), double
+//     buffered when they fit twice, so the MMAs of tile i+1 overlap the epilogue of tile i.
+//   * one CTA per SM loops over its work items (static round-robin); for thin layers the packed
+//     weights are loaded once per CTA and stay resident in shared memory.
+//   * epilogue warps read TMEM (tcgen05.ld 32x32b), fuse noise*scale + bias + leaky-ReLU
+//     (+ residual add, + InstanceNorm sum/sumsq, or + argmax) and store 16-bit activations, 16 B per thread.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2.. = 4*G epilogue warps
+// (G warps per TMEM lane quarter).
 #include "gsx_internal.h"
 #include "ptx.cuh"
 
 namespace gsx {
 
-static constexpr int kThreads = 192;
-static constexpr int kHeaderBytes = kConvHeaderBytes;   // barriers + tmem slot + stats scratch
 static constexpr int kMaxStages = 8;
 
 struct __align__(16) SmemHeader {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
-  uint64_t accum_full;
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint64_t bres_full;
   uint32_t tmem_base;
   uint32_t pad;
-  float stats[4][2 * 256];     // [epilogue warp][channel in N_tile][sum, sumsq] -- one slot per warp, no atomics
+  int4 taps[4 * kMaxSlots];   // copy of ConvParams::taps
 };
-static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
+static_assert(sizeof(SmemHeader) <= kConvHeaderBytes, "header too large");
 
-__device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
+__device__ __forceinline__ float lrelu02(float v) { return fmaxf(v, 0.2f * v); }
 
 __device__ __forceinline__ uint32_t pack_x2(float a, float b) {
+  uint32_t r;
 #if GSX_FP16
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  __half2 h = __floats2half2_rn(a, b);
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));     // saturates instead of inf
 #else
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
 #endif
-  return *reinterpret_cast<uint32_t*>(&h);
+  return r;
 }
 __device__ __forceinline__ float2 unpack_x2(uint32_t w) {
 #if GSX_FP16
@@ -59,36 +61,54 @@ __device__ __forceinline__ float2 unpack_x2(uint32_t w) {
 #endif
 }
 
-__global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_constant__ ConvParams p) {
+struct TileCoord { int x0, y0, n0, ntile, phase, tile_in_sample; };
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int t) {
+  TileCoord c;
+  const int sp = g.tiles_x * g.tiles_y * g.tiles_n;
+  int s = t % sp;
+  const int rest = t / sp;
+  c.ntile = rest % g.n_ntiles;
+  c.phase = rest / g.n_ntiles;
+  const int tx = s % g.tiles_x; s /= g.tiles_x;
+  const int ty = s % g.tiles_y; s /= g.tiles_y;
+  c.x0 = tx * g.TW; c.y0 = ty * g.TH; c.n0 = s * g.NB;
+  c.tile_in_sample = ty * g.tiles_x + tx;
+  return c;
+}
+
+template <int G>
+__global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int kEpiWarps = 4 * G;
+  constexpr int kEpiThreads = 128 * G;
   extern __shared__ __align__(1024) uint8_t smem[];
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
-  uint8_t* a_base = smem + kHeaderBytes;
   const ConvGeom& g = p.g;
+  float* stats_slots = reinterpret_cast<float*>(smem + kConvHeaderBytes);     // [2][kEpiWarps][2*N_tile]
+  uint8_t* a_base = smem + g.a_off;
   uint8_t* b_base = a_base + (size_t)g.stages * g.a_stage_stride;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile coordinates
-  int t = blockIdx.x;
-  const int tx = t % g.tiles_x; t /= g.tiles_x;
-  const int ty = t % g.tiles_y; t /= g.tiles_y;
-  const int tn = t;
-  const int x0 = tx * g.TW, y0 = ty * g.TH, n0 = tn * g.NB;
-  const int ntile = blockIdx.y;
-  const int phase_z = g.phase_grid ? (int)blockIdx.z : 0;
+  const int total_tiles = g.tiles_x * g.tiles_y * g.tiles_n * g.n_ntiles * (g.phase_grid ? 4 : 1);
+  const int nbuf = g.acc_bufs;
+  const int cols_per_buf = g.n_groups * g.n_mtiles * g.N_tile;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.stages; ++s) {
       mbar_init(&hdr->full[s], 1);
       mbar_init(&hdr->empty[s], 1);
     }
-    mbar_init(&hdr->accum_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&hdr->tmem_full[b], 1);
+      mbar_init(&hdr->tmem_empty[b], kEpiWarps);
+    }
+    mbar_init(&hdr->bres_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.tm[0]);
     if (g.kch0 < g.n_k) tma_prefetch_desc(&p.tm[1]);
   }
-  for (int i = threadIdx.x; i < 4 * 2 * 256; i += kThreads) (&hdr->stats[0][0])[i] = 0.f;
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 4 * kMaxSlots) hdr->taps[threadIdx.x - 64] = __ldg(p.taps + threadIdx.x - 64);
   if (warp == 1) {
     tmem_alloc(&hdr->tmem_base, (uint32_t)g.tmem_cols);
     tmem_relinquish();
@@ -101,19 +121,30 @@ __global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_con
   if (warp == 0) {
     // ================================ TMA producer =================================
     if (lane == 0) {
-      const uint32_t stage_bytes = (uint32_t)(g.a_stage_bytes + g.b_stage_bytes);
-      const act_t* wsrc = p.wpack + ((size_t)(phase_z * g.n_ntiles + ntile) * g.n_k) * (size_t)(g.b_stage_bytes / 2);
-      for (int kc = 0; kc < g.n_k; ++kc) {
-        const int s = kc % g.stages;
-        const int it = kc / g.stages;
-        if (it > 0) mbar_wait(&hdr->empty[s], (uint32_t)((it - 1) & 1));
-        mbar_expect_tx(&hdr->full[s], stage_bytes);
-        const int src = kc < g.kch0 ? 0 : 1;
-        const int cb0 = (src ? kc - g.kch0 : kc) * g.CBK;
-        // dim0 is in 8-byte units (2 per pixel) so that the inner box extent reaches 128 pixels
-        tma_load_4d(a_base + (size_t)s * g.a_stage_stride, &p.tm[src], &hdr->full[s], (x0 - 1) * 2, y0 - 1, n0, cb0);
-        bulk_load(b_base + (size_t)s * g.b_stage_bytes, wsrc + (size_t)kc * (g.b_stage_bytes / 2),
-                  (uint32_t)g.b_stage_bytes, &hdr->full[s]);
+      const size_t b_stage_elems = (size_t)(g.b_stage_bytes / 2);
+      if (g.b_resident) {
+        mbar_expect_tx(&hdr->bres_full, (uint32_t)g.b_stage_bytes);
+        bulk_load(b_base, p.wpack, (uint32_t)g.b_stage_bytes, &hdr->bres_full);
+      }
+      const uint32_t stage_bytes = (uint32_t)(g.a_stage_bytes + (g.b_resident ? 0 : g.b_stage_bytes));
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(g, t);
+        const act_t* wsrc = p.wpack + ((size_t)(tc.phase * g.n_ntiles + tc.ntile) * g.n_k) * b_stage_elems;
+        for (int kc = 0; kc < g.n_k; ++kc, ++it) {
+          const int s = it % g.stages;
+          const int round = it / g.stages;
+          if (round > 0) mbar_wait(&hdr->empty[s], (uint32_t)((round - 1) & 1));
+          mbar_expect_tx(&hdr->full[s], stage_bytes);
+          const int src = kc < g.kch0 ? 0 : 1;
+          const int cb0 = (src ? kc - g.kch0 : kc) * g.CBK;
+          // dim0 is in 8-byte units (2 per pixel) so that the inner box extent reaches 128 pixels
+          tma_load_4d(a_base + (size_t)s * g.a_stage_stride, &p.tm[src], &hdr->full[s], (tc.x0 - 1) * 2, tc.y0 - 1,
+                      tc.n0, cb0);
+          if (!g.b_resident)
+            bulk_load(b_base + (size_t)s * g.b_stage_bytes, wsrc + (size_t)kc * b_stage_elems, (uint32_t)g.b_stage_bytes,
+                      &hdr->full[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -123,129 +154,162 @@ __global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_con
     const uint64_t b_hi = umma_desc_hi((uint32_t)g.N_tile * 16, 128);
     const int k16_per_chunk = g.CBK >> 1;
     const uint32_t b_tile_bytes = (uint32_t)g.N_tile * 32;
-    for (int kc = 0; kc < g.n_k; ++kc) {
-      const int s = kc % g.stages;
-      const int it = kc / g.stages;
-      mbar_wait(&hdr->full[s], (uint32_t)(it & 1));
+    // hoist everything the issue loop needs into registers
+    const int n_k = g.n_k, stages = g.stages, n_slots = g.n_slots, n_mtiles = g.n_mtiles, b_res = g.b_resident;
+    const uint32_t a_stride = (uint32_t)g.a_stage_stride, b_stride = (uint32_t)g.b_stage_bytes;
+    const uint32_t cb_stride = (uint32_t)g.cb_stride_bytes, n_tile = (uint32_t)g.N_tile;
+    const uint32_t a_smem = smem_u32(a_base), b_smem = smem_u32(b_base);
+    if (g.b_resident) mbar_wait(&hdr->bres_full, 0);
+    int it = 0, tl = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+      const TileCoord tc = decode_tile(g, t);
+      const int buf = tl % nbuf;
+      const int use = tl / nbuf;
+      if (use > 0) mbar_wait(&hdr->tmem_empty[buf], (uint32_t)((use - 1) & 1));
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(a_base + (size_t)s * g.a_stage_stride);
-        const uint32_t b_addr = smem_u32(b_base + (size_t)s * g.b_stage_bytes);
-        for (int slot = 0; slot < g.n_slots; ++slot) {
-          const int grp = g.slot_group[slot];
-          const uint32_t shift_bytes = (uint32_t)g.slot_shift[phase_z][slot] * 16u;
-          for (int j = 0; j < k16_per_chunk; ++j) {
-            const uint64_t bdesc = umma_desc(b_hi, b_addr + (uint32_t)(slot * k16_per_chunk + j) * b_tile_bytes);
-            const uint32_t acc = (kc > 0 || j > 0 || !g.slot_first[slot]) ? 1u : 0u;
-            const uint32_t a_k = a_addr + (uint32_t)(2 * j) * (uint32_t)g.cb_stride_bytes + shift_bytes;
-            for (int mt = 0; mt < g.n_mtiles; ++mt) {
-              const uint64_t adesc = umma_desc(a_hi, a_k + (uint32_t)mt * 2048u);
-              umma_f16kind(tmem_base + (uint32_t)((grp * g.n_mtiles + mt) * g.N_tile), adesc, bdesc, idesc, acc);
+      const uint32_t acc_base = tmem_base + (uint32_t)(buf * cols_per_buf);
+      const int4* taps = hdr->taps + tc.phase * kMaxSlots;
+      for (int kc = 0; kc < n_k; ++kc, ++it) {
+        const int s = it % stages;
+        mbar_wait(&hdr->full[s], (uint32_t)((it / stages) & 1));
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = a_smem + (uint32_t)s * a_stride;
+          uint32_t b_addr = b_smem + (b_res ? 0u : (uint32_t)s * b_stride);
+          for (int slot = 0; slot < n_slots; ++slot) {
+            const int4 tp = taps[slot];                            // {shift bytes, group, first, -}
+            const uint32_t d0 = acc_base + (uint32_t)(tp.y * n_mtiles) * n_tile;
+            for (int j = 0; j < k16_per_chunk; ++j, b_addr += b_tile_bytes) {
+              const uint64_t bdesc = umma_desc(b_hi, b_addr);
+              const uint32_t acc = (kc > 0 || j > 0 || !tp.z) ? 1u : 0u;
+              uint64_t adesc = umma_desc(a_hi, a_addr + (uint32_t)(2 * j) * cb_stride + (uint32_t)tp.x);
+              uint32_t d = d0;
+              for (int mt = 0; mt < n_mtiles; ++mt, adesc += 128 /* 2048 B >> 4 */, d += n_tile)
+                umma_f16kind(d, adesc, bdesc, idesc, acc);
             }
           }
+          umma_commit(&hdr->empty[s]);
+          if (kc == n_k - 1) umma_commit(&hdr->tmem_full[buf]);
         }
-        umma_commit(&hdr->empty[s]);
-        if (kc == g.n_k - 1) umma_commit(&hdr->accum_full);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ================================ epilogue =====================================
     const ConvEpi& e = p.e;
+    const int ew = warp - 2;                      // 0 .. kEpiWarps-1
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int egrp = ew >> 2;                     // which of the G warps sharing this quarter
     const int row = quarter * 32 + lane;
-    const int box_pix = g.BH * g.BW;
     const bool do_stats = (e.flags & EPI_STATS) != 0;
     const bool do_act = (e.flags & EPI_LRELU) != 0;
     const size_t plane_out = (size_t)e.Ho * e.Wo;
+    const int n_chunks = g.N_tile >> 4;
+    const int n_units = g.n_groups * g.n_mtiles;
+    const int slot_floats = 2 * g.N_tile;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
 
-    mbar_wait(&hdr->accum_full, 0);
-    tc_fence_after();
-
-    if (e.flags & EPI_ARGMAX) {
-      for (int mt = 0; mt < g.n_mtiles; ++mt) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * g.N_tile), v);
-        tmem_ld_wait();
-        const int q = mt * 128 + row;
-        const int nb = q / box_pix;
-        const int rem = q - nb * box_pix;
-        const int yl = rem / g.BW, xl = rem - yl * g.BW;
-        const int n = n0 + nb, y = y0 + yl, x = x0 + xl;
-        if (nb < g.NB && yl < g.TH && xl < g.TW && n < g.N && y < g.H && x < g.W) {
-          float best = __uint_as_float(v[0]) + (e.bias ? e.bias[0] : 0.f);
-          int arg = 0;
-          const size_t pix = (size_t)y * e.Wo + x;
-          if (e.logits) e.logits[((size_t)n * e.num_classes) * plane_out + pix] = best;
-#pragma unroll
-          for (int c = 1; c < 16; ++c) {
-            if (c < e.num_classes) {
-              const float lv = __uint_as_float(v[c]) + (e.bias ? e.bias[c] : 0.f);
-              if (e.logits) e.logits[((size_t)n * e.num_classes + c) * plane_out + pix] = lv;
-              if (lv > best) { best = lv; arg = c; }       // first maximum wins (seg_solver.py:326)
-            }
-          }
-          e.mask[(size_t)n * plane_out + pix] = (unsigned char)arg;
-        }
+    int tl = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+      const TileCoord tc = decode_tile(g, t);
+      const int buf = tl % nbuf;
+      float* my_slot = stats_slots + ((size_t)(tl & 1) * kEpiWarps + ew) * slot_floats;
+      if (do_stats) {
+        for (int i = lane; i < slot_floats; i += 32) my_slot[i] = 0.f;
+        __syncwarp();
       }
-    } else {
-      const int n_chunks = g.N_tile >> 4;
-      for (int cc = 0; cc < n_chunks; ++cc) {
-        const int c0 = ntile * g.N_tile + cc * 16;          // first output channel of this chunk
-        float bias_r[16], ns_r[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          bias_r[i] = e.bias ? __ldg(e.bias + c0 + i) : 0.f;
-          ns_r[i] = e.nscale ? __ldg(e.nscale + c0 + i) : 0.f;
-        }
-        float s1[16], s2[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+      mbar_wait(&hdr->tmem_full[buf], (uint32_t)((tl / nbuf) & 1));
+      tc_fence_after();
+      const uint32_t acc_base = tmem_base + (uint32_t)(buf * cols_per_buf) + lane_base;
 
-        for (int grp = 0; grp < g.n_groups; ++grp) {
-          const int ph = g.phase_grid ? phase_z : grp;
-          const int py = ph >> 1, px = ph & 1;
-          for (int mt = 0; mt < g.n_mtiles; ++mt) {
-            uint32_t v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                          (uint32_t)((grp * g.n_mtiles + mt) * g.N_tile + cc * 16), v);
-            tmem_ld_wait();
-            const int q = mt * 128 + row;
-            const int nb = q / box_pix;
-            const int rem = q - nb * box_pix;
-            const int yl = rem / g.BW, xl = rem - yl * g.BW;
-            const int n = n0 + nb;
-            int y = y0 + yl, x = x0 + xl;
-            const bool valid = nb < g.NB && yl < g.TH && xl < g.TW && n < g.N && y < g.H && x < g.W;
-            if (valid) {
-              if (e.up) { y = 2 * y + py; x = 2 * x + px; }
-              const size_t pix = (size_t)y * e.Wo + x;
-              float f[16];
-              const float nz = e.noise ? __ldg(e.noise + (size_t)n * plane_out + pix) : 0.f;
+      // position of this thread's row inside MMA tile `mt`:  q = mt*128 + row  ->  (nb, yl, xl)
+      auto locate = [&](int mt, int& n, int& y, int& x) -> bool {
+        const int q = mt * 128 + row;
+        const int nb = (int)__umulhi((uint32_t)q, g.magic_box);
+        const int rem = q - nb * (g.BH * g.BW);
+        const int yl = (int)__umulhi((uint32_t)rem, g.magic_bw);
+        const int xl = rem - yl * g.BW;
+        n = tc.n0 + nb; y = tc.y0 + yl; x = tc.x0 + xl;
+        return nb < g.NB && yl < g.TH && xl < g.TW && n < g.N && y < g.H && x < g.W;
+      };
+
+      if (e.flags & EPI_ARGMAX) {
+        for (int mt = egrp; mt < g.n_mtiles; mt += G) {
+          uint32_t v[16];
+          tmem_ld16(acc_base + (uint32_t)(mt * g.N_tile), v);
+          tmem_ld_wait();
+          int n, y, x;
+          if (locate(mt, n, y, x)) {
+            float best = __uint_as_float(v[0]) + (e.bias ? __ldg(e.bias) : 0.f);
+            int arg = 0;
+            const size_t pix = (size_t)y * e.Wo + x;
+            if (e.logits) e.logits[((size_t)n * e.num_classes) * plane_out + pix] = best;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float a = __uint_as_float(v[i]) + ns_r[i] * nz + bias_r[i];
-                f[i] = do_act ? lrelu02(a) : a;
+            for (int c = 1; c < 16; ++c) {
+              if (c < e.num_classes) {
+                const float lv = __uint_as_float(v[c]) + (e.bias ? __ldg(e.bias + c) : 0.f);
+                if (e.logits) e.logits[((size_t)n * e.num_classes + c) * plane_out + pix] = lv;
+                if (lv > best) { best = lv; arg = c; }       // first maximum wins (seg_solver.py:326)
               }
+            }
+            e.mask[(size_t)n * plane_out + pix] = (unsigned char)arg;
+          }
+        }
+      } else {
+        for (int cc = 0; cc < n_chunks; ++cc) {
+          const int c0 = tc.ntile * g.N_tile + cc * 16;          // first output channel of this chunk
+          float bias_r[16], ns_r[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            bias_r[i] = e.bias ? __ldg(e.bias + c0 + i) : 0.f;
+            ns_r[i] = e.nscale ? __ldg(e.nscale + c0 + i) : 0.f;
+          }
+          float s1[16], s2[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+
+          // units (accumulator group, MMA tile) of this chunk are dealt round-robin to the G warps of a quarter
+          for (int u = (egrp + cc) % G; u < n_units; u += G) {
+            const int grp = u / g.n_mtiles, mt = u - grp * g.n_mtiles;
+            const int ph = g.phase_grid ? tc.phase : grp;
+            uint32_t v[16];
+            tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + cc * 16), v);
+            int n, y, x;
+            const bool valid = locate(mt, n, y, x);
+            if (e.up) { y = 2 * y + (ph >> 1); x = 2 * x + (ph & 1); }
+            const size_t pix = (size_t)y * e.Wo + x;
+            float nz = 0.f;
+            uint4 add0 = make_uint4(0, 0, 0, 0), add1 = add0;
+            if (valid) {                                          // issue the global loads before waiting on TMEM
+              if (e.noise) nz = __ldg(e.noise + (size_t)n * plane_out + pix);
               if (e.addsrc) {
                 const size_t plane_lo = (size_t)(e.Ho >> 1) * (e.Wo >> 1);
                 const size_t pl = (size_t)(y >> 1) * (e.Wo >> 1) + (x >> 1);
+                const act_t* ap = e.addsrc + (((size_t)(c0 >> 3) * g.N + n) * plane_lo + pl) * 8;
+                add0 = __ldg(reinterpret_cast<const uint4*>(ap));
+                add1 = __ldg(reinterpret_cast<const uint4*>(ap + (size_t)g.N * plane_lo * 8));
+              }
+            }
+            tmem_ld_wait();
+            if (valid) {
+              float f[16];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const uint4 r = *reinterpret_cast<const uint4*>(
-                      e.addsrc + (((size_t)((c0 >> 3) + h) * g.N + n) * plane_lo + pl) * 8);
-                  const uint32_t w4[4] = {r.x, r.y, r.z, r.w};
+              for (int i = 0; i < 16; ++i) {
+                const float a = fmaf(ns_r[i], nz, __uint_as_float(v[i]) + bias_r[i]);
+                f[i] = do_act ? lrelu02(a) : a;
+              }
+              if (e.addsrc) {
+                const uint32_t w8[8] = {add0.x, add0.y, add0.z, add0.w, add1.x, add1.y, add1.z, add1.w};
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const float2 b2 = unpack_x2(w4[k]);
-                    f[h * 8 + 2 * k] += b2.x;
-                    f[h * 8 + 2 * k + 1] += b2.y;
-                  }
+                for (int k = 0; k < 8; ++k) {
+                  const float2 b2 = unpack_x2(w8[k]);
+                  f[2 * k] += b2.x;
+                  f[2 * k + 1] += b2.y;
                 }
               }
               if (do_stats) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) { s1[i] += f[i]; s2[i] += f[i] * f[i]; }
+                for (int i = 0; i < 16; ++i) { s1[i] += f[i]; s2[i] = fmaf(f[i], f[i], s2[i]); }
               }
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
@@ -260,40 +324,44 @@ __global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_con
               }
             }
           }
-        }
-        if (do_stats) {
-          // 32 values (16 sums, 16 sums of squares) x 32 lanes -> lane L ends up holding value L fully reduced
-          float vals[32];
+          if (do_stats) {
+            // 32 values (16 sums, 16 sums of squares) x 32 lanes -> lane L ends up holding value L fully reduced
+            float vals[32];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { vals[i] = s1[i]; vals[16 + i] = s2[i]; }
+            for (int i = 0; i < 16; ++i) { vals[i] = s1[i]; vals[16 + i] = s2[i]; }
 #pragma unroll
-          for (int step = 0; step < 5; ++step) {
-            const int half = 16 >> step;                      // values kept per lane after this step
-            const int bit = 16 >> step;                       // lane bit deciding which half is kept
-            const bool upper = (lane & bit) != 0;
+            for (int step = 0; step < 5; ++step) {
+              const int half = 16 >> step;                      // values kept per lane after this step
+              const bool upper = (lane & half) != 0;            // lane bit deciding which half is kept
 #pragma unroll
-            for (int i = 0; i < half; ++i) {
-              const float keep = upper ? vals[half + i] : vals[i];
-              const float send = upper ? vals[i] : vals[half + i];
-              vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+              for (int i = 0; i < half; ++i) {
+                const float keep = upper ? vals[half + i] : vals[i];
+                const float send = upper ? vals[i] : vals[half + i];
+                vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+              }
             }
+            // value index = lane: 0..15 channel sums, 16..31 sums of squares; this warp's own slot: plain add
+            my_slot[(cc * 16 + (lane & 15)) * 2 + (lane >> 4)] += vals[0];
           }
-          // lane's bits (16,8,4,2,1) selected halves successively -> value index = lane
-          const int vi = lane;                                 // 0..15 sums, 16..31 sumsq
-          const int ch = cc * 16 + (vi & 15);
-          hdr->stats[warp - 2][ch * 2 + (vi >> 4)] += vals[0];     // this warp's own slot: plain add
         }
       }
+
+      // accumulator buffer drained -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&hdr->tmem_empty[buf]);
+
       if (do_stats) {
-        named_bar_sync(1, 128);                                // the 4 epilogue warps
-        const int tid = threadIdx.x - 64;
-        // fused stats need a single sample per CTA (NB == 1); enforced by the callers.  Fixed summation
+        named_bar_sync(1, kEpiThreads);                          // all epilogue warps finished this tile
+        // fused stats need a single sample per CTA tile (NB == 1); enforced by the callers.  Fixed summation
         // order + one partial per (sample, tile): bit-reproducible, finalize_kernel adds the tiles up.
-        const int tile_in_sample = ty * g.tiles_x + tx;
-        for (int i = tid; i < g.N_tile * 2; i += 128) {
-          const int ch = ntile * g.N_tile + (i >> 1);
-          const float s = (hdr->stats[0][i] + hdr->stats[1][i]) + (hdr->stats[2][i] + hdr->stats[3][i]);
-          if (ch < e.Cout) e.stats[(((size_t)n0 * e.stats_T + tile_in_sample) * e.Cout + ch) * 2 + (i & 1)] = s;
+        const float* slots = stats_slots + (size_t)(tl & 1) * kEpiWarps * slot_floats;
+        for (int i = threadIdx.x - 64; i < slot_floats; i += kEpiThreads) {
+          const int ch = tc.ntile * g.N_tile + (i >> 1);
+          float s = 0.f;
+#pragma unroll
+          for (int w = 0; w < kEpiWarps; ++w) s += slots[w * slot_floats + i];
+          if (ch < e.Cout) e.stats[(((size_t)tc.n0 * e.stats_T + tc.tile_in_sample) * e.Cout + ch) * 2 + (i & 1)] = s;
         }
       }
     }
@@ -304,14 +372,29 @@ __global__ void __launch_bounds__(kThreads, 1) shiftconv_kernel(const __grid_con
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
 }
 
-void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
-  static int configured_smem = 0;
-  if (p.g.smem_bytes > configured_smem) {
-    cudaFuncSetAttribute(shiftconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    configured_smem = 227 * 1024;
+template <int G>
+static void launch_g(const ConvParams& p, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(shiftconv_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = true;
   }
-  dim3 grid((unsigned)(p.g.tiles_x * p.g.tiles_y * p.g.tiles_n), (unsigned)p.g.n_ntiles, p.g.phase_grid ? 4u : 1u);
-  shiftconv_kernel<<<grid, kThreads, p.g.smem_bytes, st>>>(p);
+  shiftconv_kernel<G><<<grid, 64 + 128 * G, p.g.smem_bytes, st>>>(p);
+}
+
+void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const ConvGeom& g = p.g;
+  const int total = g.tiles_x * g.tiles_y * g.tiles_n * g.n_ntiles * (g.phase_grid ? 4 : 1);
+  const int grid = total < num_sms * g.ctas_per_sm ? total : num_sms * g.ctas_per_sm;
+  if (g.epi_groups == 4) launch_g<4>(p, grid, st);
+  else if (g.epi_groups == 2) launch_g<2>(p, grid, st);
+  else launch_g<1>(p, grid, st);
 }
 
 }  // namespace gsx

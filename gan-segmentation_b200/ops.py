@@ -10,7 +10,7 @@ import torch
 from . import _lib as L
 
 PLAN_FIELDS = ('TH', 'TW', 'NB', 'CBK', 'N_tile', 'stages', 'phase_grid', 'n_mtiles', 'n_k', 'tmem_cols',
-               'smem_bytes', 'tiles', 'n_ntiles', 'n_groups', 'n_slots', 'BW')
+               'smem_bytes', 'tiles', 'n_ntiles', 'groups_bufs_epi', 'n_slots', 'BW')
 
 
 def _stream():
@@ -39,7 +39,7 @@ def conv(mode, x0, weight, x1=None, bias=None, nscale=None, noise=None, flags=0,
     logits = torch.empty((n, num_classes, ho, wo), dtype=torch.float32, device=dev) if argmax else None
     ov = None
     if override:
-        ov = L.PlanOverride(TH=0, TW=0, NB=0, CBK=0, N_tile=0, stages=0, phase_grid=-1)
+        ov = L.PlanOverride(TH=0, TW=0, NB=0, CBK=0, N_tile=0, stages=0, phase_grid=-1, epi_groups=0, acc_bufs=0, max_mtiles=0)
         for k, v in override.items():
             setattr(ov, k, v)
     plan = (C.c_int * 16)()

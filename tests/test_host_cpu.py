@@ -86,7 +86,9 @@ def test_planner_invariants(gsx_lib, gan, base):
         tag = f'{gan}{base} mode={mode} {h}x{w} {c0}+{c1}->{co}: {p}'
         assert p['smem_bytes'] <= 227 * 1024, tag
         assert p['tmem_cols'] <= 512 and p['tmem_cols'] >= 32 and p['tmem_cols'] & (p['tmem_cols'] - 1) == 0, tag
-        assert p['n_groups'] * p['n_mtiles'] * p['N_tile'] <= p['tmem_cols'], tag
+        groups, bufs, epi = p['groups_bufs_epi'] // 100, p['groups_bufs_epi'] // 10 % 10, p['groups_bufs_epi'] % 10
+        assert bufs * groups * p['n_mtiles'] * p['N_tile'] <= p['tmem_cols'], tag
+        assert bufs in (1, 2) and epi in (1, 2, 4), tag
         assert p['N_tile'] % 16 == 0 and p['N_tile'] <= 256, tag
         assert p['CBK'] % 2 == 0 and (c0 // 8) % p['CBK'] == 0 and (c1 // 8) % p['CBK'] == 0, tag
         assert p['BW'] == p['TW'] + 2 and p['BW'] <= 128, tag            # TMA box: 256 8-byte units
