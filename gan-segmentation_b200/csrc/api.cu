@@ -216,7 +216,7 @@ static SynthWs synth_layout(const gsx_synth* h, int N, void* base) {
 static int synth_stats_tiles(const gsx_synth* h, int l) {
   int hh, ww;
   h->hw(2 + l / 2, hh, ww);
-  if ((l & 1) == 0) return pass1_tiles(hh * ww);
+  if ((l & 1) == 0) return pass1_tiles(hh, ww);
   if ((size_t)(l / 2) < h->blocks.size()) {
     const ConvGeom& g = h->blocks[l / 2].conv2.g;
     if (g.NB == 1) return g.tiles_x * g.tiles_y;

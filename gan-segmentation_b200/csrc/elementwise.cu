@@ -24,14 +24,13 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
   }
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
+  uint32_t r;
 #if GSX_FP16
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  __half2 h = __floats2half2_rn(a, b);
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));     // saturates instead of inf
 #else
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
 #endif
-  return *reinterpret_cast<uint32_t*>(&h);
+  return r;
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 o;
@@ -66,16 +65,21 @@ __device__ __forceinline__ void block_reduce_store(float (&v)[NV], float* dst0, 
 }
 
 // ------------------------------------------------------------------------------------------ pass1
-static constexpr int kP1Threads = 256;
-static constexpr int kP1PixPerThread = 4;
+// One warp owns a strip of 30 output columns (32 loaded columns: one halo column each side, so the
+// horizontal blur taps come from the neighbouring lanes by shuffle) and walks down kP1Rows rows with a
+// 3-row register window for the vertical taps: 1 coalesced 512-B load per output row instead of 9.
+static constexpr int kP1Warps = 4;
+static constexpr int kP1Cols = 30;
+static constexpr int kP1Rows = 32;
 
-__global__ void __launch_bounds__(kP1Threads) pass1_kernel(const Pass1Args a) {
+__global__ void __launch_bounds__(kP1Warps * 32) pass1_kernel(const Pass1Args a, int strips, int rowblocks) {
   const int plane = blockIdx.y;                 // cb * N + n
   const int cb = plane / a.N, n = plane - cb * a.N;
   const int HW = a.H * a.W;
   const act_t* in = a.in + ((size_t)(a.in_broadcast ? cb : plane) * HW) * 8;
   act_t* out = a.out + ((size_t)plane * HW) * 8;
   const float* noise = a.noise ? a.noise + (size_t)n * HW : nullptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   float ns[8], bs[8];
 #pragma unroll
@@ -87,58 +91,80 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(const Pass1Args a) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
 
-  const int base = blockIdx.x * (kP1Threads * kP1PixPerThread);
-#pragma unroll
-  for (int it = 0; it < kP1PixPerThread; ++it) {
-    const int pix = base + it * kP1Threads + threadIdx.x;
-    if (pix < HW) {
+  const int item = blockIdx.x * kP1Warps + warp;            // (rowblock, strip)
+  if (item < strips * rowblocks) {
+    const int strip = item % strips, rb = item / strips;
+    const int x = strip * kP1Cols - 1 + lane;               // column this lane loads
+    const bool xin = x >= 0 && x < a.W;
+    const bool xout = lane >= 1 && lane <= kP1Cols && x < a.W;
+    const int y0 = rb * kP1Rows, y1 = min(a.H, y0 + kP1Rows);
+    // raw 16-B row loads, issued kP1Ahead rows ahead of their use (zero outside the image = the blur's zero pad)
+    auto raw_row = [&](int y) -> uint4 {
+      if (xin && y >= 0 && y < a.H) return ldg_nc_u4(in + ((size_t)y * a.W + x) * 8);
+      return make_uint4(0u, 0u, 0u, 0u);
+    };
+    auto raw_noise = [&](int y) -> float {
+      return (noise && xout && y < a.H) ? __ldg(noise + (size_t)y * a.W + x) : 0.f;
+    };
+    const int lead = a.blur ? 1 : 0;                         // the vertical tap below needs row y+1
+    uint4 p0 = raw_row(y0 + lead), p1 = raw_row(y0 + lead + 1), p2 = raw_row(y0 + lead + 2);
+    float n0 = raw_noise(y0), n1 = raw_noise(y0 + 1), n2 = raw_noise(y0 + 2);
+    float r0[8], r1[8], r2[8];
+    if (a.blur) { unpack8(raw_row(y0 - 1), r0); unpack8(raw_row(y0), r1); }
+    for (int y = y0; y < y1; ++y) {
+      const uint4 cur = p0;
+      const float nz = n0;
+      p0 = p1; p1 = p2; p2 = raw_row(y + lead + 3);
+      n0 = n1; n1 = n2; n2 = raw_noise(y + 3);
       float v[8];
       if (a.blur) {
-        const int y = pix / a.W, x = pix - y * a.W;
+        unpack8(cur, r2);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-          const int yy = y + dy;
-          if (yy < 0 || yy >= a.H) continue;
-#pragma unroll
-          for (int dx = -1; dx <= 1; ++dx) {
-            const int xx = x + dx;
-            if (xx < 0 || xx >= a.W) continue;
-            const float wgt = (dy == 0 ? 2.f : 1.f) * (dx == 0 ? 2.f : 1.f) * (1.f / 16.f);
-            float f[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(in + ((size_t)yy * a.W + xx) * 8)), f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += wgt * f[i];
-          }
+        for (int i = 0; i < 8; ++i) {
+          const float vb = r0[i] + 2.f * r1[i] + r2[i];                     // vertical [1,2,1]
+          const float l = __shfl_up_sync(0xffffffffu, vb, 1), r = __shfl_down_sync(0xffffffffu, vb, 1);
+          v[i] = (l + 2.f * vb + r) * (1.f / 16.f);                         // horizontal [1,2,1], /16
+          r0[i] = r1[i]; r1[i] = r2[i];
         }
       } else {
-        unpack8(__ldg(reinterpret_cast<const uint4*>(in + (size_t)pix * 8)), v);
+        unpack8(cur, v);
       }
-      const float nz = noise ? __ldg(noise + pix) : 0.f;
+      if (xout) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float t = v[i] + ns[i] * nz + bs[i];
-        t = t > 0.f ? t : 0.2f * t;
-        v[i] = t;
-        acc[i] += t;
-        acc[8 + i] += t * t;
+        for (int i = 0; i < 8; ++i) {
+          float t = v[i] + ns[i] * nz + bs[i];
+          t = fmaxf(t, 0.2f * t);
+          v[i] = t;
+          acc[i] += t;
+          acc[8 + i] = fmaf(t, t, acc[8 + i]);
+        }
+        *reinterpret_cast<uint4*>(out + ((size_t)y * a.W + x) * 8) = pack8(v);
       }
-      *reinterpret_cast<uint4*>(out + (size_t)pix * 8) = pack8(v);
     }
   }
   if (a.stats) {
     float* st = a.stats + (((size_t)n * gridDim.x + blockIdx.x) * a.C + cb * 8) * 2;
-    block_reduce_store<16>(acc, st, st + 1, kP1Threads);
+    block_reduce_store<16>(acc, st, st + 1, kP1Warps * 32);
   }
 }
 
-int pass1_tiles(int HW) { return (HW + kP1Threads * kP1PixPerThread - 1) / (kP1Threads * kP1PixPerThread); }
+static void pass1_shape(int H, int W, int& strips, int& rowblocks, int& blocks) {
+  strips = (W + kP1Cols - 1) / kP1Cols;
+  rowblocks = (H + kP1Rows - 1) / kP1Rows;
+  blocks = (strips * rowblocks + kP1Warps - 1) / kP1Warps;
+}
+
+int pass1_tiles(int H, int W) {
+  int s, r, b;
+  pass1_shape(H, W, s, r, b);
+  return b;
+}
 
 void launch_pass1(const Pass1Args& a, cudaStream_t st) {
-  const int HW = a.H * a.W;
-  dim3 grid(pass1_tiles(HW), (a.C / 8) * a.N);
-  pass1_kernel<<<grid, kP1Threads, 0, st>>>(a);
+  int strips, rowblocks, blocks;
+  pass1_shape(a.H, a.W, strips, rowblocks, blocks);
+  dim3 grid(blocks, (a.C / 8) * a.N);
+  pass1_kernel<<<grid, kP1Warps * 32, 0, st>>>(a, strips, rowblocks);
 }
 
 // ------------------------------------------------------------------------------------------ stats

@@ -74,7 +74,18 @@ struct ConvGeom {
   int n_mtiles;                // 128-row MMA tiles per CTA
   int N_tile;                  // MMA N (output channels per CTA)
   int n_ntiles;
-  int n_groups;                // accumulator groups per CTA (4 = all phases in one CTA)
+  int n_groups;                // always 1 (kept for the plan dump)
+  int up_cols;                 // 1: the 4 output phases of an up-conv are column blocks of ONE accumulator
+                               //    (N_tile = 4*cout_tile); every distinct input shift is a single MMA whose
+                               //    weight tile is zero for the phases that do not use that shift
+  int cout_tile;               // output channels per CTA (= N_tile unless up_cols / hstack)
+  int hstack;                  // 1 (thin 3x3): the three horizontal taps kx are column blocks of ONE accumulator
+                               //    (N_tile = 3*cout_tile) fed by 3 MMAs (one per ky, shift ky*BW) instead of 9;
+                               //    the epilogue forms out[q] = acc[q][0] + acc[q+1][1] + acc[q+2][2] with warp
+                               //    shuffles (+ a 3x16-float smem hand-over between neighbouring warps)
+  int mt_stride;               // positions between consecutive MMA tiles: 128, or 126 with hstack (rows 126,127 of
+                               //    a tile only feed rows 124,125 and are recomputed as rows 0,1 of the next tile)
+  int xch_off;                 // byte offset of the hstack exchange buffer in dynamic smem
   int n_slots;                 // filter taps per CTA
   int phase_grid;              // 1: blockIdx.z selects the phase (wide up-convs)
   int stages;
@@ -137,6 +148,7 @@ void build_tap_table(const ConvGeom& g, int4* out /* 4*kMaxSlots */);
 struct PlanOverride {
   int TH, TW, NB, CBK, N_tile, stages, phase_grid;   // 0 / -1 = keep default
   int epi_groups, acc_bufs, max_mtiles;              // 0 = keep default
+  int hstack;                                        // -1 = keep default, 0/1 force
 };
 
 // plan.cpp
@@ -158,10 +170,10 @@ struct Pass1Args {            // blur? + noise + bias + lrelu + stats  (generato
   int blur;                   // 1: 3x3 [1,2,1]^2/16 zero-pad blur first
   int in_broadcast;           // 1: input has a single sample (constant tensor)
   const float* nscale; const float* bias; const float* noise;   // [C], [C], [N][H][W]
-  float* stats;               // per-block partial sums [N][pass1_tiles(H*W)][C][2]
+  float* stats;               // per-block partial sums [N][pass1_tiles(H,W)][C][2]
 };
 void launch_pass1(const Pass1Args& a, cudaStream_t st);
-int pass1_tiles(int HW);
+int pass1_tiles(int H, int W);
 
 struct ApplyArgs {            // InstanceNorm + AdaIN: out = (t-mean)*rstd*(scale+1)+shift
   const act_t* in; act_t* out;  // blocked

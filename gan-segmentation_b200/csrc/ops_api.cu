@@ -37,7 +37,7 @@ extern "C" int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, in
   set_error("");
   ConvLayer L;
   PlanOverride po{};
-  if (ov) { po.TH = ov->TH; po.TW = ov->TW; po.NB = ov->NB; po.CBK = ov->CBK; po.N_tile = ov->N_tile; po.stages = ov->stages; po.phase_grid = ov->phase_grid; po.epi_groups = ov->epi_groups; po.acc_bufs = ov->acc_bufs; po.max_mtiles = ov->max_mtiles; }
+  if (ov) { po.TH = ov->TH; po.TW = ov->TW; po.NB = ov->NB; po.CBK = ov->CBK; po.N_tile = ov->N_tile; po.stages = ov->stages; po.phase_grid = ov->phase_grid; po.epi_groups = ov->epi_groups; po.acc_bufs = ov->acc_bufs; po.max_mtiles = ov->max_mtiles; po.hstack = ov->hstack; }
   plan_conv(L, mode, h, w, cin0, cin1, cout, argmax ? num_classes : 0, ov ? &po : nullptr);
   if (*last_error_cstr()) return -1;
   std::vector<act_t> packed;
@@ -115,7 +115,7 @@ extern "C" int gsx_plan_query(int mode, int h, int w, int cin0, int cin1, int co
   set_error("");
   ConvLayer L;
   PlanOverride po{};
-  if (ov) { po.TH = ov->TH; po.TW = ov->TW; po.NB = ov->NB; po.CBK = ov->CBK; po.N_tile = ov->N_tile; po.stages = ov->stages; po.phase_grid = ov->phase_grid; po.epi_groups = ov->epi_groups; po.acc_bufs = ov->acc_bufs; po.max_mtiles = ov->max_mtiles; }
+  if (ov) { po.TH = ov->TH; po.TW = ov->TW; po.NB = ov->NB; po.CBK = ov->CBK; po.N_tile = ov->N_tile; po.stages = ov->stages; po.phase_grid = ov->phase_grid; po.epi_groups = ov->epi_groups; po.acc_bufs = ov->acc_bufs; po.max_mtiles = ov->max_mtiles; po.hstack = ov->hstack; }
   plan_conv(L, mode, h, w, cin0, cin1, cout, num_classes, ov ? &po : nullptr);
   if (*last_error_cstr()) return -1;
   const ConvGeom& g = L.g;
@@ -135,7 +135,7 @@ extern "C" int gsx_op_pass1(int n, int c, int h, int w, const float* x_dev, int 
   act_t* ob = tmp.get<act_t>((size_t)n * c * h * w);
   if (!xb || !ob) { set_error("cudaMalloc failed"); return -2; }
   launch_nchw_to_blocked(x_dev, xb, c, nin, h * w, st);
-  const int T = pass1_tiles(h * w);
+  const int T = pass1_tiles(h, w);
   float* partial = stats_dev ? tmp.get<float>((size_t)n * T * c * 2) : nullptr;
   Pass1Args a{};
   a.in = xb; a.out = ob; a.C = c; a.N = n; a.H = h; a.W = w; a.blur = blur; a.in_broadcast = in_broadcast;

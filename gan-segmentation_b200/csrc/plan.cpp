@@ -43,7 +43,18 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   if (ov && ov->N_tile > 0) N_tile = ov->N_tile;
   int phase_grid = (up && cout > 64) ? 1 : 0;
   if (ov && ov->phase_grid >= 0 && up) phase_grid = ov->phase_grid;
-  const int G = (up && !phase_grid) ? 4 : 1;
+  const int up_cols = (up && !phase_grid) ? 1 : 0;
+  const int cout_tile = N_tile;
+  if (up_cols) N_tile = 4 * cout_tile;        // phases stacked along the MMA N dimension (<= 256)
+  // every M=128 kind::f16 MMA costs ~75 cycles for any N <= 128 (tools/umma_bench.cu), so thin 3x3 layers are
+  // bound by the NUMBER of MMAs: stack the 3 horizontal taps along N -> 3 MMAs per k16 step instead of 9
+  // (measured on B200: the heavier epilogue -- 3x TMEM loads, 32 shuffles, a barrier per unit -- costs more
+  //  than the MMAs it saves, so the mode is off unless forced through the plan override)
+  int hstack = 0;
+  if (ov && ov->hstack >= 0 && mode == CONV3 && cout <= 64) hstack = ov->hstack;
+  if (hstack) N_tile = 3 * cout_tile;
+  const int mt_stride = hstack ? 126 : 128;
+  const int G = 1;
   const bool thin = (cin0 + cin1) <= 64 && cout <= 64;
   // thin layers: 256 columns per accumulator buffer so that two buffers fit (MMA / epilogue overlap);
   // wide layers: all 512 columns for one buffer (more MMA rows per weight load; the epilogue is a small
@@ -54,15 +65,16 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   int max_mt = std::max(1, budget_cols / (G * N_tile));
   max_mt = std::min(max_mt, 32);
   if (ov && ov->max_mtiles > 0) max_mt = std::min(max_mt, ov->max_mtiles);
-  int epi_groups = (N_tile <= 32) ? 4 : 2;
+  int epi_groups = 2;          // 8 epilogue warps; the 16-warp variant spills (112-register cap)
   if (ov && ov->epi_groups > 0) epi_groups = ov->epi_groups;
-  const int stats_bytes = (2 * 4 * epi_groups * 2 * N_tile * 4 + 1023) / 1024 * 1024;
-  const int hdr_bytes = kHeader + stats_bytes;
+  const int stats_bytes = (2 * 4 * epi_groups * 2 * cout_tile * 4 + 1023) / 1024 * 1024;
+  const int xch_bytes = hstack ? 2 * epi_groups * 5 * 48 * 4 : 0;
+  const int hdr_bytes = kHeader + stats_bytes + (xch_bytes + 1023) / 1024 * 1024;
 
   int TW = (W <= 126) ? W : ((W % 64 == 0) ? 64 : 126);
   if (ov && ov->TW > 0) TW = ov->TW;
   const int BW = TW + 2;
-  const int cap = max_mt * 128;
+  const int cap = max_mt * mt_stride;
   int NB = 1, TH;
   if (TW == W && (H + 2) * BW * 2 <= cap) {
     TH = H;
@@ -76,10 +88,10 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   if (ov && ov->TH > 0) TH = ov->TH;
   if (ov && ov->NB > 0) NB = ov->NB;
 
-  const int n_slots = (mode == CONV3) ? 9 : (mode == CONV1 ? 1 : (phase_grid ? 4 : 16));
+  const int n_slots = (mode == CONV3) ? (hstack ? 3 : 9) : (mode == CONV1 ? 1 : (phase_grid ? 4 : 9));
 
   // k-chunk depth and pipeline stages under the shared-memory limit
-  int CBK = 0, stages = 0;
+  int CBK = 0, stages = 0, b_resident = 0;
   for (;;) {
     const int BH = TH + 2;
     int cbs[4] = {8, 4, 2, 0};
@@ -93,13 +105,19 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
       const long a_st = ((long)NB * BH * BW * 16 * c + 127) / 128 * 128;   // TMA smem destinations are 128-B aligned
       const long b_st = (long)n_slots * (c / 2) * N_tile * 32;
       if ((long)NB * BH * BW * 16 >= (1 << 18)) continue;                 // LBO field is 14 bits of 16-byte units
-      // the stage ring runs across work items, so even single-chunk layers want >= 2 stages
-      const bool bres = (n_k == 1) && !phase_grid && (argmax_classes > 0 || cout <= N_tile);
+      // the stage ring runs across work items, so even single-chunk layers want >= 2 stages.
+      // Weights stay resident in smem (loaded once per CTA) when one CTA only ever needs one weight set
+      // and it leaves room for >= 2 activation stages.
+      const bool one_set = !phase_grid && (argmax_classes > 0 || cout <= cout_tile);
       const int s_hi = (ov && ov->stages > 0) ? ov->stages : (n_k == 1 ? 3 : 4);
       const int s_lo = (ov && ov->stages > 0) ? ov->stages : 2;
-      for (int s = s_hi; s >= s_lo && s >= 1; --s) {
-        const long tot = hdr_bytes + (bres ? s * a_st + b_st : s * (a_st + b_st)) + kSlack;
-        if (tot <= lim) { CBK = c; stages = s; found = true; break; }
+      for (int pass = 0; pass < 2 && !found; ++pass) {
+        const bool bres = (pass == 0) && one_set && (long)n_k * b_st <= 160 * 1024;
+        if (pass == 0 && !bres) continue;
+        for (int s = s_hi; s >= s_lo && s >= 1; --s) {
+          const long tot = hdr_bytes + (bres ? s * a_st + n_k * b_st : s * (a_st + b_st)) + kSlack;
+          if (tot <= lim) { CBK = c; stages = s; b_resident = bres ? 1 : 0; found = true; break; }
+        }
       }
     }
     if (found) break;
@@ -112,9 +130,11 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   g.TH = TH; g.TW = TW; g.NB = NB; g.BH = TH + 2; g.BW = BW;
   g.tiles_x = ceil_div(W, TW); g.tiles_y = ceil_div(H, TH);
   g.CBK = CBK; g.kch0 = cb0 / CBK; g.n_k = cbt / CBK;
-  g.N_tile = N_tile; g.n_ntiles = ceil_div(argmax_classes > 0 ? argmax_classes : cout, N_tile);
+  g.N_tile = N_tile; g.n_ntiles = ceil_div(argmax_classes > 0 ? argmax_classes : cout, cout_tile);
+  g.up_cols = up_cols; g.cout_tile = cout_tile;
   g.n_groups = G; g.n_slots = n_slots; g.phase_grid = phase_grid; g.stages = stages;
-  g.n_mtiles = ceil_div(((NB - 1) * g.BH + TH - 1) * BW + TW, 128);
+  g.n_mtiles = ceil_div(((NB - 1) * g.BH + TH - 1) * BW + TW, mt_stride);
+  g.hstack = hstack; g.mt_stride = mt_stride; g.xch_off = kHeader + stats_bytes;
   g.cb_stride_bytes = NB * g.BH * BW * 16;
   g.a_stage_bytes = g.cb_stride_bytes * CBK;
   g.a_stage_stride = (g.a_stage_bytes + 127) / 128 * 128;
@@ -124,17 +144,21 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   if (ov && ov->acc_bufs == 1) g.acc_bufs = 1;
   g.tmem_cols = pow2_cols(g.acc_bufs * cols);
   if (cols > 512) { set_error("plan_conv: TMEM budget exceeded"); return; }
-  g.b_resident = (g.n_k == 1 && g.n_ntiles == 1 && !phase_grid) ? 1 : 0;
+  g.b_resident = b_resident;
   g.epi_groups = epi_groups;
   g.ctas_per_sm = 1;
   g.a_off = hdr_bytes;
   g.magic_box = (unsigned)((0x100000000ULL + (unsigned long long)(g.BH * BW) - 1) / (unsigned long long)(g.BH * BW));
   g.magic_bw = (unsigned)((0x100000000ULL + (unsigned long long)BW - 1) / (unsigned long long)BW);
-  g.smem_bytes = hdr_bytes + stages * g.a_stage_stride + (g.b_resident ? 1 : stages) * g.b_stage_bytes + kSlack;
+  g.smem_bytes = hdr_bytes + stages * g.a_stage_stride + (g.b_resident ? g.n_k : stages) * g.b_stage_bytes + kSlack;
 
   for (int ph = 0; ph < 4; ++ph)
     for (int s = 0; s < kMaxSlots; ++s) g.slot_shift[ph][s] = 0;
-  if (mode == CONV3) {
+  if (hstack) {
+    for (int ky = 0; ky < 3; ++ky) {
+      g.slot_shift[0][ky] = (short)(ky * BW); g.slot_group[ky] = 0; g.slot_first[ky] = (ky == 0);
+    }
+  } else if (mode == CONV3 || up_cols) {
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx) {
         const int s = ky * 3 + kx;
@@ -148,13 +172,8 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
       for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b) {
           const short sh = (short)((py + a) * BW + (px + b));
-          if (phase_grid) {
-            const int s = a * 2 + b;
-            g.slot_shift[ph][s] = sh; g.slot_group[s] = 0; g.slot_first[s] = (s == 0);
-          } else {
-            const int s = ph * 4 + a * 2 + b;
-            g.slot_shift[0][s] = sh; g.slot_group[s] = (signed char)ph; g.slot_first[s] = (a == 0 && b == 0);
-          }
+          const int s = a * 2 + b;
+          g.slot_shift[ph][s] = sh; g.slot_group[s] = 0; g.slot_first[s] = (s == 0);
         }
     }
   }
@@ -187,12 +206,22 @@ void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& o
   out.assign((size_t)nz * g.n_ntiles * g.n_k * g.n_slots * k16pc * tile, to_act(0.f));
   const bool up = (L.mode == UPCONV3 || L.mode == DECONV4);
 
-  auto wval = [&](int z, int slot, int co, int ci) -> float {
+  auto wval = [&](int z, int slot, int co, int ci) -> float {   // co: row of the MMA weight tile
+    if (L.mode == CONV3 && g.hstack) {                       // row block kx of the weight tile, slot = ky
+      const int kx = co / g.cout_tile, c = co % g.cout_tile;
+      if (c >= cout) return 0.f;
+      return w[(((size_t)c * cin + ci) * 3 + slot) * 3 + kx];
+    }
     if (L.mode == CONV3) { const int ky = slot / 3, kx = slot % 3; return w[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx]; }
     if (L.mode == CONV1) return w[(size_t)co * cin + ci];
     int ph, a, b;
     if (g.phase_grid) { ph = z; a = slot >> 1; b = slot & 1; }
-    else { ph = slot >> 2; a = (slot >> 1) & 1; b = slot & 1; }
+    else {
+      // up_cols: slot = input shift (dy,dx) in box coordinates, row block of the weight tile = phase
+      ph = co / g.cout_tile; co = co % g.cout_tile;
+      a = slot / 3 - (ph >> 1); b = slot % 3 - (ph & 1);
+      if (a < 0 || a > 1 || b < 0 || b > 1) return 0.f;       // this phase does not read that shift
+    }
     const int py = ph >> 1, px = ph & 1;
     if (L.mode == UPCONV3) {
       int ky[2], kx[2], nky, nkx;
@@ -214,8 +243,8 @@ void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& o
         for (int slot = 0; slot < g.n_slots; ++slot)
           for (int j = 0; j < k16pc; ++j, base += tile)
             for (int nr = 0; nr < g.N_tile; ++nr) {
-              const int co = nt * g.N_tile + nr;
-              if (co >= cout) continue;
+              const int co = (g.up_cols || g.hstack) ? nr : nt * g.N_tile + nr;
+              if (!(g.up_cols || g.hstack) && co >= cout) continue;
               for (int k = 0; k < 16; ++k) {
                 const int ci = (kc * g.CBK + 2 * j) * 8 + k;
                 out[base + (size_t)(k >> 3) * (g.N_tile * 8) + (size_t)nr * 8 + (k & 7)] =

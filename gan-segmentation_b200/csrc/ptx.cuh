@@ -95,6 +95,19 @@ __device__ __forceinline__ void umma_f16kind(uint32_t d_tmem, uint64_t adesc, ui
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the descriptors given as (lo, hi) 32-bit halves: only the low word (start address) changes
+// between the MMAs of a k-chunk, so the issue loop does 32-bit adds only.
+__device__ __forceinline__ void umma_f16kind_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                  uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier when all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -138,6 +151,22 @@ __host__ __device__ inline uint32_t umma_idesc_16bit(uint32_t M, uint32_t N, uin
 }
 
 // ---------------------------------------------------------------- misc
+// One lane of a converged warp; lets the compiler keep the tcgen05 / TMA issue sequence in uniform
+// registers without wrapping every instruction in a per-thread loop (which `lane == 0` does).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// Keeps a loop-invariant value in a register (stops the compiler from re-loading it from the
+// constant bank inside the single-thread MMA issue loop, where every load is on the critical path).
+__device__ __forceinline__ void keep_in_reg(uint32_t& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void keep_in_reg(int& v) { asm volatile("" : "+r"(v)); }
+
 __device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"

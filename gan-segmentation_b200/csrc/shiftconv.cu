@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
   const int lane = threadIdx.x & 31;
   const int total_tiles = g.tiles_x * g.tiles_y * g.tiles_n * g.n_ntiles * (g.phase_grid ? 4 : 1);
   const int nbuf = g.acc_bufs;
-  const int cols_per_buf = g.n_groups * g.n_mtiles * g.N_tile;
+  const int cols_per_buf = g.n_mtiles * g.N_tile;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.stages; ++s) {
@@ -120,11 +120,11 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
 
   if (warp == 0) {
     // ================================ TMA producer =================================
-    if (lane == 0) {
+    if (elect_one()) {
       const size_t b_stage_elems = (size_t)(g.b_stage_bytes / 2);
-      if (g.b_resident) {
-        mbar_expect_tx(&hdr->bres_full, (uint32_t)g.b_stage_bytes);
-        bulk_load(b_base, p.wpack, (uint32_t)g.b_stage_bytes, &hdr->bres_full);
+      if (g.b_resident) {                                      // all k-chunks of the (single) weight set
+        mbar_expect_tx(&hdr->bres_full, (uint32_t)(g.n_k * g.b_stage_bytes));
+        bulk_load(b_base, p.wpack, (uint32_t)(g.n_k * g.b_stage_bytes), &hdr->bres_full);
       }
       const uint32_t stage_bytes = (uint32_t)(g.a_stage_bytes + (g.b_resident ? 0 : g.b_stage_bytes));
       int it = 0;
@@ -149,15 +149,22 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ===================================
-    const uint32_t idesc = umma_idesc_16bit(128, (uint32_t)g.N_tile, GSX_FP16 ? 0u : 1u);
-    const uint64_t a_hi = umma_desc_hi((uint32_t)g.cb_stride_bytes, 128);
-    const uint64_t b_hi = umma_desc_hi((uint32_t)g.N_tile * 16, 128);
-    const int k16_per_chunk = g.CBK >> 1;
-    const uint32_t b_tile_bytes = (uint32_t)g.N_tile * 32;
-    // hoist everything the issue loop needs into registers
-    const int n_k = g.n_k, stages = g.stages, n_slots = g.n_slots, n_mtiles = g.n_mtiles, b_res = g.b_resident;
-    const uint32_t a_stride = (uint32_t)g.a_stage_stride, b_stride = (uint32_t)g.b_stage_bytes;
-    const uint32_t cb_stride = (uint32_t)g.cb_stride_bytes, n_tile = (uint32_t)g.N_tile;
+    uint32_t idesc = umma_idesc_16bit(128, (uint32_t)g.N_tile, GSX_FP16 ? 0u : 1u);
+    uint32_t a_hi = (uint32_t)(umma_desc_hi((uint32_t)g.cb_stride_bytes, 128) >> 32);
+    uint32_t b_hi = (uint32_t)(umma_desc_hi((uint32_t)g.N_tile * 16, 128) >> 32);
+    const uint32_t a_lbo = (((uint32_t)g.cb_stride_bytes >> 4) & 0x3FFF) << 16;      // low-word part of the A descriptor
+    const uint32_t b_lbo = ((((uint32_t)g.N_tile * 16) >> 4) & 0x3FFF) << 16;
+    // hoist everything the issue loop needs into registers (and keep it there)
+    int n_k = g.n_k, stages = g.stages, n_slots = g.n_slots, n_mtiles = g.n_mtiles, k16_per_chunk = g.CBK >> 1;
+    const int b_res = g.b_resident;
+    uint32_t a_stride = (uint32_t)g.a_stage_stride, b_stride = (uint32_t)g.b_stage_bytes;
+    uint32_t kstep_desc = (2u * (uint32_t)g.cb_stride_bytes) >> 4;     // two channel blocks per k16 step, in 16-B units
+    uint32_t n_tile = (uint32_t)g.N_tile, b_tile_desc = ((uint32_t)g.N_tile * 32) >> 4;
+    uint32_t mt_desc = (uint32_t)g.mt_stride;                          // MMA-tile pitch in 16-B units (= positions)
+    keep_in_reg(mt_desc);
+    keep_in_reg(idesc); keep_in_reg(a_hi); keep_in_reg(b_hi); keep_in_reg(n_k); keep_in_reg(stages); keep_in_reg(n_slots);
+    keep_in_reg(n_mtiles); keep_in_reg(k16_per_chunk); keep_in_reg(a_stride); keep_in_reg(b_stride);
+    keep_in_reg(kstep_desc); keep_in_reg(n_tile); keep_in_reg(b_tile_desc);
     const uint32_t a_smem = smem_u32(a_base), b_smem = smem_u32(b_base);
     if (g.b_resident) mbar_wait(&hdr->bres_full, 0);
     int it = 0, tl = 0;
@@ -173,19 +180,18 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         const int s = it % stages;
         mbar_wait(&hdr->full[s], (uint32_t)((it / stages) & 1));
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = a_smem + (uint32_t)s * a_stride;
-          uint32_t b_addr = b_smem + (b_res ? 0u : (uint32_t)s * b_stride);
+        if (elect_one()) {
+          // descriptor low words: start address (16-B units) | LBO << 16
+          const uint32_t a_lo0 = (((a_smem + (uint32_t)s * a_stride) >> 4) & 0x3FFF) | a_lbo;
+          uint32_t b_lo = (((b_smem + (uint32_t)(b_res ? kc : s) * b_stride) >> 4) & 0x3FFF) | b_lbo;
           for (int slot = 0; slot < n_slots; ++slot) {
-            const int4 tp = taps[slot];                            // {shift bytes, group, first, -}
-            const uint32_t d0 = acc_base + (uint32_t)(tp.y * n_mtiles) * n_tile;
-            for (int j = 0; j < k16_per_chunk; ++j, b_addr += b_tile_bytes) {
-              const uint64_t bdesc = umma_desc(b_hi, b_addr);
+            const int4 tp = taps[slot];                            // {shift bytes, -, first, -}
+            uint32_t a_k = a_lo0 + ((uint32_t)tp.x >> 4);
+            for (int j = 0; j < k16_per_chunk; ++j, b_lo += b_tile_desc, a_k += kstep_desc) {
               const uint32_t acc = (kc > 0 || j > 0 || !tp.z) ? 1u : 0u;
-              uint64_t adesc = umma_desc(a_hi, a_addr + (uint32_t)(2 * j) * cb_stride + (uint32_t)tp.x);
-              uint32_t d = d0;
-              for (int mt = 0; mt < n_mtiles; ++mt, adesc += 128 /* 2048 B >> 4 */, d += n_tile)
-                umma_f16kind(d, adesc, bdesc, idesc, acc);
+              uint32_t a_lo = a_k, d = acc_base;
+              for (int mt = 0; mt < n_mtiles; ++mt, a_lo += mt_desc, d += n_tile)
+                umma_f16kind_lohi(d, a_lo, a_hi, b_lo, b_hi, idesc, acc);
             }
           }
           umma_commit(&hdr->empty[s]);
@@ -204,10 +210,38 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     const bool do_stats = (e.flags & EPI_STATS) != 0;
     const bool do_act = (e.flags & EPI_LRELU) != 0;
     const size_t plane_out = (size_t)e.Ho * e.Wo;
-    const int n_chunks = g.N_tile >> 4;
-    const int n_units = g.n_groups * g.n_mtiles;
-    const int slot_floats = 2 * g.N_tile;
+    const int n_chunks = g.hstack ? (g.cout_tile >> 4) : (g.N_tile >> 4);
+    const int cpp = g.cout_tile >> 4;             // 16-channel chunks per phase block (== n_chunks unless up_cols)
+    const int n_units = g.n_mtiles;
+    const int slot_floats = 2 * g.cout_tile;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+
+    // hstack: out[q] = acc[q][0] + acc[q+1][1] + acc[q+2][2].  Rows q+1, q+2 live in the next lanes (shuffle) or,
+    // for lanes 30/31, in the next warp quarter: lanes 0/1 of every quarter publish the values their lower
+    // neighbour needs through a small double-buffered smem area, one 128-thread named barrier per unit.
+    float* xch = reinterpret_cast<float*>(smem + g.xch_off) + (size_t)egrp * 5 * 48;       // [parity][G][5][48]
+    int xparity = 0;
+    auto hstack_combine = [&](uint32_t (&v)[16], const uint32_t (&v1)[16], const uint32_t (&v2)[16]) {
+      float* mine = xch + (size_t)xparity * G * 5 * 48 + quarter * 48;
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { mine[i] = __uint_as_float(v1[i]); mine[16 + i] = __uint_as_float(v2[i]); }
+      } else if (lane == 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mine[32 + i] = __uint_as_float(v2[i]);
+      }
+      named_bar_sync(2 + egrp, 128);
+      const float* nb = mine + 48;                          // next quarter (quarter 3 reads an unused pad: its
+#pragma unroll                                              //   lanes 30/31 are rows 126/127, never output)
+      for (int i = 0; i < 16; ++i) {
+        float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[i]), 1);
+        float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 2);
+        if (lane == 31) { a1 = nb[i]; a2 = nb[32 + i]; }
+        if (lane == 30) a2 = nb[16 + i];
+        v[i] = __float_as_uint(__uint_as_float(v[i]) + a1 + a2);
+      }
+      xparity ^= 1;
+    };
 
     int tl = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
@@ -218,25 +252,36 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         for (int i = lane; i < slot_floats; i += 32) my_slot[i] = 0.f;
         __syncwarp();
       }
-      mbar_wait(&hdr->tmem_full[buf], (uint32_t)((tl / nbuf) & 1));
-      tc_fence_after();
+      bool waited = false;
+      if (e.flags & EPI_ARGMAX) {
+        mbar_wait(&hdr->tmem_full[buf], (uint32_t)((tl / nbuf) & 1));
+        tc_fence_after();
+        waited = true;
+      }
       const uint32_t acc_base = tmem_base + (uint32_t)(buf * cols_per_buf) + lane_base;
 
       // position of this thread's row inside MMA tile `mt`:  q = mt*128 + row  ->  (nb, yl, xl)
       auto locate = [&](int mt, int& n, int& y, int& x) -> bool {
-        const int q = mt * 128 + row;
+        const int q = mt * g.mt_stride + row;
         const int nb = (int)__umulhi((uint32_t)q, g.magic_box);
         const int rem = q - nb * (g.BH * g.BW);
         const int yl = (int)__umulhi((uint32_t)rem, g.magic_bw);
         const int xl = rem - yl * g.BW;
         n = tc.n0 + nb; y = tc.y0 + yl; x = tc.x0 + xl;
-        return nb < g.NB && yl < g.TH && xl < g.TW && n < g.N && y < g.H && x < g.W;
+        return row < g.mt_stride && nb < g.NB && yl < g.TH && xl < g.TW && n < g.N && y < g.H && x < g.W;
       };
 
       if (e.flags & EPI_ARGMAX) {
         for (int mt = egrp; mt < g.n_mtiles; mt += G) {
           uint32_t v[16];
           tmem_ld16(acc_base + (uint32_t)(mt * g.N_tile), v);
+          if (g.hstack) {
+            uint32_t v1[16], v2[16];
+            tmem_ld16(acc_base + (uint32_t)(mt * g.N_tile + g.cout_tile), v1);
+            tmem_ld16(acc_base + (uint32_t)(mt * g.N_tile + 2 * g.cout_tile), v2);
+            tmem_ld_wait();
+            hstack_combine(v, v1, v2);
+          }
           tmem_ld_wait();
           int n, y, x;
           if (locate(mt, n, y, x)) {
@@ -257,7 +302,9 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         }
       } else {
         for (int cc = 0; cc < n_chunks; ++cc) {
-          const int c0 = tc.ntile * g.N_tile + cc * 16;          // first output channel of this chunk
+          const int ph = g.up_cols ? cc / cpp : tc.phase;        // output phase of this column chunk
+          const int cl = (cc - (g.up_cols ? ph * cpp : 0)) * 16; // first channel of the chunk inside the CTA's block
+          const int c0 = tc.ntile * g.cout_tile + cl;            // first output channel of this chunk
           float bias_r[16], ns_r[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -268,29 +315,54 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
 
-          // units (accumulator group, MMA tile) of this chunk are dealt round-robin to the G warps of a quarter
-          for (int u = (egrp + cc) % G; u < n_units; u += G) {
-            const int grp = u / g.n_mtiles, mt = u - grp * g.n_mtiles;
-            const int ph = g.phase_grid ? tc.phase : grp;
-            uint32_t v[16];
-            tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + cc * 16), v);
-            int n, y, x;
-            const bool valid = locate(mt, n, y, x);
-            if (e.up) { y = 2 * y + (ph >> 1); x = 2 * x + (ph & 1); }
-            const size_t pix = (size_t)y * e.Wo + x;
-            float nz = 0.f;
-            uint4 add0 = make_uint4(0, 0, 0, 0), add1 = add0;
-            if (valid) {                                          // issue the global loads before waiting on TMEM
-              if (e.noise) nz = __ldg(e.noise + (size_t)n * plane_out + pix);
+          // MMA tiles are dealt round-robin to the G warps of a quarter.  The global operands of a unit (its noise
+          // value, its residual vectors) are requested one unit ahead, so their latency overlaps the previous
+          // unit's work instead of stalling every unit (the first request of a tile is issued before the
+          // accumulators are even ready).
+          struct Pre { int n, y, x; bool valid; size_t pix; float nz; uint4 add0, add1; };
+          auto prefetch = [&](int mt) -> Pre {
+            Pre q;
+            q.valid = locate(mt, q.n, q.y, q.x);
+            if (e.up) { q.y = 2 * q.y + (ph >> 1); q.x = 2 * q.x + (ph & 1); }
+            q.pix = (size_t)q.y * e.Wo + q.x;
+            q.nz = 0.f;
+            q.add0 = make_uint4(0, 0, 0, 0); q.add1 = q.add0;
+            if (q.valid) {
+              if (e.noise) q.nz = __ldg(e.noise + (size_t)q.n * plane_out + q.pix);
               if (e.addsrc) {
                 const size_t plane_lo = (size_t)(e.Ho >> 1) * (e.Wo >> 1);
-                const size_t pl = (size_t)(y >> 1) * (e.Wo >> 1) + (x >> 1);
-                const act_t* ap = e.addsrc + (((size_t)(c0 >> 3) * g.N + n) * plane_lo + pl) * 8;
-                add0 = __ldg(reinterpret_cast<const uint4*>(ap));
-                add1 = __ldg(reinterpret_cast<const uint4*>(ap + (size_t)g.N * plane_lo * 8));
+                const size_t pl = (size_t)(q.y >> 1) * (e.Wo >> 1) + (q.x >> 1);
+                const act_t* ap = e.addsrc + (((size_t)(c0 >> 3) * g.N + q.n) * plane_lo + pl) * 8;
+                q.add0 = __ldg(reinterpret_cast<const uint4*>(ap));
+                q.add1 = __ldg(reinterpret_cast<const uint4*>(ap + (size_t)g.N * plane_lo * 8));
               }
             }
+            return q;
+          };
+          Pre nxt = prefetch(egrp < n_units ? egrp : 0);
+          if (cc == 0 && !waited) {                               // operands of the first unit are in flight: now wait
+            mbar_wait(&hdr->tmem_full[buf], (uint32_t)((tl / nbuf) & 1));
+            tc_fence_after();
+            waited = true;
+          }
+          for (int u = egrp; u < n_units; u += G) {
+            const int mt = u;
+            const Pre cur = nxt;
+            uint32_t v[16], v1[16], v2[16];
+            tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + cc * 16), v);
+            if (g.hstack) {
+              tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + g.cout_tile + cc * 16), v1);
+              tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + 2 * g.cout_tile + cc * 16), v2);
+            }
+            if (u + G < n_units) nxt = prefetch(u + G);
+            const bool valid = cur.valid;
+            const int n = cur.n;
+            const size_t pix = cur.pix;
+            const float nz = cur.nz;
+            const uint4 add0 = cur.add0, add1 = cur.add1;
+            (void)mt;
             tmem_ld_wait();
+            if (g.hstack) hstack_combine(v, v1, v2);
             if (valid) {
               float f[16];
 #pragma unroll
@@ -341,7 +413,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
               }
             }
             // value index = lane: 0..15 channel sums, 16..31 sums of squares; this warp's own slot: plain add
-            my_slot[(cc * 16 + (lane & 15)) * 2 + (lane >> 4)] += vals[0];
+            my_slot[(cl + (lane & 15)) * 2 + (lane >> 4)] += vals[0];
           }
         }
       }
@@ -357,7 +429,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         // order + one partial per (sample, tile): bit-reproducible, finalize_kernel adds the tiles up.
         const float* slots = stats_slots + (size_t)(tl & 1) * kEpiWarps * slot_floats;
         for (int i = threadIdx.x - 64; i < slot_floats; i += kEpiThreads) {
-          const int ch = tc.ntile * g.N_tile + (i >> 1);
+          const int ch = tc.ntile * g.cout_tile + (i >> 1);
           float s = 0.f;
 #pragma unroll
           for (int w = 0; w < kEpiWarps; ++w) s += slots[w * slot_floats + i];

@@ -50,6 +50,7 @@ typedef struct {
 typedef struct {
   int TH, TW, NB, CBK, N_tile, stages, phase_grid;     /* 0 (phase_grid: -1) keeps the planner's choice */
   int epi_groups, acc_bufs, max_mtiles;
+  int hstack;                                         /* -1 keeps the planner's choice */
 } gsx_plan_override;
 
 const char* gsx_last_error(void);
