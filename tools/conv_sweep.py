@@ -18,6 +18,8 @@ from gan_segmentation_b200 import _lib as L, ops  # noqa: E402
 # name: (mode, cin0, cin1, cout, H, W, flags, extras)
 LAYERS = {
     'g10.conv2': ('CONV3', 16, 0, 16, 1024, 1024, 'gen'),
+    'g10.conv2.nonoise': ('CONV3', 16, 0, 16, 1024, 1024, 'gen_nonoise'),
+    'g10.conv2.nostats': ('CONV3', 16, 0, 16, 1024, 1024, 'gen_nostats'),
     'g9.conv2': ('CONV3', 32, 0, 32, 512, 512, 'gen'),
     'g8.conv2': ('CONV3', 64, 0, 64, 256, 256, 'gen'),
     'g7.conv2': ('CONV3', 128, 0, 128, 128, 128, 'gen'),
@@ -51,6 +53,11 @@ def run(name, n, override, repeat, dtype):
     if kind == 'gen':
         kw = dict(bias=torch.randn(co).cuda(), nscale=torch.randn(co).cuda(), noise=torch.randn((n, 1, ho, wo)).cuda(),
                   flags=L.EPI_LRELU | L.EPI_STATS)
+    elif kind == 'gen_nonoise':
+        kw = dict(bias=torch.randn(co).cuda(), flags=L.EPI_LRELU | L.EPI_STATS)
+    elif kind == 'gen_nostats':
+        kw = dict(bias=torch.randn(co).cuda(), nscale=torch.randn(co).cuda(), noise=torch.randn((n, 1, ho, wo)).cuda(),
+                  flags=L.EPI_LRELU)
     elif kind == 'dec':
         kw = dict(bias=torch.randn(co).cuda(), flags=L.EPI_LRELU)
     elif kind == 'res':
