@@ -116,6 +116,15 @@ static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1
   make_act_tensormap(&p.tm[0], x0, L.cin0, N, L.H, L.W, p.g.BW, p.g.BH, p.g.NB, p.g.CBK);
   if (L.cin1 > 0) make_act_tensormap(&p.tm[1], x1, L.cin1, N, L.H, L.W, p.g.BW, p.g.BH, p.g.NB, p.g.CBK);
   else p.tm[1] = p.tm[0];
+  if (p.g.aux_kind == 1) {
+    if (!epi.noise) p.g.aux_kind = 0;
+    else make_noise_tensormap(&p.tm_aux, epi.noise, N, epi.Ho, epi.Wo, p.g.TW, p.g.TH, p.g.NB);
+  } else if (p.g.aux_kind == 2) {
+    if (!epi.addsrc) p.g.aux_kind = 0;
+    else make_act_tensormap(&p.tm_aux, epi.addsrc, L.cout, N, epi.Ho / 2, epi.Wo / 2, p.g.aux_bw, p.g.aux_bh, p.g.NB,
+                            p.g.cout_tile / 8);
+  }
+  if (!p.g.aux_kind) p.tm_aux = p.tm[0];
   if (*last_error_cstr()) return false;
   launch_shiftconv(p, st);
   g_launches++;
@@ -379,7 +388,7 @@ extern "C" int gsx_synth_finalize(gsx_synth* h) {
       std::vector<float> ws(w->v);
       for (auto& x : ws) x *= std_;
       set_error("");
-      plan_conv(b.conv2, CONV3, b.H, b.W, b.C, 0, b.C, 0, nullptr);
+      plan_conv(b.conv2, CONV3, b.H, b.W, b.C, 0, b.C, 0, nullptr, /*aux: noise tile*/ 1);
       if (*gsx_last_error()) return -1;
       if (!upload_conv(b.conv2, ws.data())) return -2;
     }
@@ -681,7 +690,7 @@ extern "C" int gsx_dec_finalize(gsx_dec* d) {
       l.b_a = dev_upload(b);
       if (!fold_conv_bn(P, mb + ".base_layers." + std::to_string(j_b), bn ? mb + ".base_layers." + std::to_string(j_b + 1) : "",
                         l.fnext, (size_t)l.fnext * 9, w, b)) return -1;
-      plan_conv(l.conv_b, CONV3, l.H * 2, l.W * 2, l.fnext, 0, l.fnext, 0, nullptr);
+      plan_conv(l.conv_b, CONV3, l.H * 2, l.W * 2, l.fnext, 0, l.fnext, 0, nullptr, /*aux: residual tile*/ 2);
       if (*gsx_last_error()) return -1;
       if (!upload_conv(l.conv_b, w.data())) return -2;
       l.b_b = dev_upload(b);

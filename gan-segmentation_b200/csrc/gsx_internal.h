@@ -86,6 +86,11 @@ struct ConvGeom {
   int mt_stride;               // positions between consecutive MMA tiles: 128, or 126 with hstack (rows 126,127 of
                                //    a tile only feed rows 124,125 and are recomputed as rows 0,1 of the next tile)
   int xch_off;                 // byte offset of the hstack exchange buffer in dynamic smem
+  int aux_kind;                // epilogue operand staged per tile by TMA into smem (2 buffers): 0 none,
+                               //   1 = noise plane tile [NB][TH][TW] fp32, 2 = residual tile (blocked, half resolution)
+  int aux_off, aux_bytes;      // smem offset of the 2 aux buffers, bytes per buffer (128-aligned)
+  int aux_bytes_tx;            // bytes one TMA box delivers (the mbarrier transaction count)
+  int aux_bw, aux_bh;          // residual box: columns / rows at half resolution
   int n_slots;                 // filter taps per CTA
   int phase_grid;              // 1: blockIdx.z selects the phase (wide up-convs)
   int stages;
@@ -124,6 +129,7 @@ struct ConvEpi {
 
 struct ConvParams {
   CUtensorMap tm[2];
+  CUtensorMap tm_aux;          // noise (3-D fp32) or residual (4-D blocked) tensor map when g.aux_kind != 0
   ConvGeom g;
   ConvEpi e;
   const act_t* wpack;
@@ -153,7 +159,8 @@ struct PlanOverride {
 
 // plan.cpp
 void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cout, int argmax_classes,
-               const PlanOverride* ov);
+               const PlanOverride* ov, int aux_kind = 0);
+void make_noise_tensormap(CUtensorMap* tm, const void* base, int N, int H, int W, int boxW, int boxH, int boxN);
 void finish_geom_for_batch(ConvGeom& g, int N);
 // weights: CONV3/UPCONV3 (Cout,Cin,3,3); DECONV4 (Cin,Cout,4,4); CONV1/UPCONV1 (Cout,Cin,1,1); fp32, already
 // scaled (wscale / BN folded).  Returns packed act_t host buffer in the order the kernel streams it.

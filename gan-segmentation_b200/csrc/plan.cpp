@@ -31,7 +31,7 @@ static int pow2_cols(int c) {
 }
 
 void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cout, int argmax_classes,
-               const PlanOverride* ov) {
+               const PlanOverride* ov, int aux_kind) {
   L.mode = mode; L.H = H; L.W = W; L.cin0 = cin0; L.cin1 = cin1; L.cout = cout;
   ConvGeom& g = L.g;
   std::memset(&g, 0, sizeof(g));
@@ -90,10 +90,15 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
 
   const int n_slots = (mode == CONV3) ? (hstack ? 3 : 9) : (mode == CONV1 ? 1 : (phase_grid ? 4 : 9));
 
+  if (mode != CONV3 || (W * 4) % 16 != 0 || (TW & 1)) aux_kind = 0;       // aux staging: plain 3x3 layers only
   // k-chunk depth and pipeline stages under the shared-memory limit
   int CBK = 0, stages = 0, b_resident = 0;
+  long aux_bytes = 0;
   for (;;) {
     const int BH = TH + 2;
+    aux_bytes = aux_kind == 1 ? (long)NB * TH * TW * 4
+              : aux_kind == 2 ? (long)NB * (TH / 2 + 1) * (TW / 2) * 16 * (cout_tile / 8) : 0;
+    aux_bytes = (aux_bytes + 127) / 128 * 128;
     int cbs[4] = {8, 4, 2, 0};
     if (ov && ov->CBK > 0) { cbs[0] = ov->CBK; cbs[1] = 0; }
     bool found = false;
@@ -115,7 +120,7 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
         const bool bres = (pass == 0) && one_set && (long)n_k * b_st <= 160 * 1024;
         if (pass == 0 && !bres) continue;
         for (int s = s_hi; s >= s_lo && s >= 1; --s) {
-          const long tot = hdr_bytes + (bres ? s * a_st + n_k * b_st : s * (a_st + b_st)) + kSlack;
+          const long tot = hdr_bytes + 2 * aux_bytes + (bres ? s * a_st + n_k * b_st : s * (a_st + b_st)) + kSlack;
           if (tot <= lim) { CBK = c; stages = s; b_resident = bres ? 1 : 0; found = true; break; }
         }
       }
@@ -147,10 +152,13 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   g.b_resident = b_resident;
   g.epi_groups = epi_groups;
   g.ctas_per_sm = 1;
-  g.a_off = hdr_bytes;
+  g.aux_kind = aux_kind; g.aux_off = hdr_bytes; g.aux_bytes = (int)aux_bytes;
+  g.aux_bw = TW / 2; g.aux_bh = TH / 2 + 1;
+  g.aux_bytes_tx = aux_kind == 1 ? NB * TH * TW * 4 : aux_kind == 2 ? NB * (TH / 2 + 1) * (TW / 2) * 16 * (cout_tile / 8) : 0;
+  g.a_off = hdr_bytes + 2 * (int)aux_bytes;
   g.magic_box = (unsigned)((0x100000000ULL + (unsigned long long)(g.BH * BW) - 1) / (unsigned long long)(g.BH * BW));
   g.magic_bw = (unsigned)((0x100000000ULL + (unsigned long long)BW - 1) / (unsigned long long)BW);
-  g.smem_bytes = hdr_bytes + stages * g.a_stage_stride + (g.b_resident ? g.n_k : stages) * g.b_stage_bytes + kSlack;
+  g.smem_bytes = g.a_off + stages * g.a_stage_stride + (g.b_resident ? g.n_k : stages) * g.b_stage_bytes + kSlack;
 
   for (int ph = 0; ph < 4; ++ph)
     for (int s = 0; s < kMaxSlots; ++s) g.slot_shift[ph][s] = 0;
@@ -268,6 +276,23 @@ static EncodeTiledFn encode_fn() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   });
   return fn;
+}
+
+void make_noise_tensormap(CUtensorMap* tm, const void* base, int N, int H, int W, int boxW, int boxH, int boxN) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return; }
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, (cuuint32_t)boxN};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled (noise) failed (%d) N=%d H=%d W=%d box=%dx%dx%d", (int)r, N, H, W, boxW, boxH, boxN);
+    set_error(buf);
+  }
 }
 
 void make_act_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, int W, int boxW, int boxH, int boxN,

@@ -36,6 +36,8 @@ struct __align__(16) SmemHeader {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t bres_full;
+  uint64_t aux_full[2];
+  uint64_t aux_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
   int4 taps[4 * kMaxSlots];   // copy of ConvParams::taps
@@ -104,9 +106,14 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
       mbar_init(&hdr->tmem_empty[b], kEpiWarps);
     }
     mbar_init(&hdr->bres_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&hdr->aux_full[b], 1);
+      mbar_init(&hdr->aux_empty[b], kEpiWarps);
+    }
     fence_barrier_init();
     tma_prefetch_desc(&p.tm[0]);
     if (g.kch0 < g.n_k) tma_prefetch_desc(&p.tm[1]);
+    if (g.aux_kind) tma_prefetch_desc(&p.tm_aux);
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + 4 * kMaxSlots) hdr->taps[threadIdx.x - 64] = __ldg(p.taps + threadIdx.x - 64);
   if (warp == 1) {
@@ -127,9 +134,18 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         bulk_load(b_base, p.wpack, (uint32_t)(g.n_k * g.b_stage_bytes), &hdr->bres_full);
       }
       const uint32_t stage_bytes = (uint32_t)(g.a_stage_bytes + (g.b_resident ? 0 : g.b_stage_bytes));
-      int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int it = 0, tlp = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tlp) {
         const TileCoord tc = decode_tile(g, t);
+        if (g.aux_kind) {
+          // per-tile epilogue operand (noise plane tile / residual tile), double buffered on its own barriers
+          const int ab = tlp & 1;
+          if (tlp >= 2) mbar_wait(&hdr->aux_empty[ab], (uint32_t)(((tlp >> 1) - 1) & 1));
+          mbar_expect_tx(&hdr->aux_full[ab], (uint32_t)g.aux_bytes_tx);
+          uint8_t* dst = smem + g.aux_off + (size_t)ab * g.aux_bytes;
+          if (g.aux_kind == 1) tma_load_3d(dst, &p.tm_aux, &hdr->aux_full[ab], tc.x0, tc.y0, tc.n0);
+          else tma_load_4d(dst, &p.tm_aux, &hdr->aux_full[ab], (tc.x0 >> 1) * 2, tc.y0 >> 1, tc.n0, tc.ntile * (g.cout_tile >> 3));
+        }
         const act_t* wsrc = p.wpack + ((size_t)(tc.phase * g.n_ntiles + tc.ntile) * g.n_k) * b_stage_elems;
         for (int kc = 0; kc < g.n_k; ++kc, ++it) {
           const int s = it % g.stages;
@@ -252,21 +268,22 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         for (int i = lane; i < slot_floats; i += 32) my_slot[i] = 0.f;
         __syncwarp();
       }
-      bool waited = false;
-      if (e.flags & EPI_ARGMAX) {
-        mbar_wait(&hdr->tmem_full[buf], (uint32_t)((tl / nbuf) & 1));
-        tc_fence_after();
-        waited = true;
-      }
+      mbar_wait(&hdr->tmem_full[buf], (uint32_t)((tl / nbuf) & 1));
+      tc_fence_after();
+      const int ab = tl & 1;
+      const uint8_t* aux = smem + g.aux_off + (size_t)ab * g.aux_bytes;
+      if (g.aux_kind) mbar_wait(&hdr->aux_full[ab], (uint32_t)((tl >> 1) & 1));
       const uint32_t acc_base = tmem_base + (uint32_t)(buf * cols_per_buf) + lane_base;
 
       // position of this thread's row inside MMA tile `mt`:  q = mt*128 + row  ->  (nb, yl, xl)
+      int nb_l = 0, yl_l = 0, xl_l = 0;            // tile-local coordinates of the last located row
       auto locate = [&](int mt, int& n, int& y, int& x) -> bool {
         const int q = mt * g.mt_stride + row;
         const int nb = (int)__umulhi((uint32_t)q, g.magic_box);
         const int rem = q - nb * (g.BH * g.BW);
         const int yl = (int)__umulhi((uint32_t)rem, g.magic_bw);
         const int xl = rem - yl * g.BW;
+        nb_l = nb; yl_l = yl; xl_l = xl;
         n = tc.n0 + nb; y = tc.y0 + yl; x = tc.x0 + xl;
         return row < g.mt_stride && nb < g.NB && yl < g.TH && xl < g.TW && n < g.N && y < g.H && x < g.W;
       };
@@ -315,52 +332,44 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
 
-          // MMA tiles are dealt round-robin to the G warps of a quarter.  The global operands of a unit (its noise
-          // value, its residual vectors) are requested one unit ahead, so their latency overlaps the previous
-          // unit's work instead of stalling every unit (the first request of a tile is issued before the
-          // accumulators are even ready).
-          struct Pre { int n, y, x; bool valid; size_t pix; float nz; uint4 add0, add1; };
-          auto prefetch = [&](int mt) -> Pre {
-            Pre q;
-            q.valid = locate(mt, q.n, q.y, q.x);
-            if (e.up) { q.y = 2 * q.y + (ph >> 1); q.x = 2 * q.x + (ph & 1); }
-            q.pix = (size_t)q.y * e.Wo + q.x;
-            q.nz = 0.f;
-            q.add0 = make_uint4(0, 0, 0, 0); q.add1 = q.add0;
-            if (q.valid) {
-              if (e.noise) q.nz = __ldg(e.noise + (size_t)q.n * plane_out + q.pix);
-              if (e.addsrc) {
-                const size_t plane_lo = (size_t)(e.Ho >> 1) * (e.Wo >> 1);
-                const size_t pl = (size_t)(q.y >> 1) * (e.Wo >> 1) + (q.x >> 1);
-                const act_t* ap = e.addsrc + (((size_t)(c0 >> 3) * g.N + q.n) * plane_lo + pl) * 8;
-                q.add0 = __ldg(reinterpret_cast<const uint4*>(ap));
-                q.add1 = __ldg(reinterpret_cast<const uint4*>(ap + (size_t)g.N * plane_lo * 8));
-              }
-            }
-            return q;
-          };
-          Pre nxt = prefetch(egrp < n_units ? egrp : 0);
-          if (cc == 0 && !waited) {                               // operands of the first unit are in flight: now wait
-            mbar_wait(&hdr->tmem_full[buf], (uint32_t)((tl / nbuf) & 1));
-            tc_fence_after();
-            waited = true;
-          }
+          // MMA tiles are dealt round-robin to the G warps of a quarter.  The per-pixel operands of the epilogue
+          // (noise value, residual vectors) come from the tile the producer staged in smem by TMA; the global
+          // loads below are only the fallback for layers the planner could not stage.
           for (int u = egrp; u < n_units; u += G) {
             const int mt = u;
-            const Pre cur = nxt;
             uint32_t v[16], v1[16], v2[16];
             tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + cc * 16), v);
             if (g.hstack) {
               tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + g.cout_tile + cc * 16), v1);
               tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + 2 * g.cout_tile + cc * 16), v2);
             }
-            if (u + G < n_units) nxt = prefetch(u + G);
-            const bool valid = cur.valid;
-            const int n = cur.n;
-            const size_t pix = cur.pix;
-            const float nz = cur.nz;
-            const uint4 add0 = cur.add0, add1 = cur.add1;
-            (void)mt;
+            int n, y, x;
+            const bool valid = locate(mt, n, y, x);
+            if (e.up) { y = 2 * y + (ph >> 1); x = 2 * x + (ph & 1); }
+            const size_t pix = (size_t)y * e.Wo + x;
+            float nz = 0.f;
+            uint4 add0 = make_uint4(0, 0, 0, 0), add1 = add0;
+            if (valid) {
+              if (g.aux_kind == 1) {
+                nz = reinterpret_cast<const float*>(aux)[(nb_l * g.TH + yl_l) * g.TW + xl_l];
+              } else if (e.noise) {
+                nz = __ldg(e.noise + (size_t)n * plane_out + pix);
+              }
+              if (g.aux_kind == 2) {
+                // residual tile [cb][nb][row/2][col/2] of 16-B vectors at half resolution
+                const int yy = (y >> 1) - (tc.y0 >> 1), xx = (x >> 1) - (tc.x0 >> 1);
+                const uint4* ap = reinterpret_cast<const uint4*>(aux) +
+                                  ((size_t)((cl >> 3) * g.NB + nb_l) * g.aux_bh + yy) * g.aux_bw + xx;
+                add0 = ap[0];
+                add1 = ap[(size_t)g.NB * g.aux_bh * g.aux_bw];
+              } else if (e.addsrc) {
+                const size_t plane_lo = (size_t)(e.Ho >> 1) * (e.Wo >> 1);
+                const size_t pl = (size_t)(y >> 1) * (e.Wo >> 1) + (x >> 1);
+                const act_t* ap = e.addsrc + (((size_t)(c0 >> 3) * g.N + n) * plane_lo + pl) * 8;
+                add0 = __ldg(reinterpret_cast<const uint4*>(ap));
+                add1 = __ldg(reinterpret_cast<const uint4*>(ap + (size_t)g.N * plane_lo * 8));
+              }
+            }
             tmem_ld_wait();
             if (g.hstack) hstack_combine(v, v1, v2);
             if (valid) {
@@ -370,7 +379,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
                 const float a = fmaf(ns_r[i], nz, __uint_as_float(v[i]) + bias_r[i]);
                 f[i] = do_act ? lrelu02(a) : a;
               }
-              if (e.addsrc) {
+              if (e.addsrc || g.aux_kind == 2) {
                 const uint32_t w8[8] = {add0.x, add0.y, add0.z, add0.w, add1.x, add1.y, add1.z, add1.w};
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -421,7 +430,10 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
       // accumulator buffer drained -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&hdr->tmem_empty[buf]);
+      if (lane == 0) {
+        mbar_arrive(&hdr->tmem_empty[buf]);
+        if (g.aux_kind) mbar_arrive(&hdr->aux_empty[ab]);
+      }
 
       if (do_stats) {
         named_bar_sync(1, kEpiThreads);                          // all epilogue warps finished this tile
