@@ -169,6 +169,7 @@ struct gsx_synth {
   float *d_latent_avg = nullptr, *d_psi = nullptr, *d_wrgb = nullptr, *d_brgb = nullptr;
   act_t* d_const = nullptr;
   int last_n = 0;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};   // gsx_generate_host pipelining
 
   int nf(int r) const {
     const int f = (int)(cfg.fmap_base / std::pow(2.0, (r - 1) * (double)cfg.fmap_decay));
@@ -263,6 +264,7 @@ extern "C" int gsx_synth_create(const gsx_synth_cfg* cfg, gsx_synth** out) {
 
 extern "C" void gsx_synth_destroy(gsx_synth* h) {
   if (!h) return;
+  for (int i = 0; i < 2; ++i) { if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); }
   for (int i = 0; i < 8; ++i) { cudaFree(h->d_map_w[i]); cudaFree(h->d_map_b[i]); }
   cudaFree(h->d_aff_w); cudaFree(h->d_aff_b); cudaFree(h->d_unit_layer); cudaFree(h->d_latent_avg);
   cudaFree(h->d_psi); cudaFree(h->d_wrgb); cudaFree(h->d_brgb); cudaFree(h->d_const);
@@ -798,19 +800,30 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
 extern "C" int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z_host, const float* psi_host,
                                  uint64_t seed, uint64_t first_sample, uint8_t* img_u8_host, uint8_t* mask_host,
                                  void* synth_ws, size_t synth_ws_bytes, void* dec_ws, size_t dec_ws_bytes,
-                                 void* stage_dev, size_t stage_bytes, gsx_stream stream) {
-  if (!s || !d || !stage_dev) { set_error("bad argument"); return -1; }
+                                 void* stage_dev, size_t stage_bytes, gsx_stream stream, gsx_stream copy_stream,
+                                 int slot) {
+  if (!s || !d || !stage_dev || slot < 0 || slot > 1) { set_error("bad argument"); return -1; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaStream_t cs = copy_stream ? static_cast<cudaStream_t>(copy_stream) : st;
   int H, W;
   s->hw(s->L, H, W);
   const int Z = s->cfg.latent_size, nc = s->cfg.channels;
   const size_t zb = align_up((size_t)n * Z * sizeof(float), 1024), ib = align_up((size_t)n * H * W * nc, 1024),
-               mb = (size_t)n * H * W;
-  if (stage_bytes < zb + ib + mb) { set_error("staging buffer too small"); return -1; }
-  uint8_t* base = static_cast<uint8_t*>(stage_dev);
+               mb = align_up((size_t)n * H * W, 1024);
+  const size_t per_slot = zb + ib + mb;
+  if (stage_bytes < per_slot * (copy_stream ? 2 : 1)) { set_error("staging buffer too small"); return -1; }
+  uint8_t* base = static_cast<uint8_t*>(stage_dev) + (copy_stream ? (size_t)slot * per_slot : 0);
   float* z_dev = reinterpret_cast<float*>(base);
   uint8_t* img_dev = base + zb;
   uint8_t* mask_dev = base + zb + ib;
+  if (copy_stream) {
+    for (int i = 0; i < 2; ++i) {
+      if (!s->ev_done[i]) cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming);
+      if (!s->ev_copied[i]) { cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming); cudaEventRecord(s->ev_copied[i], cs); }
+    }
+    // the staging slot is free once its previous device-to-host copies have finished
+    if (!cuda_ok(cudaStreamWaitEvent(st, s->ev_copied[slot], 0), "wait copied")) return -2;
+  }
   if (z_host && !cuda_ok(cudaMemcpyAsync(z_dev, z_host, (size_t)n * Z * sizeof(float), cudaMemcpyHostToDevice, st), "H2D z"))
     return -2;
   int rc = gsx_synth_forward(s, n, z_host ? z_dev : nullptr, psi_host, nullptr, seed, first_sample, nullptr, img_dev,
@@ -818,9 +831,15 @@ extern "C" int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z
   if (rc) return rc;
   rc = gsx_dec_forward(d, n, nullptr, s, synth_ws, nullptr, mask_dev, dec_ws, dec_ws_bytes, stream);
   if (rc) return rc;
-  if (img_u8_host && !cuda_ok(cudaMemcpyAsync(img_u8_host, img_dev, (size_t)n * H * W * nc, cudaMemcpyDeviceToHost, st), "D2H img"))
+  if (copy_stream) {
+    // device-to-host copies run on the copy stream and overlap the next step's kernels
+    if (!cuda_ok(cudaEventRecord(s->ev_done[slot], st), "record done")) return -2;
+    if (!cuda_ok(cudaStreamWaitEvent(cs, s->ev_done[slot], 0), "wait done")) return -2;
+  }
+  if (img_u8_host && !cuda_ok(cudaMemcpyAsync(img_u8_host, img_dev, (size_t)n * H * W * nc, cudaMemcpyDeviceToHost, cs), "D2H img"))
     return -2;
-  if (mask_host && !cuda_ok(cudaMemcpyAsync(mask_host, mask_dev, mb, cudaMemcpyDeviceToHost, st), "D2H mask")) return -2;
+  if (mask_host && !cuda_ok(cudaMemcpyAsync(mask_host, mask_dev, (size_t)n * H * W, cudaMemcpyDeviceToHost, cs), "D2H mask")) return -2;
+  if (copy_stream && !cuda_ok(cudaEventRecord(s->ev_copied[slot], cs), "record copied")) return -2;
   return 0;
 }
 

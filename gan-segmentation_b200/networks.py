@@ -265,36 +265,54 @@ class Decoder:
 
 class GeneratePipeline:
     """z (host) -> uint8 image + uint8 mask (host) through gsx_generate_host: the whole ``main.py generate``
-    inner loop (main.py:97-99) for one batch, H2D/D2H included, features resident in HBM."""
+    inner loop (main.py:97-99) for one batch, H2D/D2H included, features resident in HBM.  With
+    ``overlap=True`` the device-to-host copies run on a second stream into alternating host slots and
+    overlap the next batch's kernels."""
 
-    def __init__(self, generator, decoder, n):
+    def __init__(self, generator, decoder, n, overlap=True):
         self.g, self.d, self.n = generator, decoder, n
         dev = generator.device
         H, W = generator.out_hw
         nc = generator.cfg['channels']
         self.gws = generator.workspace(n)
         self.dws = decoder.workspace(n)
-        self.stage = torch.empty(n * (generator.latent_size * 4 + H * W * (nc + 1)) + 4096, dtype=torch.uint8, device=dev)
-        self.img_host = torch.empty((n, H, W, nc), dtype=torch.uint8).pin_memory()
-        self.mask_host = torch.empty((n, H, W), dtype=torch.uint8).pin_memory()
-        self.z_host = torch.empty((n, generator.latent_size), dtype=torch.float32).pin_memory()
-        self.h2d_bytes = self.z_host.numel() * 4
-        self.d2h_bytes = self.img_host.numel() + self.mask_host.numel()
+        self.overlap = overlap
+        slots = 2 if overlap else 1
+        per_slot = n * (generator.latent_size * 4 + H * W * (nc + 1)) + 4096
+        self.stage = torch.empty(per_slot * slots, dtype=torch.uint8, device=dev)
+        self.img_host = [torch.empty((n, H, W, nc), dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        self.mask_host = [torch.empty((n, H, W), dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        self.z_host = [torch.empty((n, generator.latent_size), dtype=torch.float32).pin_memory() for _ in range(slots)]
+        with torch.cuda.device(dev):
+            self.copy_stream = torch.cuda.Stream() if overlap else None
+        self.h2d_bytes = self.z_host[0].numel() * 4
+        self.d2h_bytes = self.img_host[0].numel() + self.mask_host[0].numel()
+        self._calls = 0
 
     def run(self, z=None, psi=None, seed=0, first_sample=0, stream=None):
-        """Enqueues one batch; outputs are valid in ``img_host`` / ``mask_host`` after the stream syncs."""
+        """Enqueues one batch and returns the slot index; ``img_host[slot]`` / ``mask_host[slot]`` are valid
+        after ``wait()`` (or once the same slot comes round again)."""
         lib = self.g._lib
+        slot = self._calls % len(self.img_host)
+        self._calls += 1
         zp = None
         if z is not None:
-            self.z_host.copy_(torch.as_tensor(z, dtype=torch.float32))
-            zp = L.ptr(self.z_host)
+            self.z_host[slot].copy_(torch.as_tensor(z, dtype=torch.float32))
+            zp = L.ptr(self.z_host[slot])
         psi_arr = None
         if psi is not None:
             psi_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(psi, np.float32), (self.g.num_layers,)))
+        cs = C.c_void_p(self.copy_stream.cuda_stream) if self.copy_stream is not None else None
         with torch.cuda.device(self.g.device):
             rc = lib.gsx_generate_host(self.g._h, self.d._h, self.n, zp, L.np_ptr(psi_arr), seed, first_sample,
-                                       L.ptr(self.img_host), L.ptr(self.mask_host), L.ptr(self.gws), self.gws.numel(),
-                                       L.ptr(self.dws), self.dws.numel(), L.ptr(self.stage), self.stage.numel(),
-                                       _stream(stream))
+                                       L.ptr(self.img_host[slot]), L.ptr(self.mask_host[slot]), L.ptr(self.gws),
+                                       self.gws.numel(), L.ptr(self.dws), self.dws.numel(), L.ptr(self.stage),
+                                       self.stage.numel(), _stream(stream), cs, slot)
         L.check(rc, 'gsx_generate_host', self.g.dtype)
         self.g._last_n = self.n
+        return slot
+
+    def wait(self):
+        if self.copy_stream is not None:
+            self.copy_stream.synchronize()
+        torch.cuda.current_stream(self.g.device).synchronize()

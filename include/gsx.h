@@ -99,12 +99,15 @@ int gsx_dec_forward(gsx_dec* h, int n, const float* const* feats_f32_dev, const 
                     gsx_stream stream);
 
 /* ---- whole generate step with HOST buffers (main.py:97-99 per batch): z_host (or NULL) in,
- *      uint8 image + uint8 mask out; H2D/D2H copies are enqueued on the stream inside the call.
- *      stage_dev: n*(latent*4 + H*W*4) bytes of device scratch. ---- */
+ *      uint8 image + uint8 mask out; H2D/D2H copies are enqueued inside the call.
+ *      copy_stream == NULL: everything on `stream`, stage_dev >= n*(latent*4 + H*W*4) (+3 KiB) bytes.
+ *      copy_stream != NULL: the device-to-host copies go to copy_stream and overlap the next call's kernels;
+ *      consecutive calls alternate slot 0/1 (two staging slots: stage_dev twice as large, two sets of host
+ *      buffers); outputs of a call are complete once copy_stream has drained (or the same slot is reused). ---- */
 int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z_host, const float* psi_host, uint64_t seed,
                       uint64_t first_sample, uint8_t* img_u8_host, uint8_t* mask_host, void* synth_ws,
                       size_t synth_ws_bytes, void* dec_ws, size_t dec_ws_bytes, void* stage_dev,
-                      size_t stage_bytes, gsx_stream stream);
+                      size_t stage_bytes, gsx_stream stream, gsx_stream copy_stream, int slot);
 
 /* ---- per-launch timing of the forward passes (bench.py's per-layer roofline table): enable, run a
  *      forward, dump "label\tms\talgorithmic_bytes\talgorithmic_flops\n" lines.  Off by default. ---- */

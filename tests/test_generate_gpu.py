@@ -123,3 +123,24 @@ def test_scope_kats_on_device():
     c = G.forward(z, noise=noise, psi=0.0)['img'].clone()
     d = G.forward(z[::-1].copy(), noise=noise, psi=0.0)['img'].clone()
     assert torch.equal(c, d)
+
+
+def test_host_pipeline_matches_device_path():
+    """gsx_generate_host (host latents in, uint8 image + mask out, copies on a second stream, two slots) returns
+    exactly what the device-resident calls produce for the same latents / seed."""
+    from gan_segmentation_b200.networks import Generator, Decoder, GeneratePipeline
+    gc, dc, gp, dp, z, _ = make_case(6, 3, seed=21)
+    G = Generator(gc)
+    G.set_parameters(gp)
+    D = Decoder(dc)
+    D.set_parameters(dp)
+    pipe = GeneratePipeline(G, D, 3, overlap=True)
+    slots = [pipe.run(z, seed=5, first_sample=10 * i) for i in range(3)]       # slot 0, 1, 0
+    pipe.wait()
+    assert slots == [0, 1, 0]
+    for i, slot in ((1, 1), (2, 0)):
+        out = G.forward(z, seed=5, first_sample=10 * i, return_u8=True, return_image=False, return_features=False)
+        dec = D.forward(generator=G, return_logits=False)
+        torch.cuda.synchronize()
+        assert torch.equal(out['img_u8'].cpu(), pipe.img_host[slot])
+        assert torch.equal(dec['mask'].cpu(), pipe.mask_host[slot])
