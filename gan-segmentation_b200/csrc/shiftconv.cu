@@ -79,7 +79,9 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int t) {
   return c;
 }
 
-template <int G>
+// GEN = the generator's conv_2 epilogue (noise, InstanceNorm statistics); the decoder / raw variant compiles those
+// paths out, which is what lets it run 16 epilogue warps inside the 112-register budget.
+template <int G, bool GEN>
 __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid_constant__ ConvParams p) {
   constexpr int kEpiWarps = 4 * G;
   constexpr int kEpiThreads = 128 * G;
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int egrp = ew >> 2;                     // which of the G warps sharing this quarter
     const int row = quarter * 32 + lane;
-    const bool do_stats = (e.flags & EPI_STATS) != 0;
+    const bool do_stats = GEN && (e.flags & EPI_STATS) != 0;
     const bool do_act = (e.flags & EPI_LRELU) != 0;
     const size_t plane_out = (size_t)e.Ho * e.Wo;
     const int n_chunks = g.hstack ? (g.cout_tile >> 4) : (g.N_tile >> 4);
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             bias_r[i] = e.bias ? __ldg(e.bias + c0 + i) : 0.f;
-            ns_r[i] = e.nscale ? __ldg(e.nscale + c0 + i) : 0.f;
+            ns_r[i] = (GEN && e.nscale) ? __ldg(e.nscale + c0 + i) : 0.f;
           }
           float s1[16], s2[16];
 #pragma unroll
@@ -350,10 +352,9 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
             float nz = 0.f;
             uint4 add0 = make_uint4(0, 0, 0, 0), add1 = add0;
             if (valid) {
-              if (g.aux_kind == 1) {
-                nz = reinterpret_cast<const float*>(aux)[(nb_l * g.TH + yl_l) * g.TW + xl_l];
-              } else if (e.noise) {
-                nz = __ldg(e.noise + (size_t)n * plane_out + pix);
+              if (GEN) {
+                if (g.aux_kind == 1) nz = reinterpret_cast<const float*>(aux)[(nb_l * g.TH + yl_l) * g.TW + xl_l];
+                else if (e.noise) nz = __ldg(e.noise + (size_t)n * plane_out + pix);
               }
               if (g.aux_kind == 2) {
                 // residual tile [cb][nb][row/2][col/2] of 16-B vectors at half resolution
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
               float f[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const float a = fmaf(ns_r[i], nz, __uint_as_float(v[i]) + bias_r[i]);
+                const float a = GEN ? fmaf(ns_r[i], nz, __uint_as_float(v[i]) + bias_r[i]) : __uint_as_float(v[i]) + bias_r[i];
                 f[i] = do_act ? lrelu02(a) : a;
               }
               if (e.addsrc || g.aux_kind == 2) {
@@ -456,14 +457,14 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
 }
 
-template <int G>
+template <int G, bool GEN>
 static void launch_g(const ConvParams& p, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(shiftconv_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(shiftconv_kernel<G, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured = true;
   }
-  shiftconv_kernel<G><<<grid, 64 + 128 * G, p.g.smem_bytes, st>>>(p);
+  shiftconv_kernel<G, GEN><<<grid, 64 + 128 * G, p.g.smem_bytes, st>>>(p);
 }
 
 void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
@@ -476,9 +477,14 @@ void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
   const ConvGeom& g = p.g;
   const int total = g.tiles_x * g.tiles_y * g.tiles_n * g.n_ntiles * (g.phase_grid ? 4 : 1);
   const int grid = total < num_sms * g.ctas_per_sm ? total : num_sms * g.ctas_per_sm;
-  if (g.epi_groups == 4) launch_g<4>(p, grid, st);
-  else if (g.epi_groups == 2) launch_g<2>(p, grid, st);
-  else launch_g<1>(p, grid, st);
+  const bool gen = p.e.noise != nullptr || p.e.nscale != nullptr || (p.e.flags & EPI_STATS) != 0;
+  if (gen) {                                   // generator conv_2: 8 epilogue warps (register budget)
+    launch_g<2, true>(p, grid, st);
+  } else if (g.epi_groups == 4) {
+    launch_g<4, false>(p, grid, st);
+  } else {
+    launch_g<2, false>(p, grid, st);
+  }
 }
 
 }  // namespace gsx
