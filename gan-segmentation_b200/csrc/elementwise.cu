@@ -193,18 +193,28 @@ void launch_stats(const act_t* in, float* stats_partial, int C, int N, int HW, c
 }
 
 // ------------------------------------------------------------------------------------------ finalize
-__global__ void finalize_kernel(const float* __restrict__ partial, int T, int N, int C, float inv_hw,
-                                const float* __restrict__ styles, int style_stride, int style_off,
-                                float* __restrict__ coef) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // (n, c)
+// One warp per (n, c): lane l sums tiles l, l+32, ... (fixed order), then a fixed butterfly adds the 32 partials,
+// so the result is bit-reproducible and the tile loop is 32-way parallel (544 tiles at 1024^2).
+__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ partial, int T, int N, int C, float inv_hw,
+                                                       const float* __restrict__ styles, int style_stride, int style_off,
+                                                       float* __restrict__ coef) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // (n, c)
+  const int lane = threadIdx.x & 31;
   if (i >= N * C) return;
   const int n = i / C, c = i - n * C;
   float s1 = 0.f, s2 = 0.f;
-  const float* p = partial + ((size_t)n * T * C + c) * 2;
-  for (int t = 0; t < T; ++t) {                             // fixed order
-    s1 += p[(size_t)t * C * 2];
-    s2 += p[(size_t)t * C * 2 + 1];
+  const float2* p = reinterpret_cast<const float2*>(partial) + ((size_t)n * T * C + c);
+  for (int t = lane; t < T; t += 32) {
+    const float2 v = __ldg(p + (size_t)t * C);
+    s1 += v.x;
+    s2 += v.y;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane != 0) return;
   if (!styles) { coef[(size_t)i * 2] = s1; coef[(size_t)i * 2 + 1] = s2; return; }
   const float mean = s1 * inv_hw;
   const float var = fmaxf(s2 * inv_hw - mean * mean, 0.f);  // biased variance (InstanceNorm)
@@ -217,8 +227,9 @@ __global__ void finalize_kernel(const float* __restrict__ partial, int T, int N,
 
 void launch_finalize(const float* partial, int T, int N, int C, int HW, const float* styles, int style_stride,
                      int style_off, float* coef, cudaStream_t st) {
-  finalize_kernel<<<(N * C + 127) / 128, 128, 0, st>>>(partial, T, N, C, 1.f / (float)HW, styles, style_stride,
-                                                        style_off, coef);
+  const int warps = N * C;
+  finalize_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(partial, T, N, C, 1.f / (float)HW, styles, style_stride,
+                                                           style_off, coef);
 }
 
 // ------------------------------------------------------------------------------------------ apply
