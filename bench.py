@@ -141,10 +141,28 @@ def run_reference(args, wl, rank, world):
                 impl='reference', config=dict(workload=wl['name'], step='1 latent (bounded sample of the batch)'),
                 cpu_baseline=dict(base), gpu_launches=0,
                 e2e=dict(value=base['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else libraries print (NCCL banner, warnings)
+    was redirected to stderr at start-up."""
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # stray library output (e.g. "NCCL version ...") -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=30)
@@ -307,7 +325,7 @@ def main():
                          d2h_bytes_per_step=pipe.d2h_bytes * world,
                          api='gsx_generate_host (pinned host z in, uint8 image + mask out to pinned host; D2H on a second stream, double-buffered)'),
                 roofline=roofline, cpu_baseline=cpu)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
