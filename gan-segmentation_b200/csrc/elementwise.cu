@@ -71,6 +71,18 @@ __device__ __forceinline__ void block_reduce_store(float (&v)[NV], float* dst0, 
 static constexpr int kP1Warps = 4;
 static constexpr int kP1Cols = 30;
 static constexpr int kP1Rows = 32;
+static constexpr int kP1Ring = 8;      // ring slots per lane
+static constexpr int kP1Ahead = 6;     // rows in flight per lane
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(kP1Warps * 32) pass1_kernel(const Pass1Args a, int strips, int rowblocks) {
   const int plane = blockIdx.y;                 // cb * N + n
@@ -80,6 +92,8 @@ __global__ void __launch_bounds__(kP1Warps * 32) pass1_kernel(const Pass1Args a,
   act_t* out = a.out + ((size_t)plane * HW) * 8;
   const float* noise = a.noise ? a.noise + (size_t)n * HW : nullptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ __align__(16) uint4 s_rows[kP1Warps][kP1Ring][32];
+  __shared__ float s_noise[kP1Warps][kP1Ring][32];
 
   float ns[8], bs[8];
 #pragma unroll
@@ -98,24 +112,36 @@ __global__ void __launch_bounds__(kP1Warps * 32) pass1_kernel(const Pass1Args a,
     const bool xin = x >= 0 && x < a.W;
     const bool xout = lane >= 1 && lane <= kP1Cols && x < a.W;
     const int y0 = rb * kP1Rows, y1 = min(a.H, y0 + kP1Rows);
-    // raw 16-B row loads, issued kP1Ahead rows ahead of their use (zero outside the image = the blur's zero pad)
-    auto raw_row = [&](int y) -> uint4 {
-      if (xin && y >= 0 && y < a.H) return ldg_nc_u4(in + ((size_t)y * a.W + x) * 8);
-      return make_uint4(0u, 0u, 0u, 0u);
-    };
-    auto raw_noise = [&](int y) -> float {
-      return (noise && xout && y < a.H) ? __ldg(noise + (size_t)y * a.W + x) : 0.f;
-    };
+    // Rows stream through a per-lane shared-memory ring filled by cp.async kP1Ahead rows ahead of their use
+    // (zero-filled outside the image = the blur's zero padding): deep prefetch without spending registers,
+    // which is what a latency-bound streaming pass needs (bytes in flight, not occupancy).
+    uint4* ring = &s_rows[warp][0][lane];
+    float* nring = &s_noise[warp][0][lane];
     const int lead = a.blur ? 1 : 0;                         // the vertical tap below needs row y+1
-    uint4 p0 = raw_row(y0 + lead), p1 = raw_row(y0 + lead + 1), p2 = raw_row(y0 + lead + 2);
-    float n0 = raw_noise(y0), n1 = raw_noise(y0 + 1), n2 = raw_noise(y0 + 2);
+    auto issue = [&](int j) {                                // j-th consumed row: image row y0 + lead + j - ...
+      const int y = y0 - lead + j;                           // rows y0-1 (blur) .. y1-1+lead
+      const bool ok = xin && y >= 0 && y < a.H && y <= y1 - 1 + lead;
+      cp_async16(ring + (j % kP1Ring) * 32, ok ? (const void*)(in + ((size_t)y * a.W + x) * 8) : (const void*)in, ok ? 16 : 0);
+      const int yn = y0 + j;                                 // noise row for output row y0 + j
+      const bool nok = noise && xout && yn < y1;
+      cp_async4(nring + (j % kP1Ring) * 32, nok ? (const void*)(noise + (size_t)yn * a.W + x) : (const void*)in, nok ? 4 : 0);
+      cp_async_commit();
+    };
+    const int n_rows = (y1 - y0) + 2 * lead;                 // rows to stream
+#pragma unroll
+    for (int j = 0; j < kP1Ahead; ++j) issue(j);
     float r0[8], r1[8], r2[8];
-    if (a.blur) { unpack8(raw_row(y0 - 1), r0); unpack8(raw_row(y0), r1); }
-    for (int y = y0; y < y1; ++y) {
-      const uint4 cur = p0;
-      const float nz = n0;
-      p0 = p1; p1 = p2; p2 = raw_row(y + lead + 3);
-      n0 = n1; n1 = n2; n2 = raw_noise(y + 3);
+    int j = 0;
+    if (a.blur) {                                            // prime the 3-row window with rows y0-1, y0
+      cp_async_wait<kP1Ahead - 1>(); unpack8(ring[(0 % kP1Ring) * 32], r0); issue(kP1Ahead);
+      cp_async_wait<kP1Ahead - 1>(); unpack8(ring[(1 % kP1Ring) * 32], r1); issue(kP1Ahead + 1);
+      j = 2;
+    }
+    for (int y = y0; y < y1; ++y, ++j) {
+      cp_async_wait<kP1Ahead - 1>();
+      const uint4 cur = ring[(j % kP1Ring) * 32];
+      const float nz = nring[((y - y0) % kP1Ring) * 32];
+      issue(j + kP1Ahead);
       float v[8];
       if (a.blur) {
         unpack8(cur, r2);
@@ -141,6 +167,8 @@ __global__ void __launch_bounds__(kP1Warps * 32) pass1_kernel(const Pass1Args a,
         *reinterpret_cast<uint4*>(out + ((size_t)y * a.W + x) * 8) = pack8(v);
       }
     }
+    cp_async_wait<0>();
+    (void)n_rows;
   }
   if (a.stats) {
     float* st = a.stats + (((size_t)n * gridDim.x + blockIdx.x) * a.C + cb * 8) * 2;
@@ -381,11 +409,13 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
   }
 }
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  // hardware-approximate log / sin / cos: this generator DEFINES the noise stream (there is no reference
+  // stream to match -- MXNet's sampler is not reproducible outside MXNet), it only has to be N(0,1) and cheap
   const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;      // (0,1]
   const float u2 = (float)b * 2.3283064365386963e-10f;               // [0,1)
-  const float r = sqrtf(-2.f * logf(u1));
+  const float r = sqrtf(-2.f * __logf(u1));
   float s, c;
-  sincospif(2.f * u2, &s, &c);
+  __sincosf(6.283185307179586f * u2, &s, &c);
   z0 = r * c; z1 = r * s;
 }
 __global__ void fill_normal_kernel(float* out, size_t per_sample, int N, uint64_t seed, uint64_t first_sample,
