@@ -472,16 +472,30 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     ProfScope ps("styles", 4.0 * h->S_total * Z + 4.0 * N * (Z + h->S_total), 2.0 * N * Z * h->S_total, st);
     launch_dense(d, st); g_launches++;
   }
-  // noise planes
+  // noise planes: explicit inputs, or all of them from the Philox generator in one launch
   std::vector<const float*> noise(h->nlayers);
-  for (int l = 0; l < h->nlayers; ++l) {
-    if (noise_dev && noise_dev[l]) noise[l] = noise_dev[l];
-    else {
+  {
+    NoisePlanes pl{};
+    bool any = false, all = true;
+    for (int l = 0; l < h->nlayers; ++l) {
       int hh, ww;
       h->hw(2 + l / 2, hh, ww);
-      ProfScope ps("noise", 4.0 * N * hh * ww, 0, st);
-      launch_fill_noise(w.noise[l], (size_t)hh * ww, N, seed, first_sample, l, st); g_launches++;
-      noise[l] = w.noise[l];
+      pl.ptr[l] = w.noise[l];
+      pl.elems[l] = (size_t)hh * ww;
+      if (noise_dev && noise_dev[l]) { noise[l] = noise_dev[l]; all = false; }
+      else { noise[l] = w.noise[l]; any = true; }
+    }
+    if (any && all && h->nlayers <= 24) {
+      size_t tot = 0;
+      for (int l = 0; l < h->nlayers; ++l) tot += pl.elems[l];
+      ProfScope ps("noise", 4.0 * N * tot, 0, st);
+      launch_fill_noise_all(pl, h->nlayers, N, seed, first_sample, st); g_launches++;
+    } else if (any) {
+      for (int l = 0; l < h->nlayers; ++l) {
+        if (noise[l] != w.noise[l]) continue;
+        ProfScope ps("noise", 4.0 * N * pl.elems[l], 0, st);
+        launch_fill_noise(w.noise[l], pl.elems[l], N, seed, first_sample, l, st); g_launches++;
+      }
     }
   }
   h->last_n = N;

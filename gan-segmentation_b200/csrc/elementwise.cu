@@ -441,6 +441,37 @@ void launch_fill_noise(float* out, size_t plane_elems, int N, uint64_t seed, uin
   dim3 grid((unsigned)min((size_t)1024, (quads + 255) / 256), N);
   fill_normal_kernel<<<grid, 256, 0, st>>>(out, plane_elems, N, seed, first_sample, (uint32_t)layer);
 }
+// all noise planes of a forward pass in one launch: blockIdx.z = style layer
+__global__ void fill_noise_all_kernel(NoisePlanes pl, int N, uint64_t seed, uint64_t first_sample) {
+  const int layer = blockIdx.z;
+  const size_t per_sample = pl.elems[layer];
+  float* out = pl.ptr[layer];
+  const size_t quads = (per_sample + 3) / 4;
+  const int n = blockIdx.y;
+  const uint64_t gs = first_sample + (uint64_t)n;
+  for (size_t qd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quads; qd += (size_t)gridDim.x * blockDim.x) {
+    uint32_t c[4] = {(uint32_t)qd, (uint32_t)layer, (uint32_t)gs, (uint32_t)(gs >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float z[4];
+    box_muller(c[0], c[1], z[0], z[1]);
+    box_muller(c[2], c[3], z[2], z[3]);
+    float* dst = out + (size_t)n * per_sample + qd * 4;
+    if (qd * 4 + 3 < per_sample) {
+      *reinterpret_cast<float4*>(dst) = make_float4(z[0], z[1], z[2], z[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (qd * 4 + i < per_sample) dst[i] = z[i];
+    }
+  }
+}
+void launch_fill_noise_all(const NoisePlanes& pl, int nlayers, int N, uint64_t seed, uint64_t first_sample, cudaStream_t st) {
+  size_t maxq = 1;
+  for (int l = 0; l < nlayers; ++l) maxq = pl.elems[l] / 4 > maxq ? pl.elems[l] / 4 : maxq;
+  dim3 grid((unsigned)min((size_t)512, (maxq + 255) / 256), N, nlayers);
+  fill_noise_all_kernel<<<grid, 256, 0, st>>>(pl, N, seed, first_sample);
+}
+
 void launch_fill_latents(float* z, int N, int Z, uint64_t seed, uint64_t first_sample, cudaStream_t st) {
   dim3 grid(1, N);
   fill_normal_kernel<<<grid, 128, 0, st>>>(z, (size_t)Z, N, seed, first_sample, 0xFFFFu);

@@ -204,6 +204,8 @@ void launch_nchw_to_blocked(const float* in, act_t* out, int C, int N, int HW, c
 void launch_fill_noise(float* out, size_t plane_elems, int N, uint64_t seed, uint64_t first_sample, int layer,
                        cudaStream_t st);
 void launch_fill_latents(float* z, int N, int Z, uint64_t seed, uint64_t first_sample, cudaStream_t st);
+struct NoisePlanes { float* ptr[24]; size_t elems[24]; };   // per style layer: plane base, elements per sample (mult. of 4)
+void launch_fill_noise_all(const NoisePlanes& pl, int nlayers, int N, uint64_t seed, uint64_t first_sample, cudaStream_t st);
 
 struct DenseArgs {            // y[n][u] = act( sum_k x'[n][k] W[u][k] + b[u] ), W pre-scaled fp32
   const float* x; const float* W; const float* b; float* y;

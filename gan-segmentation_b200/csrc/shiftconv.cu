@@ -319,6 +319,46 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
             e.mask[(size_t)n * plane_out + pix] = (unsigned char)arg;
           }
         }
+      } else if (g.up_cols) {
+        // up-conv with the 4 phases as column blocks: the px=0 / px=1 outputs of a low-res pixel are adjacent in
+        // the output row, so both phases are processed together and leave as ONE 32-byte store per channel block
+        // (full sectors instead of two half-sector writes).  Raw or bias+lrelu epilogue only.
+        for (int pc = 0; pc < 2 * cpp; ++pc) {
+          const int py = pc / cpp, c16 = pc - py * cpp;
+          const int c0 = tc.ntile * g.cout_tile + c16 * 16;
+          const int col0 = ((2 * py) * cpp + c16) * 16, col1 = ((2 * py + 1) * cpp + c16) * 16;
+          float bias_r[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) bias_r[i] = e.bias ? __ldg(e.bias + c0 + i) : 0.f;
+          for (int u = egrp; u < n_units; u += G) {
+            uint32_t va[16], vb[16];
+            tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + col0), va);
+            tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + col1), vb);
+            int n, y, x;
+            const bool valid = locate(u, n, y, x);
+            const size_t pix = (size_t)(2 * y + py) * e.Wo + 2 * x;
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                if (c0 + h * 8 < e.Cout) {
+                  uint32_t o[8];
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    float a0 = __uint_as_float(va[h * 8 + 2 * k]) + bias_r[h * 8 + 2 * k];
+                    float a1 = __uint_as_float(va[h * 8 + 2 * k + 1]) + bias_r[h * 8 + 2 * k + 1];
+                    float b0 = __uint_as_float(vb[h * 8 + 2 * k]) + bias_r[h * 8 + 2 * k];
+                    float b1 = __uint_as_float(vb[h * 8 + 2 * k + 1]) + bias_r[h * 8 + 2 * k + 1];
+                    if (do_act) { a0 = lrelu02(a0); a1 = lrelu02(a1); b0 = lrelu02(b0); b1 = lrelu02(b1); }
+                    o[k] = pack_x2(a0, a1);
+                    o[4 + k] = pack_x2(b0, b1);
+                  }
+                  st_global_256(e.out + (((size_t)((c0 >> 3) + h) * g.N + n) * plane_out + pix) * 8, o);
+                }
+              }
+            }
+          }
+        }
       } else {
         for (int cc = 0; cc < n_chunks; ++cc) {
           const int ph = g.up_cols ? cc / cpp : tc.phase;        // output phase of this column chunk

@@ -8,7 +8,7 @@
 using namespace gsx;
 
 __global__ void __launch_bounds__(128, 1) bench(int N, int a_off_bytes, int lbo, int sbo, int iters, int taps, int tap_pitch,
-                                                long long* out) {
+                                                long long* out, int dcol_stride, int n_acc) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int a_off_bytes, int lbo,
     long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       for (int t = 0; t < taps; ++t)
-        umma_f16kind(tmem + (uint32_t)((i & 1) * N), umma_desc(a_hi, a_addr + (uint32_t)(t * tap_pitch)), umma_desc(b_hi, b_addr), idesc,
+        umma_f16kind(tmem + (uint32_t)((i % n_acc) * dcol_stride), umma_desc(a_hi, a_addr + (uint32_t)(t * tap_pitch)), umma_desc(b_hi, b_addr), idesc,
                      t > 0);
     }
     umma_commit(&bar);
@@ -60,13 +60,22 @@ int main() {
   for (int N : {16, 32, 64, 128, 256}) {
     printf("N=%3d:", N);
     for (auto& c : cfgs) {
-      bench<<<148, 128, 200 * 1024>>>(N, c.off, c.lbo, c.sbo, iters, taps, c.pitch, d);
+      bench<<<148, 128, 200 * 1024>>>(N, c.off, c.lbo, c.sbo, iters, taps, c.pitch, d, N, 2);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf(" ERR(%s)", cudaGetErrorString(e)); return 1; }
       long long cyc; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
       printf("  %s=%.1f", c.name, (double)cyc / (iters * taps));
     }
     printf("\n");
+  }
+  printf("accumulator-address effects (9 taps accumulate into one tile, tiles round-robin):\n");
+  struct A { int N, dstride, nacc, off; } accs[] = {{16, 16, 16, 0}, {48, 48, 10, 0}, {48, 64, 8, 0}, {48, 48, 10, 2016}, {64, 64, 8, 0}, {96, 96, 5, 0}, {96, 128, 4, 0}, {32, 32, 16, 0}, {16, 16, 1, 0}};
+  for (auto& a : accs) {
+    bench<<<148, 128, 200 * 1024>>>(a.N, a.off, 32768, 128, iters, 3, 1056, d, a.dstride, a.nacc);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf(" ERR(%s)\n", cudaGetErrorString(e)); return 1; }
+    long long cyc; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
+    printf("  N=%d dcol_stride=%d n_acc=%d a_off=%d: %.1f cycles/MMA\n", a.N, a.dstride, a.nacc, a.off, (double)cyc / (iters * 3));
   }
   return 0;
 }
