@@ -60,7 +60,7 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   // thin layers: 256 columns per accumulator buffer so that two buffers fit (MMA / epilogue overlap);
   // wide layers: all 512 columns for one buffer (more MMA rows per weight load; the epilogue is a small
   // fraction of the k-loop there)
-  int budget_cols = thin ? 256 : 512;
+  int budget_cols = (thin && N_tile < 128) ? 256 : 512;     // (N >= 128: 4 tiles in one buffer beat 2+2, measured)
   if (hstack) budget_cols = 512;               // 3x the columns per MMA tile: one accumulator buffer, larger tiles
   if (ov && ov->acc_bufs == 1) budget_cols = 512;
   if (ov && ov->acc_bufs == 2) budget_cols = 256;

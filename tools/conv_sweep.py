@@ -92,8 +92,8 @@ if __name__ == '__main__':
         ovs = [json.loads(args.override) if args.override else None]
         if args.sweep:
             mode = LAYERS[name][0]
-            ths = [3, 7, 15, 31] if mode in ('CONV3', 'CONV1') else [1, 3, 7, 15]
-            ovs = [None] + [dict(TH=th, stages=st) for th, st in itertools.product(ths, [1, 2])]
+            ths = [7, 15, 23, 31, 47] if mode in ('CONV3', 'CONV1') else [3, 5, 7, 11, 15]
+            ovs = [None] + [dict(TH=th, acc_bufs=ab) for th, ab in itertools.product(ths, [1, 2])]
         for ov in ovs:
             try:
                 r, by, fl = run(name, args.n, ov, args.repeat, args.dtype)
