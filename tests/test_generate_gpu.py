@@ -1,5 +1,7 @@
 """Whole-path parity on the GPU: C-ABI generator + decoder against the CPU oracle on identical latents,
 noise and random-init weights (BASELINE.json configs 1 and 3 at test size)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -144,3 +146,33 @@ def test_host_pipeline_matches_device_path():
         torch.cuda.synchronize()
         assert torch.equal(out['img_u8'].cpu(), pipe.img_host[slot])
         assert torch.equal(dec['mask'].cpu(), pipe.mask_host[slot])
+
+
+def test_dataset_writer_files_and_split_invariance(tmp_path):
+    """main.py generate's output files (img_XXXXXX.jpg + mask_XXXXXX.png with class ids), written by two "ranks"
+    with a different batch size than a single-rank run: same masks bit for bit (Philox keyed by global index)."""
+    import cv2
+    from gan_segmentation_b200.networks import Generator, Decoder, GeneratePipeline
+    from gan_segmentation_b200.dataset_writer import generate_dataset
+    gc, dc, gp, dp, _, _ = make_case(6, 1, seed=31)
+    G = Generator(gc)
+    G.set_parameters(gp)
+    D = Decoder(dc)
+    D.set_parameters(dp)
+    a, b = tmp_path / 'one', tmp_path / 'two'
+    assert generate_dataset(GeneratePipeline(G, D, 4), str(a), 7, seed=3, psi=0.7) == 7
+    p2 = GeneratePipeline(G, D, 3)
+    n0 = generate_dataset(p2, str(b), 7, seed=3, psi=0.7, rank=0, world=2)
+    n1 = generate_dataset(p2, str(b), 7, seed=3, psi=0.7, rank=1, world=2)
+    assert n0 + n1 == 7
+    names = sorted(os.listdir(a))
+    assert names == sorted(os.listdir(b)) and len(names) == 14
+    assert names[0] == 'img_000000.jpg' and names[-1] == 'mask_000006.png'
+    for i in range(7):
+        ma = cv2.imread(str(a / f'mask_{i:06d}.png'), cv2.IMREAD_UNCHANGED)
+        mb = cv2.imread(str(b / f'mask_{i:06d}.png'), cv2.IMREAD_UNCHANGED)
+        assert ma.shape == (64, 64) and ma.dtype == np.uint8 and set(np.unique(ma)) <= {0, 1}
+        assert np.array_equal(ma, mb)
+        ia = cv2.imread(str(a / f'img_{i:06d}.jpg'))
+        ib = cv2.imread(str(b / f'img_{i:06d}.jpg'))
+        assert ia.shape == (64, 64, 3) and np.array_equal(ia, ib)
