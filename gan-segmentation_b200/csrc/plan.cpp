@@ -46,13 +46,14 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   const int up_cols = (up && !phase_grid) ? 1 : 0;
   const int cout_tile = N_tile;
   if (up_cols) N_tile = 4 * cout_tile;        // phases stacked along the MMA N dimension (<= 256)
-  // every M=128 kind::f16 MMA costs ~75 cycles for any N <= 128 (tools/umma_bench.cu), so thin 3x3 layers are
-  // bound by the NUMBER of MMAs: stack the 3 horizontal taps along N -> 3 MMAs per k16 step instead of 9
-  // (measured on B200: the heavier epilogue -- 3x TMEM loads, 32 shuffles, a barrier per unit -- costs more
-  //  than the MMAs it saves, so the mode is off unless forced through the plan override)
-  //  That holds even for the final classifier conv with its tiny argmax epilogue: 2.5 ms stacked vs 1.0 ms plain.
-  int hstack = 0;
-  if (ov && ov->hstack >= 0 && mode == CONV3 && cout <= 64) hstack = ov->hstack;
+  // every M=128 kind::f16 MMA costs ~60-75 cycles for any N <= 128 (tools/umma_bench.cu), so thin 3x3 layers are
+  // bound by the NUMBER of MMAs.  Stacking the 3 horizontal taps along N (3 MMAs per k16 step instead of 9, the
+  // epilogue forming out[q] = acc[q][0] + acc[q+1][1] + acc[q+2][2] by shuffles) was implemented and parity-green
+  // in round 1 but measured 2-2.5x SLOWER (heavier epilogue: 3x TMEM loads, 32 shuffles, a barrier per unit), and
+  // merely compiling the path in cost the plain epilogue 40 registers -- it was removed from the kernel
+  // (git history: "hstack"); the geometry fields stay for the next attempt.
+  const int hstack = 0;
+  if (ov && ov->hstack > 0) { set_error("plan_conv: hstack mode is not compiled into this build"); return; }
   if (hstack) N_tile = 3 * cout_tile;
   const int mt_stride = hstack ? 126 : 128;
   const int G = 1;
@@ -61,7 +62,6 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   // wide layers: all 512 columns for one buffer (more MMA rows per weight load; the epilogue is a small
   // fraction of the k-loop there)
   int budget_cols = (thin && N_tile < 128) ? 256 : 512;     // (N >= 128: 4 tiles in one buffer beat 2+2, measured)
-  if (hstack) budget_cols = 512;               // 3x the columns per MMA tile: one accumulator buffer, larger tiles
   if (ov && ov->acc_bufs == 1) budget_cols = 512;
   if (ov && ov->acc_bufs == 2) budget_cols = 256;
   int max_mt = std::max(1, budget_cols / (G * N_tile));

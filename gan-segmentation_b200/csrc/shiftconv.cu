@@ -228,38 +228,11 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     const bool do_stats = GEN && (e.flags & EPI_STATS) != 0;
     const bool do_act = (e.flags & EPI_LRELU) != 0;
     const size_t plane_out = (size_t)e.Ho * e.Wo;
-    const int n_chunks = g.hstack ? (g.cout_tile >> 4) : (g.N_tile >> 4);
+    const int n_chunks = g.N_tile >> 4;
     const int cpp = g.cout_tile >> 4;             // 16-channel chunks per phase block (== n_chunks unless up_cols)
     const int n_units = g.n_mtiles;
     const int slot_floats = 2 * g.cout_tile;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-
-    // hstack: out[q] = acc[q][0] + acc[q+1][1] + acc[q+2][2].  Rows q+1, q+2 live in the next lanes (shuffle) or,
-    // for lanes 30/31, in the next warp quarter: lanes 0/1 of every quarter publish the values their lower
-    // neighbour needs through a small double-buffered smem area, one 128-thread named barrier per unit.
-    float* xch = reinterpret_cast<float*>(smem + g.xch_off) + (size_t)egrp * 5 * 48;       // [parity][G][5][48]
-    int xparity = 0;
-    auto hstack_combine = [&](uint32_t (&v)[16], const uint32_t (&v1)[16], const uint32_t (&v2)[16]) {
-      float* mine = xch + (size_t)xparity * G * 5 * 48 + quarter * 48;
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { mine[i] = __uint_as_float(v1[i]); mine[16 + i] = __uint_as_float(v2[i]); }
-      } else if (lane == 1) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) mine[32 + i] = __uint_as_float(v2[i]);
-      }
-      named_bar_sync(2 + egrp, 128);
-      const float* nb = mine + 48;                          // next quarter (quarter 3 reads an unused pad: its
-#pragma unroll                                              //   lanes 30/31 are rows 126/127, never output)
-      for (int i = 0; i < 16; ++i) {
-        float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[i]), 1);
-        float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 2);
-        if (lane == 31) { a1 = nb[i]; a2 = nb[32 + i]; }
-        if (lane == 30) a2 = nb[16 + i];
-        v[i] = __float_as_uint(__uint_as_float(v[i]) + a1 + a2);
-      }
-      xparity ^= 1;
-    };
 
     int tl = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
@@ -294,13 +267,6 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         for (int mt = egrp; mt < g.n_mtiles; mt += G) {
           uint32_t v[16];
           tmem_ld16(acc_base + (uint32_t)(mt * g.N_tile), v);
-          if (g.hstack) {
-            uint32_t v1[16], v2[16];
-            tmem_ld16(acc_base + (uint32_t)(mt * g.N_tile + g.cout_tile), v1);
-            tmem_ld16(acc_base + (uint32_t)(mt * g.N_tile + 2 * g.cout_tile), v2);
-            tmem_ld_wait();
-            hstack_combine(v, v1, v2);
-          }
           tmem_ld_wait();
           int n, y, x;
           if (locate(mt, n, y, x)) {
@@ -379,12 +345,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
           // loads below are only the fallback for layers the planner could not stage.
           for (int u = egrp; u < n_units; u += G) {
             const int mt = u;
-            uint32_t v[16], v1[16], v2[16];
+            uint32_t v[16];
             tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + cc * 16), v);
-            if (g.hstack) {
-              tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + g.cout_tile + cc * 16), v1);
-              tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + 2 * g.cout_tile + cc * 16), v2);
-            }
             int n, y, x;
             const bool valid = locate(mt, n, y, x);
             if (e.up) { y = 2 * y + (ph >> 1); x = 2 * x + (ph & 1); }
@@ -412,7 +374,6 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
               }
             }
             tmem_ld_wait();
-            if (g.hstack) hstack_combine(v, v1, v2);
             if (valid) {
               float f[16];
 #pragma unroll

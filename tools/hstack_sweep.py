@@ -4,7 +4,7 @@ from conv_sweep import run, LAYERS
 layers = sys.argv[1].split(',')
 hss = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0, 1]
 for name in layers:
-    for hs, eg, ab in itertools.product(hss,[2,4],[1,2]):
+    for hs, eg, ab in itertools.product([0],[2,4],[2]):
         ov=dict(hstack=hs, epi_groups=eg, acc_bufs=ab)
         try:
             r,by,fl = run(name, 32, ov, 10, 'fp16')
