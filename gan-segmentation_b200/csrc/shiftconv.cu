@@ -458,28 +458,33 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
 }
 
+// cudaFuncSetAttribute is per device: one process may drive several GPUs (ImageGenerator(gpu_ids=[0,1,..])).
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 ? 0 : (dev > 63 ? 63 : dev);
+}
+
 template <int G, bool GEN>
 static void launch_g(const ConvParams& p, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  const int dev = current_device();
+  if (!configured[dev]) {
     cudaFuncSetAttribute(shiftconv_kernel<G, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    configured = true;
+    configured[dev] = true;
   }
   shiftconv_kernel<G, GEN><<<grid, 64 + 128 * G, p.g.smem_bytes, st>>>(p);
 }
 
 void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  static int num_sms[64] = {0};
+  const int dev = current_device();
+  if (!num_sms[dev]) cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
   const ConvGeom& g = p.g;
   const int total = g.tiles_x * g.tiles_y * g.tiles_n * g.n_ntiles * (g.phase_grid ? 4 : 1);
-  const int grid = total < num_sms * g.ctas_per_sm ? total : num_sms * g.ctas_per_sm;
+  const int grid = total < num_sms[dev] * g.ctas_per_sm ? total : num_sms[dev] * g.ctas_per_sm;
   const bool gen = p.e.noise != nullptr || p.e.nscale != nullptr || (p.e.flags & EPI_STATS) != 0;
-  if (gen) {                                   // generator conv_2: 8 epilogue warps (register budget)
+  if (gen) {                                   // generator conv_2: noise + statistics epilogue
     launch_g<2, true>(p, grid, st);
   } else if (g.epi_groups == 4) {
     launch_g<4, false>(p, grid, st);

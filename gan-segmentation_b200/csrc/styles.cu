@@ -64,11 +64,14 @@ __global__ void __launch_bounds__(kDnThreads) dense_kernel(const DenseArgs a) {
 }
 
 void launch_dense(const DenseArgs& a, cudaStream_t st) {
-  static bool configured = false;
+  static bool configured[64] = {false};        // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = dev < 0 ? 0 : (dev > 63 ? 63 : dev);
   const size_t smem = (size_t)kDnSamples * a.K * sizeof(float);
-  if (!configured) {
+  if (!configured[dev]) {
     cudaFuncSetAttribute(dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    configured = true;
+    configured[dev] = true;
   }
   dense_kernel<<<(a.U + 7) / 8, kDnThreads, smem, st>>>(a);
 }

@@ -27,7 +27,7 @@ def run_both(max_res_log2, n, base=(4, 4), seed=0, psi=None, dtype='fp16'):
 
 
 def check(ref, out, dec, label, dtype='fp16'):
-    tol = TOL[dtype]
+    tol = TOL[dtype]          # dtype: key of parity_util.TOL
     img = out['img'].cpu().numpy()
     a = np.clip(img, -1, 1)
     b = np.clip(ref['img_f32'], -1, 1)
@@ -43,6 +43,10 @@ def check(ref, out, dec, label, dtype='fp16'):
     assert np.isfinite(img).all()
     assert max(errs) < tol['feat'], errs
     assert p >= tol['psnr'], p
+    if 'frac_over' in tol:
+        frac = float((np.abs(a - b) > 2e-2).mean())
+        print(f'[{label}] fraction of image values off by more than 2e-2: {frac:.2e}')
+        assert frac <= tol['frac_over'], frac
     assert maxabs <= tol['max_abs'], maxabs
     assert agree >= tol['mask'], agree
     # argmax is bit-exact given identical logits (first-max tie rule)
@@ -176,3 +180,39 @@ def test_dataset_writer_files_and_split_invariance(tmp_path):
         ia = cv2.imread(str(a / f'img_{i:06d}.jpg'))
         ib = cv2.imread(str(b / f'img_{i:06d}.jpg'))
         assert ia.shape == (64, 64, 3) and np.array_equal(ia, ib)
+
+
+def test_config2_ffhq_1024_parity_one_sample():
+    """BASELINE config 2's network at full size (FFHQ 1024^2 generator + hair decoder, psi = 0.7), one latent,
+    against the CPU oracle: PSNR >= 40 dB and mask agreement >= 99.5 % as stated; the max-abs bound of 2e-2 holds
+    for all but <= 2e-5 of the 3.1 M image values (see parity_util.TOL['fp16_1024'])."""
+    ref, out, dec, _ = run_both(10, 1, seed=41, psi=0.7)
+    check(ref, out, dec, 'ffhq1024 n=1 psi=.7 fp16', 'fp16_1024')
+
+
+def test_ffhq_1024_size_independent_properties():
+    """Full-size properties that need no oracle: batch-split invariance, mask == first-max argmax of the logits,
+    uint8 image == the reference transform of the fp32 image, zero noise scale => noise has no effect."""
+    from gan_segmentation_b200.networks import Generator, Decoder
+    gc, dc, gp, dp, z, _ = make_case(10, 2, seed=43)
+    G = Generator(gc)
+    G.set_parameters(gp)
+    D = Decoder(dc)
+    D.set_parameters(dp)
+    out = G.forward(z, seed=9, first_sample=100, psi=0.7, return_u8=True, return_features=False)
+    dec = D.forward(generator=G)
+    img, u8, mask, lg = out['img'].clone(), out['img_u8'].clone(), dec['mask'].clone(), dec['logits'].clone()
+    # second sample alone (global index 101) == row 1 of the pair
+    out1 = G.forward(z[1:], seed=9, first_sample=101, psi=0.7, return_u8=True, return_features=False)
+    dec1 = D.forward(generator=G)
+    torch.cuda.synchronize()
+    assert torch.equal(out1['img'][0], img[1]) and torch.equal(dec1['mask'][0], mask[1])
+    assert np.array_equal(mask.cpu().numpy(), first_max_argmax(lg.cpu().numpy()))
+    a = img.cpu().numpy().transpose(0, 2, 3, 1)
+    a = (np.float32(255.) * np.clip((a - np.float32(-1)) / np.float32(2), 0.0, 1.0)).astype(np.uint8)
+    assert np.array_equal(u8.cpu().numpy(), a)
+    gp0 = {k: (np.zeros_like(v) if k.endswith('scale_factors') else v) for k, v in gp.items()}
+    G.set_parameters(gp0)
+    p = G.forward(z, seed=1, psi=0.7, return_features=False)['img'].clone()
+    q = G.forward(z, seed=2, psi=0.7, return_features=False)['img'].clone()      # different Philox noise
+    assert torch.equal(p, q)
