@@ -59,6 +59,9 @@ class ImageGenerator:
         n_batches = n // self.batch_size + (1 if n % self.batch_size > 0 else 0)
         n_generated = 0
         rng = np.random if seed is None else np.random.RandomState(seed)
+        # the noise planes AddNoise samples per call (networks_stylegan.py:300) come from the device Philox stream
+        # keyed by (noise_seed, running sample index): fresh per sample, independent of the context split
+        noise_seed = int(rng.randint(0, 2 ** 31 - 1))
         for _ in range(n_batches):
             bs = min(self.batch_size, n - n_generated)
             latent_z = rng.standard_normal((bs, self.latent_size)).astype(np.float32)
@@ -67,8 +70,8 @@ class ImageGenerator:
                 if b == a:
                     continue
                 nz = None if noise is None else [p[n_generated + a:n_generated + b] for p in noise]
-                outs.append(g.forward(latent_z[a:b], psi=psi, noise=nz, return_features=return_features,
-                                      return_image=False, return_u8=True))
+                outs.append(g.forward(latent_z[a:b], psi=psi, noise=nz, seed=noise_seed, first_sample=n_generated + a,
+                                      return_features=return_features, return_image=False, return_u8=True))
             for g in self.netG:
                 torch.cuda.synchronize(g.device)                  # mx.nd.waitall() (:102)
             if device_outputs:

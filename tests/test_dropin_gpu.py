@@ -45,6 +45,9 @@ def test_multi_context_matches_single(tmp_path):
         pytest.skip('needs 2 GPUs')
     a = _run([0], tmp_path, batch=4)
     b = _run([0, 1], tmp_path, batch=4)
-    # explicit z, device Philox noise keyed by the per-call sample index -> only z-identical checks hold across
-    # splits for the image; compare shapes and that both produce valid outputs, plus exact equality of sample 0
-    assert np.array_equal(a[0][0], b[0][0]) and np.array_equal(a[0][1], b[0][1])
+    # z from the seeded host RNG, noise from the Philox stream keyed by the running sample index: every sample is
+    # bit-identical however the batch is split over contexts
+    for (ia, ma), (ib, mb) in zip(a, b):
+        assert np.array_equal(ia, ib) and np.array_equal(ma, mb)
+    # and consecutive samples do not share noise
+    assert not np.array_equal(a[0][0], a[1][0])
