@@ -51,8 +51,7 @@ enum ConvMode {
   CONV3 = 0,        // 3x3, stride 1, pad 1                      (reference Conv2DW / nn.Conv2D)
   UPCONV3 = 1,      // nearest x2 then 3x3 pad 1, as 4 phases of 2x2 taps on the low-res input
   DECONV4 = 2,      // 4x4 stride-2 pad-1 transposed conv, as 4 phases of 2x2 taps
-  CONV1 = 3,        // 1x1
-  UPCONV1 = 4       // nearest x2 then 1x1 == 1x1 at low res (output stays low-res; consumer upsamples)
+  CONV1 = 3         // 1x1 (a res-block shortcut on the upsampled input == 1x1 at low res; the consumer upsamples)
 };
 
 enum EpiFlags {
@@ -79,13 +78,9 @@ struct ConvGeom {
                                //    (N_tile = 4*cout_tile); every distinct input shift is a single MMA whose
                                //    weight tile is zero for the phases that do not use that shift
   int cout_tile;               // output channels per CTA (= N_tile unless up_cols / hstack)
-  int hstack;                  // 1 (thin 3x3): the three horizontal taps kx are column blocks of ONE accumulator
-                               //    (N_tile = 3*cout_tile) fed by 3 MMAs (one per ky, shift ky*BW) instead of 9;
-                               //    the epilogue forms out[q] = acc[q][0] + acc[q+1][1] + acc[q+2][2] with warp
-                               //    shuffles (+ a 3x16-float smem hand-over between neighbouring warps)
-  int mt_stride;               // positions between consecutive MMA tiles: 128, or 126 with hstack (rows 126,127 of
-                               //    a tile only feed rows 124,125 and are recomputed as rows 0,1 of the next tile)
-  int xch_off;                 // byte offset of the hstack exchange buffer in dynamic smem
+  int hstack;                  // always 0 in this build (3 horizontal taps stacked along N: removed, see plan.cpp)
+  int mt_stride;               // positions between consecutive MMA tiles (128)
+  int xch_off;                 // unused (hstack exchange buffer)
   int aux_kind;                // epilogue operand staged per tile by TMA into smem (2 buffers): 0 none,
                                //   1 = noise plane tile [NB][TH][TW] fp32, 2 = residual tile (blocked, half resolution)
   int aux_off, aux_bytes;      // smem offset of the 2 aux buffers, bytes per buffer (128-aligned)
@@ -162,7 +157,7 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
                const PlanOverride* ov, int aux_kind = 0);
 void make_noise_tensormap(CUtensorMap* tm, const void* base, int N, int H, int W, int boxW, int boxH, int boxN);
 void finish_geom_for_batch(ConvGeom& g, int N);
-// weights: CONV3/UPCONV3 (Cout,Cin,3,3); DECONV4 (Cin,Cout,4,4); CONV1/UPCONV1 (Cout,Cin,1,1); fp32, already
+// weights: CONV3/UPCONV3 (Cout,Cin,3,3); DECONV4 (Cin,Cout,4,4); CONV1 (Cout,Cin,1,1); fp32, already
 // scaled (wscale / BN folded).  Returns packed act_t host buffer in the order the kernel streams it.
 void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& out);
 void make_act_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, int W, int boxW, int boxH, int boxN,
@@ -214,7 +209,6 @@ struct DenseArgs {            // y[n][u] = act( sum_k x'[n][k] W[u][k] + b[u] ),
   int pixelnorm;              // 1: x' = x * rsqrt(mean(x^2)+1e-8)  (first mapping layer)
   // styles mode: x' = avg*(1-psi[l]) + x*psi[l] with l = layer of unit u
   const float* latent_avg; const float* psi; const int* unit_layer;
-  float add_one_first_half;   // unused
 };
 void launch_dense(const DenseArgs& a, cudaStream_t st);
 
