@@ -109,6 +109,18 @@ int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z_host, cons
                       size_t synth_ws_bytes, void* dec_ws, size_t dec_ws_bytes, void* stage_dev,
                       size_t stage_bytes, gsx_stream stream, gsx_stream copy_stream, int slot);
 
+/* ---- decoder-training building blocks (seg_solver.py:351-465).  Round 1: loss and optimizer step only; the
+ *      decoder backward pass is not built yet.
+ * gsx_softmax_ce: SoftmaxCELoss(axis=1) with sample_weight = (label > -1) (seg_solver.py:404-407).
+ *   logits [n,classes,h,w] fp32, labels [n,h,w] int32 (-1 = ignore) -> loss_dev[n] (mean over all h*w pixels) and,
+ *   if dlogits_dev != NULL, d(sum_n loss_n)/dlogits.  scratch_dev: n*256 floats.
+ * gsx_adam_step: MXNet Adam on one flat fp32 bucket after the single gradient all-reduce (seg_solver.py:56,421):
+ *   lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t), g' = g*rescale_grad + wd*w. ---- */
+int gsx_softmax_ce(const float* logits_dev, const int* labels_dev, int n, int num_classes, int h, int w,
+                   float* loss_dev, float* dlogits_dev, float* scratch_dev, size_t scratch_floats, gsx_stream stream);
+int gsx_adam_step(float* w_dev, const float* g_dev, float* m_dev, float* v_dev, size_t count, int t, float lr, float beta1,
+                  float beta2, float eps, float wd, float rescale_grad, gsx_stream stream);
+
 /* ---- per-launch timing of the forward passes (bench.py's per-layer roofline table): enable, run a
  *      forward, dump "label\tms\talgorithmic_bytes\talgorithmic_flops\n" lines.  Off by default. ---- */
 int gsx_profile_enable(int on);

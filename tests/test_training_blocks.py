@@ -1,0 +1,89 @@
+"""Decoder-training building blocks: loss + flat-bucket all-reduce / Adam."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+
+@pytest.mark.gpu
+def test_softmax_ce_matches_reference_semantics(gsx_lib):
+    """SoftmaxCELoss(axis=1) with sample_weight=(mask>-1): per-sample mean over ALL pixels (ignored ones in the
+    denominator), gradient of the summed loss."""
+    from gan_segmentation_b200.training import softmax_ce
+    g = torch.Generator().manual_seed(0)
+    for k in (2, 5):
+        n, h, w = 3, 37, 53
+        lg = (torch.randn((n, k, h, w), generator=g) * 3).cuda().requires_grad_(True)
+        lab = torch.randint(-1, k, (n, 1, h, w), generator=g).cuda()
+        wgt = (lab > -1).float()
+        lp = F.log_softmax(lg, dim=1)
+        picked = -torch.gather(lp, 1, lab.clamp(min=0)) * wgt
+        ref = picked.mean(dim=(1, 2, 3))
+        ref.sum().backward()
+        loss, dl = softmax_ce(lg.detach(), lab.int())
+        assert torch.allclose(loss, ref.detach(), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(dl, lg.grad, rtol=1e-4, atol=1e-8)
+
+
+@pytest.mark.gpu
+def test_flat_adam_matches_mxnet_formula(gsx_lib):
+    from gan_segmentation_b200.training import FlatAdam
+    shapes = {'a.weight': (7, 5, 3, 3), 'a.bias': (7,), 'b.gamma': (11,)}
+    opt = FlatAdam(shapes, lr=1e-2, wd=1e-3)
+    rs = np.random.RandomState(0)
+    params = {k: rs.randn(*s).astype(np.float32) for k, s in shapes.items()}
+    opt.load(params)
+    w = np.concatenate([params[k].ravel() for k in shapes]).astype(np.float64)
+    m = np.zeros_like(w); v = np.zeros_like(w)
+    for t in range(1, 4):
+        g = rs.randn(w.size).astype(np.float32)
+        opt.g.copy_(torch.from_numpy(g))
+        opt.step(global_batch=4)
+        gg = g.astype(np.float64) / 4 + 1e-3 * w
+        m = 0.9 * m + 0.1 * gg
+        v = 0.999 * v + 0.001 * gg * gg
+        lr_t = 1e-2 * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+        w = w - lr_t * m / (np.sqrt(v) + 1e-8)
+    torch.cuda.synchronize()
+    assert np.allclose(opt.w.cpu().numpy(), w, rtol=2e-5, atol=1e-6)
+    assert opt.state()['a.bias'].shape == (7,)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from gan_segmentation_b200.training import FlatAdam
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    opt = FlatAdam({'w': (4, 3), 'b': (5,)}, device='cpu')
+    opt.g.copy_(torch.arange(opt.count, dtype=torch.float32) * (rank + 1))
+    opt.allreduce_grads()                         # the only collective of a training step
+    if rank == 0:
+        q.put(opt.g.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_gloo_two_ranks():
+    """world_size-2 on CPU: one all-reduce over the flat gradient bucket sums the ranks' gradients."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    g = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(g, np.arange(17, dtype=np.float32) * 3)
