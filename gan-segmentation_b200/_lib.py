@@ -15,7 +15,7 @@ DEFAULT_DTYPE = os.environ.get('GSX_DTYPE', 'fp16')
 CSRC = os.path.join(_HERE, 'csrc')
 
 # enums of gsx_internal.h / gsx.h
-CONV3, UPCONV3, DECONV4, CONV1 = 0, 1, 2, 3
+CONV3, UPCONV3, DECONV4, CONV1, DECONV4B = 0, 1, 2, 3, 4
 EPI_LRELU, EPI_STATS, EPI_ARGMAX = 1, 2, 4
 
 

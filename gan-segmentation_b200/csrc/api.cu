@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -103,7 +104,7 @@ static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1
   double bytes = 2.0 * in_el + ((epi.flags & EPI_ARGMAX) ? out_px : 2.0 * out_px * L.cout);
   if (epi.noise) bytes += 4.0 * out_px;
   if (epi.addsrc) bytes += 2.0 * out_px / 4 * L.cout;
-  const double taps = L.mode == CONV1 ? 1 : (L.mode == DECONV4 ? 4 : 9);    // per OUTPUT pixel
+  const double taps = L.mode == CONV1 ? 1 : ((L.mode == DECONV4 || L.mode == DECONV4B) ? 4 : 9);    // per OUTPUT pixel
   const double flops = 2.0 * out_px * taps * (L.cin0 + L.cin1) * L.cout;
   ProfScope ps(label, bytes, flops, st);
   ConvParams p;
@@ -118,7 +119,7 @@ static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1
   else p.tm[1] = p.tm[0];
   if (p.g.aux_kind == 1) {
     if (!epi.noise) p.g.aux_kind = 0;
-    else make_noise_tensormap(&p.tm_aux, epi.noise, N, epi.Ho, epi.Wo, p.g.TW, p.g.TH, p.g.NB);
+    else make_noise_tensormap(&p.tm_aux, epi.noise, N, epi.Ho, epi.Wo, p.g.TW << p.g.aux_up, p.g.TH << p.g.aux_up, p.g.NB);
   } else if (p.g.aux_kind == 2) {
     if (!epi.addsrc) p.g.aux_kind = 0;
     else make_act_tensormap(&p.tm_aux, epi.addsrc, L.cout, N, epi.Ho / 2, epi.Wo / 2, p.g.aux_bw, p.g.aux_bh, p.g.NB,
@@ -153,6 +154,8 @@ struct SynthBlock {
   int r, C, Cin, H, W;
   ConvLayer conv1, conv2;                 // conv1 unused at r == 2
   float *ns1 = nullptr, *b1 = nullptr, *ns2 = nullptr, *b2 = nullptr;
+  bool fold = false;                      // conv1 = deconv + blur + noise/bias/lrelu/stats in one kernel (DECONV4B)
+  float* wt = nullptr;                    // fold: scaled deconv weights [4][4][Cin][C] fp32 for the border correction
 };
 
 struct gsx_synth {
@@ -186,6 +189,7 @@ struct SynthWs {
   std::vector<int> stats_T;
   std::vector<act_t*> feat;
   act_t *bufA, *bufB;
+  float *e_rows, *e_cols;                 // border corrections of the folded deconv+blur layers
   size_t total;
 };
 
@@ -219,6 +223,11 @@ static SynthWs synth_layout(const gsx_synth* h, int N, void* base) {
   }
   w.bufA = a.take<act_t>(maxact);
   w.bufB = a.take<act_t>(maxact);
+  size_t maxe = 0;
+  for (const auto& b : h->blocks)
+    if (b.fold) maxe = std::max(maxe, (size_t)N * 2 * std::max(b.H, b.W) * b.C);
+  w.e_rows = a.take<float>(maxe);
+  w.e_cols = a.take<float>(maxe);
   w.total = a.off;
   return w;
 }
@@ -226,7 +235,13 @@ static SynthWs synth_layout(const gsx_synth* h, int N, void* base) {
 static int synth_stats_tiles(const gsx_synth* h, int l) {
   int hh, ww;
   h->hw(2 + l / 2, hh, ww);
-  if ((l & 1) == 0) return pass1_tiles(hh, ww);
+  if ((l & 1) == 0) {
+    if ((size_t)(l / 2) < h->blocks.size() && h->blocks[l / 2].fold) {
+      const ConvGeom& g = h->blocks[l / 2].conv1.g;
+      return g.tiles_x * g.tiles_y;
+    }
+    return pass1_tiles(hh, ww);
+  }
   if ((size_t)(l / 2) < h->blocks.size()) {
     const ConvGeom& g = h->blocks[l / 2].conv2.g;
     if (g.NB == 1) return g.tiles_x * g.tiles_y;
@@ -363,7 +378,7 @@ extern "C" int gsx_synth_finalize(gsx_synth* h) {
   for (auto& b : h->blocks) {
     cudaFree(b.conv1.wpack_dev); cudaFree(b.conv2.wpack_dev);
     cudaFree(b.conv1.taps_dev); cudaFree(b.conv2.taps_dev);
-    cudaFree(b.ns1); cudaFree(b.b1); cudaFree(b.ns2); cudaFree(b.b2);
+    cudaFree(b.ns1); cudaFree(b.b1); cudaFree(b.ns2); cudaFree(b.b2); cudaFree(b.wt);
   }
   h->blocks.clear();
   for (int r = 2; r <= L; ++r) {
@@ -379,7 +394,28 @@ extern "C" int gsx_synth_finalize(gsx_synth* h) {
       const float std_ = (float)(std::sqrt(2.0) / std::sqrt((double)k * k * b.Cin));   // :399-403
       std::vector<float> ws(w->v);
       for (auto& x : ws) x *= std_;
-      plan_conv(b.conv1, deconv ? DECONV4 : UPCONV3, b.H / 2, b.W / 2, b.Cin, 0, b.C, 0, nullptr);
+      // thin deconv layers (phases stacked along the MMA N dimension anyway): fold the blur and the whole first-half
+      // epilogue into the conv -- removes the separate blur/noise/bias/lrelu/stats pass over the largest tensors
+      // (measured r01: 16-channel 1024^2 layer 1.01 -> 0.81 ms; at 32 channels the heavier epilogue cancels the gain,
+      //  GSX_FOLD_MAXC raises the limit for experiments)
+      const char* fm = getenv("GSX_FOLD_MAXC");
+      const int fold_maxc = fm ? atoi(fm) : 16;
+      if (deconv && b.C <= fold_maxc && b.C < 64) {
+        set_error("");
+        plan_conv(b.conv1, DECONV4B, b.H / 2, b.W / 2, b.Cin, 0, b.C, 0, nullptr, /*aux: noise tile*/ 1);
+        b.fold = !*gsx_last_error() && b.conv1.g.NB == 1 && b.conv1.g.up_cols;
+      }
+      if (b.fold) {
+        std::vector<float> wt((size_t)16 * b.Cin * b.C);
+        for (int ci = 0; ci < b.Cin; ++ci)
+          for (int co = 0; co < b.C; ++co)
+            for (int t = 0; t < 16; ++t) wt[((size_t)t * b.Cin + ci) * b.C + co] = ws[((size_t)ci * b.C + co) * 16 + t];
+        b.wt = dev_upload(wt);
+        if (!b.wt) return -2;
+      } else {
+        set_error("");
+        plan_conv(b.conv1, deconv ? DECONV4 : UPCONV3, b.H / 2, b.W / 2, b.Cin, 0, b.C, 0, nullptr);
+      }
       if (*gsx_last_error()) return -1;
       if (!upload_conv(b.conv1, ws.data())) return -2;
     }
@@ -510,7 +546,17 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     Pass1Args p1{};
     p1.out = w.bufB; p1.C = b.C; p1.N = N; p1.H = b.H; p1.W = b.W;
     p1.nscale = b.ns1; p1.bias = b.b1; p1.noise = noise[l1]; p1.stats = st1;
-    if (b.r == 2) {
+    if (b.fold) {
+      { ProfScope ps(tag + "border", 0, 0, st);
+        launch_deconv_border(w.feat[bi - 1], b.wt, w.e_rows, w.e_cols, N, b.Cin, b.C, b.H / 2, b.W / 2, st); g_launches++; }
+      ConvEpi e{};
+      e.out = w.bufB; e.Ho = b.H; e.Wo = b.W; e.up = 1; e.Cout = b.C;
+      e.flags = EPI_LRELU | EPI_STATS;
+      e.bias = b.b1; e.nscale = b.ns1; e.noise = noise[l1];
+      e.stats = st1; e.stats_T = w.stats_T[l1];
+      e.e_rows = w.e_rows; e.e_cols = w.e_cols;
+      if (!run_conv(b.conv1, N, w.feat[bi - 1], nullptr, e, st, (tag + "deconv+blur").c_str())) return -2;
+    } else if (b.r == 2) {
       p1.in = h->d_const; p1.in_broadcast = 1; p1.blur = 0;
     } else {
       ConvEpi e{};
@@ -518,7 +564,7 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
       if (!run_conv(b.conv1, N, w.feat[bi - 1], nullptr, e, st, (tag + (b.r >= 7 ? "deconv" : "upconv")).c_str())) return -2;
       p1.in = w.bufA; p1.in_broadcast = 0; p1.blur = 1;
     }
-    { ProfScope ps(tag + "pass1", (b.r == 2 ? 1.0 : 2.0) * act_bytes + plane_bytes, 0, st); launch_pass1(p1, st); g_launches++; }
+    if (!b.fold) { ProfScope ps(tag + "pass1", (b.r == 2 ? 1.0 : 2.0) * act_bytes + plane_bytes, 0, st); launch_pass1(p1, st); g_launches++; }
     { ProfScope ps(tag + "finalize", 0, 0, st);
       launch_finalize(st1, w.stats_T[l1], N, b.C, b.H * b.W, w.styles, h->S_total, h->style_off[l1], w.coef[l1], st);
       g_launches++; }

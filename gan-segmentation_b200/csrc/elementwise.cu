@@ -477,4 +477,86 @@ void launch_fill_latents(float* z, int N, int Z, uint64_t seed, uint64_t first_s
   fill_normal_kernel<<<grid, 128, 0, st>>>(z, (size_t)Z, N, seed, first_sample, 0xFFFFu);
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// Border correction of the folded transposed-conv + blur (DECONV4B, plan.cpp).  The reference blurs the CROPPED
+// deconv output D (networks_stylegan.py:16-17: Conv2DTranspose(4, stride 2, pad 1) then Blur with zero padding), the
+// folded 3x3-per-phase composite also sees the ring of D just outside the crop (rows -1 and Ho, columns -1 and Wo).
+// E = the blur taps that land on that ring; the conv epilogue subtracts it on the 1-pixel output border:
+//   e_rows[n][s][X][co] = 1/4 * sum_dx bl[dx] D[s ? Ho : -1][X+dx]                      (X+dx in -1..Wo)
+//   e_cols[n][s][Y][co] = 1/4 * sum_dy bl[dy] D[Y+dy][s ? Wo : -1]   for 0 <= Y+dy < Ho (corner terms live in e_rows)
+// A ring value only sees one input row/column: <= 2 taps x Cin MACs.  grid (segments, 4 sides, N).
+// ----------------------------------------------------------------------------------------------------------------
+static constexpr int kBorderSeg = 30;                 // border pixels per block (ring positions: +2)
+static constexpr int kBorderThreads = 128;
+
+__global__ void __launch_bounds__(kBorderThreads) deconv_border_kernel(const act_t* __restrict__ x, const float* __restrict__ wt,
+                                                                       float* __restrict__ e_rows, float* __restrict__ e_cols,
+                                                                       int N, int Cin, int Cout, int H, int W) {
+  extern __shared__ float ring[];                      // [kBorderSeg + 2][Cout]
+  const int side = blockIdx.y, n = blockIdx.z;         // 0 top, 1 bottom, 2 left, 3 right
+  const int Ho = 2 * H, Wo = 2 * W;
+  const bool is_row = side < 2;
+  const int len = is_row ? Wo : Ho;
+  const int p0 = blockIdx.x * kBorderSeg;
+  if (p0 >= len) return;
+  const size_t plane = (size_t)H * W;
+  for (int idx = threadIdx.x; idx < (kBorderSeg + 2) * Cout; idx += kBorderThreads) {
+    const int r = idx / Cout, co = idx - r * Cout;
+    const int P = p0 - 1 + r;                          // position along the side, ring coordinates
+    int Yr, Xr;
+    bool live;
+    if (is_row) { Yr = side == 0 ? -1 : Ho; Xr = P; live = P >= -1 && P <= Wo; }
+    else        { Xr = side == 2 ? -1 : Wo; Yr = P; live = P >= 0 && P < Ho; }
+    float acc = 0.f;
+    if (live) {
+      // D[Y][X], Y = 2i'+p':  sum_a in[i'+p'-1+a] * w[a == 0 ? 3-p' : 1-p']
+      const int ip = (Yr + 2) / 2 - 1, pp = (Yr + 2) & 1, jp = (Xr + 2) / 2 - 1, qp = (Xr + 2) & 1;
+      for (int ay = 0; ay < 2; ++ay) {
+        const int iy = ip + pp - 1 + ay;
+        if (iy < 0 || iy >= H) continue;
+        const int ky = ay == 0 ? 3 - pp : 1 - pp;
+        for (int ax = 0; ax < 2; ++ax) {
+          const int ix = jp + qp - 1 + ax;
+          if (ix < 0 || ix >= W) continue;
+          const int kx = ax == 0 ? 3 - qp : 1 - qp;
+          const float* wk = wt + ((size_t)(ky * 4 + kx) * Cin) * Cout + co;
+          for (int cb = 0; cb < Cin / 8; ++cb) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)cb * N + n) * plane + (size_t)iy * W + ix) * 8));
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#if GSX_FP16
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[k]));
+#else
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[k]));
+#endif
+              acc = fmaf(f.x, __ldg(wk + (size_t)(cb * 8 + 2 * k) * Cout), acc);
+              acc = fmaf(f.y, __ldg(wk + (size_t)(cb * 8 + 2 * k + 1) * Cout), acc);
+            }
+          }
+        }
+      }
+    }
+    ring[idx] = acc;
+  }
+  __syncthreads();
+  float* dst = (is_row ? e_rows : e_cols) + ((size_t)n * 2 + (side & 1)) * len * Cout;
+  for (int idx = threadIdx.x; idx < kBorderSeg * Cout; idx += kBorderThreads) {
+    const int q = idx / Cout, co = idx - q * Cout;
+    const int P = p0 + q;
+    if (P >= len) break;
+    const float v = 0.25f * (0.25f * ring[q * Cout + co] + 0.5f * ring[(q + 1) * Cout + co] + 0.25f * ring[(q + 2) * Cout + co]);
+    dst[(size_t)P * Cout + co] = v;
+  }
+}
+
+void launch_deconv_border(const act_t* x, const float* wt, float* e_rows, float* e_cols, int N, int Cin, int Cout, int H,
+                          int W, cudaStream_t st) {
+  const int len = 2 * (H > W ? H : W);
+  dim3 grid((len + kBorderSeg - 1) / kBorderSeg, 4, N);
+  deconv_border_kernel<<<grid, kBorderThreads, (kBorderSeg + 2) * Cout * sizeof(float), st>>>(x, wt, e_rows, e_cols, N, Cin,
+                                                                                             Cout, H, W);
+}
+
 }  // namespace gsx

@@ -51,7 +51,11 @@ enum ConvMode {
   CONV3 = 0,        // 3x3, stride 1, pad 1                      (reference Conv2DW / nn.Conv2D)
   UPCONV3 = 1,      // nearest x2 then 3x3 pad 1, as 4 phases of 2x2 taps on the low-res input
   DECONV4 = 2,      // 4x4 stride-2 pad-1 transposed conv, as 4 phases of 2x2 taps
-  CONV1 = 3         // 1x1 (a res-block shortcut on the upsampled input == 1x1 at low res; the consumer upsamples)
+  CONV1 = 3,        // 1x1 (a res-block shortcut on the upsampled input == 1x1 at low res; the consumer upsamples)
+  DECONV4B = 4      // DECONV4 followed by the 3x3 [1,2,1]^2/16 blur, folded into ONE up-conv: 4 phases of 3x3 low-res
+                    //   taps (the same 9 input shifts the stacked-phase DECONV4 already issues, so no extra MMAs).
+                    //   Exact in the interior; the 1-pixel output border gets a correction (the blur zero-pads the
+                    //   CROPPED deconv output) from launch_deconv_border, subtracted in the epilogue.
 };
 
 enum EpiFlags {
@@ -86,6 +90,7 @@ struct ConvGeom {
   int aux_off, aux_bytes;      // smem offset of the 2 aux buffers, bytes per buffer (128-aligned)
   int aux_bytes_tx;            // bytes one TMA box delivers (the mbarrier transaction count)
   int aux_bw, aux_bh;          // residual box: columns / rows at half resolution
+  int aux_up;                  // 1: the noise tile is at the OUTPUT resolution of an up-conv (2TH x 2TW)
   int n_slots;                 // filter taps per CTA
   int phase_grid;              // 1: blockIdx.z selects the phase (wide up-convs)
   int stages;
@@ -117,6 +122,8 @@ struct ConvEpi {
   float* stats;                // per-tile partial sums [N][stats_T][Cout][2] (sum, sumsq) or null; no atomics,
   int stats_T;                 //   so the InstanceNorm statistics are bit-reproducible (T = tiles per sample)
   const act_t* addsrc;          // blocked [Cout/8][N][Ho/2][Wo/2][8], added after activation, or null
+  const float* e_rows;         // DECONV4B border corrections: [N][2 (top,bottom)][Wo][Cout] and
+  const float* e_cols;         //   [N][2 (left,right)][Ho][Cout] fp32, subtracted before noise / bias; or null
   unsigned char* mask;         // [N][Ho][Wo]
   float* logits;               // [N][num_classes][Ho][Wo] or null
   int num_classes;
@@ -165,6 +172,11 @@ void make_act_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, 
 
 // launchers (shiftconv.cu / elementwise.cu / styles.cu)
 void launch_shiftconv(const ConvParams& p, cudaStream_t st);
+
+// Border correction of the folded deconv + blur (DECONV4B).  x: blocked low-res input [Cin/8][N][H][W][8];
+// wt: the (scaled) transposed-conv weights rearranged to [4][4][Cin][Cout] fp32.
+void launch_deconv_border(const act_t* x, const float* wt, float* e_rows, float* e_cols, int N, int Cin, int Cout, int H,
+                          int W, cudaStream_t st);
 
 struct Pass1Args {            // blur? + noise + bias + lrelu + stats  (generator, first half of a block)
   const act_t* in; act_t* out;  // blocked; in may have sample stride 0 (constant tensor)

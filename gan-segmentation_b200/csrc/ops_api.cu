@@ -30,7 +30,7 @@ extern "C" int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, in
                            uint8_t* mask_dev, float* logits_dev, int num_classes, const gsx_plan_override* ov,
                            int* plan_out, int repeat, float* ms_out, gsx_stream stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool up = (mode == UPCONV3 || mode == DECONV4);
+  const bool up = (mode == UPCONV3 || mode == DECONV4 || mode == DECONV4B);
   const bool argmax = (flags & EPI_ARGMAX) != 0;
   const int Ho = up ? 2 * h : h, Wo = up ? 2 * w : w;
   Tmp tmp;
@@ -77,11 +77,26 @@ extern "C" int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, in
   if (want_stats && !partial) { set_error("cudaMalloc failed"); return -2; }
   e.stats = fused_stats ? partial : nullptr;
   e.stats_T = stats_T;
+  if (mode == DECONV4B) {
+    // border correction of the folded deconv+blur: weights rearranged to [ky][kx][Cin][Cout]
+    std::vector<float> wt((size_t)16 * cin0 * cout);
+    for (int ci = 0; ci < cin0; ++ci)
+      for (int co = 0; co < cout; ++co)
+        for (int k = 0; k < 16; ++k) wt[((size_t)k * cin0 + ci) * cout + co] = w_host[((size_t)ci * cout + co) * 16 + k];
+    float* wt_d = tmp.get<float>(wt.size());
+    float* er = tmp.get<float>((size_t)n * 2 * Wo * cout);
+    float* ec = tmp.get<float>((size_t)n * 2 * Ho * cout);
+    if (!wt_d || !er || !ec) { set_error("cudaMalloc failed"); return -2; }
+    cudaMemcpyAsync(wt_d, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);                       // wt is a local
+    launch_deconv_border(xb0, wt_d, er, ec, n, cin0, cout, h, w, st); g_launches++;
+    e.e_rows = er; e.e_cols = ec;
+  }
   p.e = e;
   make_act_tensormap(&p.tm[0], xb0, cin0, n, h, w, p.g.BW, p.g.BH, p.g.NB, p.g.CBK);
   if (cin1) make_act_tensormap(&p.tm[1], xb1, cin1, n, h, w, p.g.BW, p.g.BH, p.g.NB, p.g.CBK);
   else p.tm[1] = p.tm[0];
-  if (p.g.aux_kind == 1) make_noise_tensormap(&p.tm_aux, noise_dev, n, Ho, Wo, p.g.TW, p.g.TH, p.g.NB);
+  if (p.g.aux_kind == 1) make_noise_tensormap(&p.tm_aux, noise_dev, n, Ho, Wo, p.g.TW << p.g.aux_up, p.g.TH << p.g.aux_up, p.g.NB);
   else if (p.g.aux_kind == 2) make_act_tensormap(&p.tm_aux, ab, cout, n, Ho / 2, Wo / 2, p.g.aux_bw, p.g.aux_bh, p.g.NB, p.g.cout_tile / 8);
   else p.tm_aux = p.tm[0];
   if (*last_error_cstr()) return -1;

@@ -36,7 +36,7 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   ConvGeom& g = L.g;
   std::memset(&g, 0, sizeof(g));
   g.H = H; g.W = W;
-  const bool up = (mode == UPCONV3 || mode == DECONV4);
+  const bool up = (mode == UPCONV3 || mode == DECONV4 || mode == DECONV4B);
   const int cb0 = cin0 / 8, cb1 = cin1 / 8, cbt = cb0 + cb1;
 
   int N_tile = argmax_classes > 0 ? 16 : std::min(cout, 128);
@@ -45,6 +45,10 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   // 590 KB streamed per 256 pixels at 128->64, measured 0.36 ms vs 0.25 ms), as column blocks of one MMA below
   int phase_grid = (up && cout >= 64) ? 1 : 0;
   if (ov && ov->phase_grid >= 0 && up) phase_grid = ov->phase_grid;
+  if (mode == DECONV4B) {
+    if (cout > 64) { set_error("plan_conv: DECONV4B needs cout <= 64 (phases stacked along N)"); return; }
+    phase_grid = 0;
+  }
   const int up_cols = (up && !phase_grid) ? 1 : 0;
   const int cout_tile = N_tile;
   if (up_cols) N_tile = 4 * cout_tile;        // phases stacked along the MMA N dimension (<= 256)
@@ -97,13 +101,19 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
 
   const int n_slots = (mode == CONV3) ? (hstack ? 3 : 9) : (mode == CONV1 ? 1 : (phase_grid ? 4 : 9));
 
-  if (mode != CONV3 || (W * 4) % 16 != 0 || (TW & 1)) aux_kind = 0;       // aux staging: plain 3x3 layers only
+  // aux staging: plain 3x3 layers (noise / residual tile) and the folded deconv (noise tile at output resolution);
+  // the TMA box row must be a multiple of 16 bytes
+  const int aux_up = (mode == DECONV4B) ? 1 : 0;
+  if (mode != CONV3 && mode != DECONV4B) aux_kind = 0;
+  if (mode == DECONV4B && aux_kind == 2) aux_kind = 0;
+  if (aux_kind == 1 && ((((W << aux_up) * 4) % 16) != 0 || (((TW << aux_up) * 4) % 16) != 0)) aux_kind = 0;
+  if (aux_kind == 2 && (TW & 1)) aux_kind = 0;
   // k-chunk depth and pipeline stages under the shared-memory limit
   int CBK = 0, stages = 0, b_resident = 0;
   long aux_bytes = 0;
   for (;;) {
     const int BH = TH + 2;
-    aux_bytes = aux_kind == 1 ? (long)NB * TH * TW * 4
+    aux_bytes = aux_kind == 1 ? ((long)NB * TH * TW * 4) << (2 * aux_up)
               : aux_kind == 2 ? (long)NB * (TH / 2 + 1) * (TW / 2) * 16 * (cout_tile / 8) : 0;
     aux_bytes = (aux_bytes + 127) / 128 * 128;
     int cbs[4] = {8, 4, 2, 0};
@@ -161,7 +171,8 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   g.ctas_per_sm = 1;
   g.aux_kind = aux_kind; g.aux_off = hdr_bytes; g.aux_bytes = (int)aux_bytes;
   g.aux_bw = TW / 2; g.aux_bh = TH / 2 + 1;
-  g.aux_bytes_tx = aux_kind == 1 ? NB * TH * TW * 4 : aux_kind == 2 ? NB * (TH / 2 + 1) * (TW / 2) * 16 * (cout_tile / 8) : 0;
+  g.aux_up = aux_up;
+  g.aux_bytes_tx = aux_kind == 1 ? (NB * TH * TW * 4) << (2 * aux_up) : aux_kind == 2 ? NB * (TH / 2 + 1) * (TW / 2) * 16 * (cout_tile / 8) : 0;
   g.a_off = hdr_bytes + 2 * (int)aux_bytes;
   g.magic_box = (unsigned)((0x100000000ULL + (unsigned long long)(g.BH * BW) - 1) / (unsigned long long)(g.BH * BW));
   g.magic_bw = (unsigned)((0x100000000ULL + (unsigned long long)BW - 1) / (unsigned long long)BW);
@@ -219,7 +230,7 @@ void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& o
   const int k16pc = g.CBK / 2;
   const size_t tile = (size_t)g.N_tile * 16;
   out.assign((size_t)nz * g.n_ntiles * g.n_k * g.n_slots * k16pc * tile, to_act(0.f));
-  const bool up = (L.mode == UPCONV3 || L.mode == DECONV4);
+  const bool up = (L.mode == UPCONV3 || L.mode == DECONV4 || L.mode == DECONV4B);
 
   auto wval = [&](int z, int slot, int co, int ci) -> float {   // co: row of the MMA weight tile
     if (L.mode == CONV3 && g.hstack) {                       // row block kx of the weight tile, slot = ky
@@ -229,6 +240,29 @@ void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& o
     }
     if (L.mode == CONV3) { const int ky = slot / 3, kx = slot % 3; return w[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx]; }
     if (L.mode == CONV1) return w[(size_t)co * cin + ci];
+    if (L.mode == DECONV4B) {
+      // composite of the transposed conv and the blur on the low-res grid.  1-D: out[2i+p] = sum_d bl[d] D[2i+p+d],
+      // D[2i'+p'] = sum_a in[i'+p'-1+a] * w[a == 0 ? 3-p' : 1-p'];  slot = (ty+1)*3 + (tx+1), input offset t in -1..1
+      const int ph = co / g.cout_tile, c = co % g.cout_tile;
+      if (c >= cout) return 0.f;
+      const int py = ph >> 1, px = ph & 1, ty = slot / 3 - 1, tx = slot % 3 - 1;
+      static const double bl[3] = {0.25, 0.5, 0.25};
+      double acc = 0.0;
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int ay = 0; ay < 2; ++ay) {
+          const int Yp = py + dy + 2, ip = Yp / 2 - 1, pp = Yp & 1;      // 2i+py+dy = 2(i+ip)+pp
+          if (ip + pp - 1 + ay != ty) continue;
+          const int ky = ay == 0 ? 3 - pp : 1 - pp;
+          for (int dx = -1; dx <= 1; ++dx)
+            for (int ax = 0; ax < 2; ++ax) {
+              const int Xp = px + dx + 2, jp = Xp / 2 - 1, qp = Xp & 1;
+              if (jp + qp - 1 + ax != tx) continue;
+              const int kx = ax == 0 ? 3 - qp : 1 - qp;
+              acc += bl[dy + 1] * bl[dx + 1] * (double)w[(((size_t)ci * cout + c) * 4 + ky) * 4 + kx];
+            }
+        }
+      return (float)acc;
+    }
     int ph, a, b;
     if (g.phase_grid) { ph = z; a = slot >> 1; b = slot & 1; }
     else {

@@ -45,6 +45,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 24)) __trap();
   }
 }
+// Same, for the single-thread producer: sleeps between polls so that its spin does not take issue slots from the
+// epilogue warps sharing its scheduler (the producer runs several stages ahead; wake-up latency is hidden).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(100);
+    if (++spins > (1u << 22)) __trap();
+  }
+}
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {

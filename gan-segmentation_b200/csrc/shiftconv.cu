@@ -63,17 +63,47 @@ __device__ __forceinline__ float2 unpack_x2(uint32_t w) {
 #endif
 }
 
+// 32 values (16 sums, 16 sums of squares) x 32 lanes -> lane L returns value L fully reduced over the warp
+__device__ __forceinline__ float warp_reduce_32x32(const float (&s1)[16], const float (&s2)[16], int lane) {
+  float vals[32];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { vals[i] = s1[i]; vals[16 + i] = s2[i]; }
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    const int half = 16 >> step;                      // values kept per lane after this step
+    const bool upper = (lane & half) != 0;            // lane bit deciding which half is kept
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = upper ? vals[half + i] : vals[i];
+      const float send = upper ? vals[i] : vals[half + i];
+      vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return vals[0];
+}
+
 struct TileCoord { int x0, y0, n0, ntile, phase, tile_in_sample; };
+
+// a / d for 0 <= a < 2^24 via the float reciprocal (+ one correction step): ~8 instructions instead of the ~35 of an
+// integer division -- decode_tile runs once per work item in all three roles.
+__device__ __forceinline__ int fast_div(int a, int d, int& rem) {
+  int q = __float2int_rz(__int2float_rz(a) * __frcp_rn(__int2float_rz(d)));
+  int r = a - q * d;
+  if (r < 0) { --q; r += d; }
+  if (r >= d) { ++q; r -= d; }
+  rem = r;
+  return q;
+}
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int t) {
   TileCoord c;
   const int sp = g.tiles_x * g.tiles_y * g.tiles_n;
-  int s = t % sp;
-  const int rest = t / sp;
-  c.ntile = rest % g.n_ntiles;
-  c.phase = rest / g.n_ntiles;
-  const int tx = s % g.tiles_x; s /= g.tiles_x;
-  const int ty = s % g.tiles_y; s /= g.tiles_y;
+  int s;
+  const int rest = fast_div(t, sp, s);
+  c.phase = fast_div(rest, g.n_ntiles, c.ntile);
+  int tx, ty;
+  s = fast_div(s, g.tiles_x, tx);
+  s = fast_div(s, g.tiles_y, ty);
   c.x0 = tx * g.TW; c.y0 = ty * g.TH; c.n0 = s * g.NB;
   c.tile_in_sample = ty * g.tiles_x + tx;
   return c;
@@ -142,17 +172,17 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         if (g.aux_kind) {
           // per-tile epilogue operand (noise plane tile / residual tile), double buffered on its own barriers
           const int ab = tlp & 1;
-          if (tlp >= 2) mbar_wait(&hdr->aux_empty[ab], (uint32_t)(((tlp >> 1) - 1) & 1));
+          if (tlp >= 2) mbar_wait_relaxed(&hdr->aux_empty[ab], (uint32_t)(((tlp >> 1) - 1) & 1));
           mbar_expect_tx(&hdr->aux_full[ab], (uint32_t)g.aux_bytes_tx);
           uint8_t* dst = smem + g.aux_off + (size_t)ab * g.aux_bytes;
-          if (g.aux_kind == 1) tma_load_3d(dst, &p.tm_aux, &hdr->aux_full[ab], tc.x0, tc.y0, tc.n0);
+          if (g.aux_kind == 1) tma_load_3d(dst, &p.tm_aux, &hdr->aux_full[ab], tc.x0 << g.aux_up, tc.y0 << g.aux_up, tc.n0);
           else tma_load_4d(dst, &p.tm_aux, &hdr->aux_full[ab], (tc.x0 >> 1) * 2, tc.y0 >> 1, tc.n0, tc.ntile * (g.cout_tile >> 3));
         }
         const act_t* wsrc = p.wpack + ((size_t)(tc.phase * g.n_ntiles + tc.ntile) * g.n_k) * b_stage_elems;
         for (int kc = 0; kc < g.n_k; ++kc, ++it) {
           const int s = it % g.stages;
           const int round = it / g.stages;
-          if (round > 0) mbar_wait(&hdr->empty[s], (uint32_t)((round - 1) & 1));
+          if (round > 0) mbar_wait_relaxed(&hdr->empty[s], (uint32_t)((round - 1) & 1));
           mbar_expect_tx(&hdr->full[s], stage_bytes);
           const int src = kc < g.kch0 ? 0 : 1;
           const int cb0 = (src ? kc - g.kch0 : kc) * g.CBK;
@@ -288,42 +318,99 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
       } else if (g.up_cols) {
         // up-conv with the 4 phases as column blocks: the px=0 / px=1 outputs of a low-res pixel are adjacent in
         // the output row, so both phases are processed together and leave as ONE 32-byte store per channel block
-        // (full sectors instead of two half-sector writes).  Raw or bias+lrelu epilogue only.
-        for (int pc = 0; pc < 2 * cpp; ++pc) {
-          const int py = pc / cpp, c16 = pc - py * cpp;
+        // (full sectors instead of two half-sector writes).  GEN adds the generator's first-half epilogue for the
+        // folded deconv+blur: border correction, noise (tile staged at output resolution), statistics.
+        const float slope = do_act ? 0.2f : 1.0f;
+        for (int c16 = 0; c16 < cpp; ++c16) {
           const int c0 = tc.ntile * g.cout_tile + c16 * 16;
-          const int col0 = ((2 * py) * cpp + c16) * 16, col1 = ((2 * py + 1) * cpp + c16) * 16;
-          float bias_r[16];
+          float bias_r[16], ns_r[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) bias_r[i] = e.bias ? __ldg(e.bias + c0 + i) : 0.f;
-          for (int u = egrp; u < n_units; u += G) {
-            uint32_t va[16], vb[16];
-            tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + col0), va);
-            tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + col1), vb);
-            int n, y, x;
-            const bool valid = locate(u, n, y, x);
-            const size_t pix = (size_t)(2 * y + py) * e.Wo + 2 * x;
-            tmem_ld_wait();
-            if (valid) {
+          for (int i = 0; i < 16; ++i) {
+            bias_r[i] = e.bias ? __ldg(e.bias + c0 + i) : 0.f;
+            ns_r[i] = (GEN && e.nscale) ? __ldg(e.nscale + c0 + i) : 0.f;
+          }
+          float s1[16], s2[16];
+          if (GEN) {
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                if (c0 + h * 8 < e.Cout) {
+            for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+          }
+          for (int py = 0; py < 2; ++py) {
+            const int col0 = ((2 * py) * cpp + c16) * 16, col1 = ((2 * py + 1) * cpp + c16) * 16;
+            for (int u = egrp; u < n_units; u += G) {
+              uint32_t va[16], vb[16];
+              tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + col0), va);
+              tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + col1), vb);
+              int n, y, x;
+              const bool valid = locate(u, n, y, x);
+              const int Y = 2 * y + py;
+              const size_t pix = (size_t)Y * e.Wo + 2 * x;
+              float nz0 = 0.f, nz1 = 0.f;
+              if (GEN && valid) {
+                if (g.aux_kind == 1) {
+                  const float2 t2 = *reinterpret_cast<const float2*>(
+                      reinterpret_cast<const float*>(aux) + ((size_t)(nb_l * 2 * g.TH + 2 * yl_l + py) * (2 * g.TW) + 2 * xl_l));
+                  nz0 = t2.x; nz1 = t2.y;
+                } else if (e.noise) {
+                  const float2 t2 = __ldg(reinterpret_cast<const float2*>(e.noise + (size_t)n * plane_out + pix));
+                  nz0 = t2.x; nz1 = t2.y;
+                }
+              }
+              tmem_ld_wait();
+              if (GEN && e.e_rows) {
+                // 1-pixel output border of the folded deconv+blur: subtract what the blur would have read from
+                // outside the cropped deconv output.  The vote keeps this a real (warp-uniform, rarely taken) branch.
+                const bool brow = valid && (Y == 0 || Y == e.Ho - 1);
+                const bool bl = valid && x == 0, br = valid && x == g.W - 1;
+                if (__any_sync(0xffffffffu, brow || bl || br)) {
+                  if (brow) {
+                    const float* er = e.e_rows + (((size_t)n * 2 + (Y ? 1 : 0)) * e.Wo + 2 * x) * e.Cout + c0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                      va[i] = __float_as_uint(__uint_as_float(va[i]) - __ldg(er + i));
+                      vb[i] = __float_as_uint(__uint_as_float(vb[i]) - __ldg(er + e.Cout + i));
+                    }
+                  }
+                  if (bl) {
+                    const float* ec = e.e_cols + (((size_t)n * 2) * e.Ho + Y) * e.Cout + c0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) - __ldg(ec + i));
+                  }
+                  if (br) {
+                    const float* ec = e.e_cols + (((size_t)n * 2 + 1) * e.Ho + Y) * e.Cout + c0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) vb[i] = __float_as_uint(__uint_as_float(vb[i]) - __ldg(ec + i));
+                  }
+                }
+              }
+              if (valid) {
+                act_t* obase = e.out + (((size_t)(c0 >> 3) * g.N + n) * plane_out + pix) * 8;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
                   uint32_t o[8];
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    float a0 = __uint_as_float(va[h * 8 + 2 * k]) + bias_r[h * 8 + 2 * k];
-                    float a1 = __uint_as_float(va[h * 8 + 2 * k + 1]) + bias_r[h * 8 + 2 * k + 1];
-                    float b0 = __uint_as_float(vb[h * 8 + 2 * k]) + bias_r[h * 8 + 2 * k];
-                    float b1 = __uint_as_float(vb[h * 8 + 2 * k + 1]) + bias_r[h * 8 + 2 * k + 1];
-                    if (do_act) { a0 = lrelu02(a0); a1 = lrelu02(a1); b0 = lrelu02(b0); b1 = lrelu02(b1); }
+                    const int i0 = h * 8 + 2 * k, i1 = i0 + 1;
+                    float a0 = __uint_as_float(va[i0]) + bias_r[i0], a1 = __uint_as_float(va[i1]) + bias_r[i1];
+                    float b0 = __uint_as_float(vb[i0]) + bias_r[i0], b1 = __uint_as_float(vb[i1]) + bias_r[i1];
+                    if (GEN) {
+                      a0 = fmaf(ns_r[i0], nz0, a0); a1 = fmaf(ns_r[i1], nz0, a1);
+                      b0 = fmaf(ns_r[i0], nz1, b0); b1 = fmaf(ns_r[i1], nz1, b1);
+                    }
+                    a0 = fmaxf(a0, slope * a0); a1 = fmaxf(a1, slope * a1);
+                    b0 = fmaxf(b0, slope * b0); b1 = fmaxf(b1, slope * b1);
+                    if (GEN) {
+                      s1[i0] += a0 + b0; s2[i0] = fmaf(a0, a0, fmaf(b0, b0, s2[i0]));
+                      s1[i1] += a1 + b1; s2[i1] = fmaf(a1, a1, fmaf(b1, b1, s2[i1]));
+                    }
                     o[k] = pack_x2(a0, a1);
                     o[4 + k] = pack_x2(b0, b1);
                   }
-                  st_global_256(e.out + (((size_t)((c0 >> 3) + h) * g.N + n) * plane_out + pix) * 8, o);
+                  if (c0 + h * 8 < e.Cout) st_global_256(obase + (size_t)h * g.N * plane_out * 8, o);
                 }
               }
             }
           }
+          if (do_stats) my_slot[(c16 * 16 + (lane & 15)) * 2 + (lane >> 4)] += warp_reduce_32x32(s1, s2, lane);
         }
       } else {
         for (int cc = 0; cc < n_chunks; ++cc) {
@@ -408,23 +495,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
             }
           }
           if (do_stats) {
-            // 32 values (16 sums, 16 sums of squares) x 32 lanes -> lane L ends up holding value L fully reduced
-            float vals[32];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { vals[i] = s1[i]; vals[16 + i] = s2[i]; }
-#pragma unroll
-            for (int step = 0; step < 5; ++step) {
-              const int half = 16 >> step;                      // values kept per lane after this step
-              const bool upper = (lane & half) != 0;            // lane bit deciding which half is kept
-#pragma unroll
-              for (int i = 0; i < half; ++i) {
-                const float keep = upper ? vals[half + i] : vals[i];
-                const float send = upper ? vals[i] : vals[half + i];
-                vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-              }
-            }
             // value index = lane: 0..15 channel sums, 16..31 sums of squares; this warp's own slot: plain add
-            my_slot[(cl + (lane & 15)) * 2 + (lane >> 4)] += vals[0];
+            my_slot[(cl + (lane & 15)) * 2 + (lane >> 4)] += warp_reduce_32x32(s1, s2, lane);
           }
         }
       }
@@ -483,7 +555,7 @@ void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
   const ConvGeom& g = p.g;
   const int total = g.tiles_x * g.tiles_y * g.tiles_n * g.n_ntiles * (g.phase_grid ? 4 : 1);
   const int grid = total < num_sms[dev] * g.ctas_per_sm ? total : num_sms[dev] * g.ctas_per_sm;
-  const bool gen = p.e.noise != nullptr || p.e.nscale != nullptr || (p.e.flags & EPI_STATS) != 0;
+  const bool gen = p.e.noise != nullptr || p.e.nscale != nullptr || (p.e.flags & EPI_STATS) != 0 || p.e.e_rows != nullptr;
   if (gen) {                                   // generator conv_2: noise + statistics epilogue
     launch_g<2, true>(p, grid, st);
   } else if (g.epi_groups == 4) {

@@ -25,11 +25,11 @@ def conv(mode, x0, weight, x1=None, bias=None, nscale=None, noise=None, flags=0,
     n, cin0, h, w = x0.shape
     cin1 = 0 if x1 is None else x1.shape[1]
     wnp = np.ascontiguousarray(np.asarray(weight, np.float32))
-    if mode == L.DECONV4:
+    if mode in (L.DECONV4, L.DECONV4B):
         cout = wnp.shape[1]
     else:
         cout = wnp.shape[0]
-    up = mode in (L.UPCONV3, L.DECONV4)
+    up = mode in (L.UPCONV3, L.DECONV4, L.DECONV4B)
     ho, wo = (2 * h, 2 * w) if up else (h, w)
     dev = x0.device
     argmax = bool(flags & L.EPI_ARGMAX)

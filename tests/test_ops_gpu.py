@@ -116,6 +116,39 @@ def test_conv_generator_epilogue(gsx_lib, dtype):
         assert torch.allclose(r['stats'][:, :, 1], s2, rtol=rt), r['plan']
 
 
+def test_deconv_blur_folded(gsx_lib, dtype):
+    """First half of a high-resolution synthesis block in ONE kernel (networks_stylegan.py:16-20): 4x4 stride-2
+    transposed conv -> 3x3 blur (zero padding on the CROPPED deconv output) -> + scale*noise + bias -> LeakyReLU,
+    with the InstanceNorm sums.  The blur is folded into the conv weights; the 1-pixel border gets a correction."""
+    use(dtype)
+    from gan_segmentation_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(11)
+    blur = torch.tensor([1., 2., 1.])
+    blur = (blur[:, None] * blur[None, :] / 16.0).cuda()
+    for (n, cin, cout, h, w) in [(2, 32, 16, 64, 64), (1, 64, 32, 48, 40), (3, 32, 16, 6, 8), (1, 32, 16, 130, 72)]:
+        x = bf(torch.randn((n, cin, h, w), generator=g)).cuda()
+        wt = bf(torch.randn((cin, cout, 4, 4), generator=g) / np.sqrt(cin * 4.0))
+        ns = torch.randn(cout, generator=g).cuda() * 0.3
+        b = torch.randn(cout, generator=g).cuda() * 0.2
+        nz = torch.randn((n, 1, 2 * h, 2 * w), generator=g).cuda()
+        r = ops.conv(L.DECONV4B, x, wt.numpy(), bias=b, nscale=ns, noise=nz, flags=L.EPI_LRELU | L.EPI_STATS, dtype=dtype)
+        d = F.conv_transpose2d(x, wt.cuda(), None, stride=2, padding=1)
+        d = F.conv2d(d, blur.expand(cout, 1, 3, 3).contiguous(), None, 1, 1, groups=cout)
+        v = F.leaky_relu(d + ns.view(1, -1, 1, 1) * nz + b.view(1, -1, 1, 1), 0.2)
+        rel = 2.0 ** -6 if dtype == 'bf16' else 2.0 ** -9         # the composite weights are rounded once more
+        close(r['out'], v, f'deconv+blur {n, cin, cout, h, w} plan={r["plan"]}', rel=rel)
+        # the border on its own (the correction path), and without noise / bias / activation
+        r0 = ops.conv(L.DECONV4B, x, wt.numpy(), dtype=dtype)
+        for name, sl in (('top', (slice(None), slice(None), 0)), ('bottom', (slice(None), slice(None), -1)),
+                         ('left', (slice(None), slice(None), slice(None), 0)), ('right', (slice(None), slice(None), slice(None), -1))):
+            close(r0['out'][sl], d[sl], f'deconv+blur border {name} {n, cin, cout, h, w}', rel=rel)
+        s1 = v.sum(dim=(2, 3))
+        s2 = (v * v).sum(dim=(2, 3))
+        rt = (2e-3 if r['plan']['NB'] == 1 else 8e-3) * (4 if dtype == 'bf16' else 1)   # bf16: composite-weight rounding
+        assert torch.allclose(r['stats'][:, :, 0], s1, rtol=rt, atol=rt * s2.sqrt().max().item()), r['plan']
+        assert torch.allclose(r['stats'][:, :, 1], s2, rtol=rt), r['plan']
+
+
 def test_conv_decoder_residual(gsx_lib, dtype):
     """conv_b of a DecoderResBlock: bias, LeakyReLU, + nearest-upsampled shortcut (networks_seg.py:44-46)."""
     use(dtype)

@@ -28,6 +28,9 @@ LAYERS = {
     'g10.deconv': ('DECONV4', 32, 0, 16, 512, 512, 'raw'),
     'g9.deconv': ('DECONV4', 64, 0, 32, 256, 256, 'raw'),
     'g8.deconv': ('DECONV4', 128, 0, 64, 128, 128, 'raw'),
+    'g10.deconvb': ('DECONV4B', 32, 0, 16, 512, 512, 'gen'),
+    'g9.deconvb': ('DECONV4B', 64, 0, 32, 256, 256, 'gen'),
+    'g8.deconvb': ('DECONV4B', 128, 0, 64, 128, 128, 'gen'),
     'g7.deconv': ('DECONV4', 256, 0, 128, 64, 64, 'raw'),
     'g6.upconv': ('UPCONV3', 512, 0, 256, 32, 32, 'raw'),
     'g5.upconv': ('UPCONV3', 512, 0, 512, 16, 16, 'raw'),
@@ -45,9 +48,9 @@ def run(name, n, override, repeat, dtype):
     mode, c0, c1, co, h, w, kind = LAYERS[name]
     g = torch.Generator().manual_seed(0)
     x = torch.randn((n, c0 + c1, h, w), generator=g).cuda()
-    k = {'CONV3': 3, 'UPCONV3': 3, 'DECONV4': 4, 'CONV1': 1}[mode]
-    wt = (torch.randn((c0 + c1, co, k, k) if mode == 'DECONV4' else (co, c0 + c1, k, k), generator=g) / np.sqrt((c0 + c1) * k * k)).numpy()
-    up = mode in ('UPCONV3', 'DECONV4')
+    k = {'CONV3': 3, 'UPCONV3': 3, 'DECONV4': 4, 'DECONV4B': 4, 'CONV1': 1}[mode]
+    wt = (torch.randn((c0 + c1, co, k, k) if mode in ('DECONV4', 'DECONV4B') else (co, c0 + c1, k, k), generator=g) / np.sqrt((c0 + c1) * k * k)).numpy()
+    up = mode in ('UPCONV3', 'DECONV4', 'DECONV4B')
     ho, wo = (2 * h, 2 * w) if up else (h, w)
     kw = {}
     if kind == 'gen':
@@ -73,7 +76,7 @@ def run(name, n, override, repeat, dtype):
         by += 4.0 * n * ho * wo
     if kind == 'res':
         by += 2.0 * n * co * ho * wo / 4
-    taps = {'CONV3': 9, 'UPCONV3': 9, 'DECONV4': 4, 'CONV1': 1}[mode]
+    taps = {'CONV3': 9, 'UPCONV3': 9, 'DECONV4': 4, 'DECONV4B': 4, 'CONV1': 1}[mode]
     fl = 2.0 * n * ho * wo * taps * (c0 + c1) * co
     return r, by, fl
 
