@@ -33,7 +33,7 @@ class DecCfg(C.Structure):
 class PlanOverride(C.Structure):
     _fields_ = [('TH', C.c_int), ('TW', C.c_int), ('NB', C.c_int), ('CBK', C.c_int), ('N_tile', C.c_int),
                 ('stages', C.c_int), ('phase_grid', C.c_int), ('epi_groups', C.c_int), ('acc_bufs', C.c_int),
-                ('max_mtiles', C.c_int), ('hstack', C.c_int)]
+                ('max_mtiles', C.c_int), ('hstack', C.c_int), ('s2d', C.c_int)]
 
 
 class GsxError(RuntimeError):

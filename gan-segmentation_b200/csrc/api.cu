@@ -114,9 +114,7 @@ static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1
   p.wpack = L.wpack_dev;
   p.taps = L.taps_dev;
   set_error("");
-  make_act_tensormap(&p.tm[0], x0, L.cin0, N, L.H, L.W, p.g.BW, p.g.BH, p.g.NB, p.g.CBK);
-  if (L.cin1 > 0) make_act_tensormap(&p.tm[1], x1, L.cin1, N, L.H, L.W, p.g.BW, p.g.BH, p.g.NB, p.g.CBK);
-  else p.tm[1] = p.tm[0];
+  make_input_tensormaps(p, L, N, x0, x1);
   if (p.g.aux_kind == 1) {
     if (!epi.noise) p.g.aux_kind = 0;
     else make_noise_tensormap(&p.tm_aux, epi.noise, N, epi.Ho, epi.Wo, p.g.TW << p.g.aux_up, p.g.TH << p.g.aux_up, p.g.NB);

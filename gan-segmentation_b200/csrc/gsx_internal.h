@@ -91,12 +91,18 @@ struct ConvGeom {
   int aux_bytes_tx;            // bytes one TMA box delivers (the mbarrier transaction count)
   int aux_bw, aux_bh;          // residual box: columns / rows at half resolution
   int aux_up;                  // 1: the noise tile is at the OUTPUT resolution of an up-conv (2TH x 2TW)
+  int aux_shift;               // residual tile: tile origin >> aux_shift = residual coordinates (1, or 0 in s2d mode)
+  int s2d;                     // 1: 3x3 conv on the 2x2 space-to-depth grid (thin layers, see plan.cpp): H, W, TH, TW,
+                               //    BH, BW count 2x2 pixel BLOCKS; a stage holds the 4 input phase planes; the 4 output
+                               //    phases are column blocks of one accumulator (up_cols = 1)
   int n_slots;                 // filter taps per CTA
   int phase_grid;              // 1: blockIdx.z selects the phase (wide up-convs)
   int stages;
   int cb_stride_bytes;         // NB*BH*BW*16
   int a_stage_bytes, b_stage_bytes;
   int a_stage_stride;          // a_stage_bytes rounded up to 128 (TMA destination alignment)
+  int plane_stride;            // s2d: bytes between the phase planes of a stage (128-aligned)
+  int dbg;                     // tuning only (env GSX_DBG): 1 skip epilogue work, 2 skip MMAs, 4 skip activation loads
   int a_off;                   // byte offset of the A stages in dynamic smem (after header + stats slots)
   int tmem_cols;               // allocated TMEM columns (power of two) = acc_bufs * n_groups*n_mtiles*N_tile rounded up
   int acc_bufs;                // 2: accumulators double buffered (MMA of tile i+1 overlaps epilogue of tile i)
@@ -105,7 +111,7 @@ struct ConvGeom {
   int ctas_per_sm;             // persistent grid = min(work items, SMs * ctas_per_sm)
   unsigned magic_box, magic_bw;  // ceil(2^32 / (BH*BW)), ceil(2^32 / BW): division by multiply-high
   int smem_bytes;
-  short slot_shift[4][kMaxSlots];   // [phase or 0][slot] -> position shift dy*BW+dx inside the box
+  int slot_shift[4][kMaxSlots];     // [phase or 0][slot] -> A offset in positions (16 B): dy*BW+dx inside the box (+ plane)
   signed char slot_group[kMaxSlots];
   signed char slot_first[kMaxSlots];  // first tap of its accumulator group (overwrite instead of accumulate)
 };
@@ -132,6 +138,7 @@ struct ConvEpi {
 struct ConvParams {
   CUtensorMap tm[2];
   CUtensorMap tm_aux;          // noise (3-D fp32) or residual (4-D blocked) tensor map when g.aux_kind != 0
+  CUtensorMap tm_pl[2][4];     // s2d mode: per source, the 4 input phase planes (py*2+px) as 5-D maps
   ConvGeom g;
   ConvEpi e;
   const act_t* wpack;
@@ -157,6 +164,7 @@ struct PlanOverride {
   int TH, TW, NB, CBK, N_tile, stages, phase_grid;   // 0 / -1 = keep default
   int epi_groups, acc_bufs, max_mtiles;              // 0 = keep default
   int hstack;                                        // -1 = keep default, 0/1 force
+  int s2d;                                           // -1 = keep default, 0/1 force
 };
 
 // plan.cpp
@@ -169,6 +177,11 @@ void finish_geom_for_batch(ConvGeom& g, int N);
 void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& out);
 void make_act_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, int W, int boxW, int boxH, int boxN,
                         int boxCB);
+// s2d mode: phase plane (py, px) of a blocked activation tensor, boxes in 2x2-block coordinates
+void make_plane_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, int W, int py, int px, int boxW, int boxH,
+                          int boxN, int boxCB);
+// fills p.tm[] (or p.tm_pl[][] in s2d mode) for the layer's input tensors
+void make_input_tensormaps(ConvParams& p, const ConvLayer& L, int N, const void* x0, const void* x1);
 
 // launchers (shiftconv.cu / elementwise.cu / styles.cu)
 void launch_shiftconv(const ConvParams& p, cudaStream_t st);

@@ -37,7 +37,7 @@ extern "C" int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, in
   set_error("");
   ConvLayer L;
   PlanOverride po{};
-  if (ov) { po.TH = ov->TH; po.TW = ov->TW; po.NB = ov->NB; po.CBK = ov->CBK; po.N_tile = ov->N_tile; po.stages = ov->stages; po.phase_grid = ov->phase_grid; po.epi_groups = ov->epi_groups; po.acc_bufs = ov->acc_bufs; po.max_mtiles = ov->max_mtiles; po.hstack = ov->hstack; }
+  if (ov) { po.TH = ov->TH; po.TW = ov->TW; po.NB = ov->NB; po.CBK = ov->CBK; po.N_tile = ov->N_tile; po.stages = ov->stages; po.phase_grid = ov->phase_grid; po.epi_groups = ov->epi_groups; po.acc_bufs = ov->acc_bufs; po.max_mtiles = ov->max_mtiles; po.hstack = ov->hstack; po.s2d = ov->s2d; }
   plan_conv(L, mode, h, w, cin0, cin1, cout, argmax ? num_classes : 0, ov ? &po : nullptr,
             noise_dev ? 1 : (addsrc_dev ? 2 : 0));
   if (*last_error_cstr()) return -1;
@@ -93,9 +93,7 @@ extern "C" int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, in
     e.e_rows = er; e.e_cols = ec;
   }
   p.e = e;
-  make_act_tensormap(&p.tm[0], xb0, cin0, n, h, w, p.g.BW, p.g.BH, p.g.NB, p.g.CBK);
-  if (cin1) make_act_tensormap(&p.tm[1], xb1, cin1, n, h, w, p.g.BW, p.g.BH, p.g.NB, p.g.CBK);
-  else p.tm[1] = p.tm[0];
+  make_input_tensormaps(p, L, n, xb0, xb1);
   if (p.g.aux_kind == 1) make_noise_tensormap(&p.tm_aux, noise_dev, n, Ho, Wo, p.g.TW << p.g.aux_up, p.g.TH << p.g.aux_up, p.g.NB);
   else if (p.g.aux_kind == 2) make_act_tensormap(&p.tm_aux, ab, cout, n, Ho / 2, Wo / 2, p.g.aux_bw, p.g.aux_bh, p.g.NB, p.g.cout_tile / 8);
   else p.tm_aux = p.tm[0];
@@ -134,7 +132,7 @@ extern "C" int gsx_plan_query(int mode, int h, int w, int cin0, int cin1, int co
   set_error("");
   ConvLayer L;
   PlanOverride po{};
-  if (ov) { po.TH = ov->TH; po.TW = ov->TW; po.NB = ov->NB; po.CBK = ov->CBK; po.N_tile = ov->N_tile; po.stages = ov->stages; po.phase_grid = ov->phase_grid; po.epi_groups = ov->epi_groups; po.acc_bufs = ov->acc_bufs; po.max_mtiles = ov->max_mtiles; po.hstack = ov->hstack; }
+  if (ov) { po.TH = ov->TH; po.TW = ov->TW; po.NB = ov->NB; po.CBK = ov->CBK; po.N_tile = ov->N_tile; po.stages = ov->stages; po.phase_grid = ov->phase_grid; po.epi_groups = ov->epi_groups; po.acc_bufs = ov->acc_bufs; po.max_mtiles = ov->max_mtiles; po.hstack = ov->hstack; po.s2d = ov->s2d; }
   plan_conv(L, mode, h, w, cin0, cin1, cout, num_classes, ov ? &po : nullptr);
   if (*last_error_cstr()) return -1;
   const ConvGeom& g = L.g;

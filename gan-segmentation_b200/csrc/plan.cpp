@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -35,11 +36,26 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   L.mode = mode; L.H = H; L.W = W; L.cin0 = cin0; L.cin1 = cin1; L.cout = cout;
   ConvGeom& g = L.g;
   std::memset(&g, 0, sizeof(g));
+  // Thin 3x3 layers (<= 32 channels in and out) are bound by the NUMBER of MMAs: an M=128,K=16 kind::f16 MMA costs
+  // 42 cycles of the tensor pipe at N=16, 50 at N=64, 64 at N=128 (tools/umma_bench2.cu) -- almost independent of N.
+  // Space-to-depth: rows of the GEMM are 2x2 pixel blocks, the 4 input phases are 4x the K planes and the 4 output
+  // phases 4x the N columns.  A block tap (ty,tx) in {-1,0,1}^2 only needs the input phases within one pixel of the
+  // block (1, 2 or 4 of them), 16 (tap, phase-plane) pairs in all: 16*Cin/16 MMAs per 512 output pixels instead of
+  // 36*Cin/16 -- 2.25x fewer, each at N = 4*Cout.
+  // Measured (r01, FFHQ batch 32): the phase-plane gather (TMA boxes with a 16-byte inner extent) is slow -- loads
+  // alone take as long as the whole dense-layout kernel -- so by default only the final conv + argmax uses it
+  // (0.85 -> 0.73 ms); GSX_S2D=1 enables it for every eligible layer.
+  static const int s2d_all = getenv("GSX_S2D") ? atoi(getenv("GSX_S2D")) : 0;
+  int s2d = (mode == CONV3 && cin0 + cin1 <= 32 && cout <= 32 && H % 2 == 0 && W % 2 == 0 && H >= 16 && W >= 16 &&
+             (argmax_classes > 0 || (s2d_all && cout <= 16 && aux_kind != 2)) && !getenv("GSX_NO_S2D")) ? 1 : 0;
+  if (ov && ov->s2d >= 0 && mode == CONV3 && H % 2 == 0 && W % 2 == 0) s2d = ov->s2d;
+  if (s2d) { H /= 2; W /= 2; }               // from here on H, W, TH, TW count blocks
   g.H = H; g.W = W;
   const bool up = (mode == UPCONV3 || mode == DECONV4 || mode == DECONV4B);
   const int cb0 = cin0 / 8, cb1 = cin1 / 8, cbt = cb0 + cb1;
 
   int N_tile = argmax_classes > 0 ? 16 : std::min(cout, 128);
+  if (s2d && argmax_classes > 0) N_tile = argmax_classes <= 4 ? 4 : (argmax_classes <= 8 ? 8 : 16);
   if (ov && ov->N_tile > 0) N_tile = ov->N_tile;
   // phases as work items for cout >= 64 (stacked along N they would need the whole 9-shift weight set per tile:
   // 590 KB streamed per 256 pixels at 128->64, measured 0.36 ms vs 0.25 ms), as column blocks of one MMA below
@@ -49,7 +65,7 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
     if (cout > 64) { set_error("plan_conv: DECONV4B needs cout <= 64 (phases stacked along N)"); return; }
     phase_grid = 0;
   }
-  const int up_cols = (up && !phase_grid) ? 1 : 0;
+  const int up_cols = ((up && !phase_grid) || s2d) ? 1 : 0;
   const int cout_tile = N_tile;
   if (up_cols) N_tile = 4 * cout_tile;        // phases stacked along the MMA N dimension (<= 256)
   // every M=128 kind::f16 MMA costs ~60-75 cycles for any N <= 128 (tools/umma_bench.cu), so thin 3x3 layers are
@@ -99,22 +115,24 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   if (ov && ov->TH > 0) TH = ov->TH;
   if (ov && ov->NB > 0) NB = ov->NB;
 
-  const int n_slots = (mode == CONV3) ? (hstack ? 3 : 9) : (mode == CONV1 ? 1 : (phase_grid ? 4 : 9));
+  const int n_slots = s2d ? 16 : (mode == CONV3) ? (hstack ? 3 : 9) : (mode == CONV1 ? 1 : (phase_grid ? 4 : 9));
+  const int planes = s2d ? 4 : 1;
 
   // aux staging: plain 3x3 layers (noise / residual tile) and the folded deconv (noise tile at output resolution);
   // the TMA box row must be a multiple of 16 bytes
-  const int aux_up = (mode == DECONV4B) ? 1 : 0;
+  const int aux_up = (mode == DECONV4B || s2d) ? 1 : 0;
   if (mode != CONV3 && mode != DECONV4B) aux_kind = 0;
   if (mode == DECONV4B && aux_kind == 2) aux_kind = 0;
   if (aux_kind == 1 && ((((W << aux_up) * 4) % 16) != 0 || (((TW << aux_up) * 4) % 16) != 0)) aux_kind = 0;
-  if (aux_kind == 2 && (TW & 1)) aux_kind = 0;
+  if (aux_kind == 2 && !s2d && (TW & 1)) aux_kind = 0;
   // k-chunk depth and pipeline stages under the shared-memory limit
   int CBK = 0, stages = 0, b_resident = 0;
   long aux_bytes = 0;
   for (;;) {
     const int BH = TH + 2;
     aux_bytes = aux_kind == 1 ? ((long)NB * TH * TW * 4) << (2 * aux_up)
-              : aux_kind == 2 ? (long)NB * (TH / 2 + 1) * (TW / 2) * 16 * (cout_tile / 8) : 0;
+              : aux_kind == 2 ? (s2d ? (long)NB * TH * TW * 16 * (cout_tile / 8)
+                                     : (long)NB * (TH / 2 + 1) * (TW / 2) * 16 * (cout_tile / 8)) : 0;
     aux_bytes = (aux_bytes + 127) / 128 * 128;
     int cbs[4] = {8, 4, 2, 0};
     if (ov && ov->CBK > 0) { cbs[0] = ov->CBK; cbs[1] = 0; }
@@ -124,7 +142,8 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
       const int c = cbs[ci];
       if (c > cbt || cb0 % c || (cb1 && cb1 % c)) continue;
       const int n_k = cbt / c;
-      const long a_st = ((long)NB * BH * BW * 16 * c + 127) / 128 * 128;   // TMA smem destinations are 128-B aligned
+      // TMA smem destinations are 128-B aligned (s2d: every phase plane is its own destination)
+      const long a_st = planes * (((long)NB * BH * BW * 16 * c + 127) / 128 * 128);
       const long b_st = (long)n_slots * (c / 2) * N_tile * 32;
       if ((long)NB * BH * BW * 16 >= (1 << 18)) continue;                 // LBO field is 14 bits of 16-byte units
       // the stage ring runs across work items, so even single-chunk layers want >= 2 stages.
@@ -158,8 +177,10 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   g.n_mtiles = ceil_div(((NB - 1) * g.BH + TH - 1) * BW + TW, mt_stride);
   g.hstack = hstack; g.mt_stride = mt_stride; g.xch_off = kHeader + stats_bytes;
   g.cb_stride_bytes = NB * g.BH * BW * 16;
-  g.a_stage_bytes = g.cb_stride_bytes * CBK;
-  g.a_stage_stride = (g.a_stage_bytes + 127) / 128 * 128;
+  g.a_stage_bytes = g.cb_stride_bytes * CBK * planes;
+  g.s2d = s2d;
+  g.plane_stride = (g.cb_stride_bytes * CBK + 127) / 128 * 128;
+  g.a_stage_stride = planes * g.plane_stride;
   g.b_stage_bytes = n_slots * (CBK / 2) * N_tile * 32;
   const int cols = G * g.n_mtiles * N_tile;
   g.acc_bufs = (2 * cols <= 512) ? 2 : 1;
@@ -170,9 +191,10 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   g.epi_groups = epi_groups;
   g.ctas_per_sm = 1;
   g.aux_kind = aux_kind; g.aux_off = hdr_bytes; g.aux_bytes = (int)aux_bytes;
-  g.aux_bw = TW / 2; g.aux_bh = TH / 2 + 1;
-  g.aux_up = aux_up;
-  g.aux_bytes_tx = aux_kind == 1 ? (NB * TH * TW * 4) << (2 * aux_up) : aux_kind == 2 ? NB * (TH / 2 + 1) * (TW / 2) * 16 * (cout_tile / 8) : 0;
+  g.aux_bw = s2d ? TW : TW / 2; g.aux_bh = s2d ? TH : TH / 2 + 1;
+  g.aux_up = aux_up; g.aux_shift = s2d ? 0 : 1;
+  g.aux_bytes_tx = aux_kind == 1 ? (NB * TH * TW * 4) << (2 * aux_up)
+                 : aux_kind == 2 ? NB * g.aux_bh * g.aux_bw * 16 * (cout_tile / 8) : 0;
   g.a_off = hdr_bytes + 2 * (int)aux_bytes;
   g.magic_box = (unsigned)((0x100000000ULL + (unsigned long long)(g.BH * BW) - 1) / (unsigned long long)(g.BH * BW));
   g.magic_bw = (unsigned)((0x100000000ULL + (unsigned long long)BW - 1) / (unsigned long long)BW);
@@ -180,7 +202,17 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
 
   for (int ph = 0; ph < 4; ++ph)
     for (int s = 0; s < kMaxSlots; ++s) g.slot_shift[ph][s] = 0;
-  if (hstack) {
+  if (s2d) {
+    // per axis the (block tap t, input phase p) pairs that lie within one pixel of the block: (-1,1) (0,0) (0,1) (+1,0)
+    static const int kT[4] = {-1, 0, 0, 1}, kP[4] = {1, 0, 1, 0};
+    const int plane_pos = g.plane_stride / 16;                     // positions (16 B) per phase plane of a stage
+    for (int sy = 0; sy < 4; ++sy)
+      for (int sx = 0; sx < 4; ++sx) {
+        const int s = sy * 4 + sx;
+        g.slot_shift[0][s] = (kP[sy] * 2 + kP[sx]) * plane_pos + (kT[sy] + 1) * BW + (kT[sx] + 1);
+        g.slot_group[s] = 0; g.slot_first[s] = (s == 0);
+      }
+  } else if (hstack) {
     for (int ky = 0; ky < 3; ++ky) {
       g.slot_shift[0][ky] = (short)(ky * BW); g.slot_group[ky] = 0; g.slot_first[ky] = (ky == 0);
     }
@@ -233,6 +265,15 @@ void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& o
   const bool up = (L.mode == UPCONV3 || L.mode == DECONV4 || L.mode == DECONV4B);
 
   auto wval = [&](int z, int slot, int co, int ci) -> float {   // co: row of the MMA weight tile
+    if (g.s2d) {
+      // row block q = output phase (qy,qx); slot = (tap, input phase) pair per axis; pixel tap k = 2t + p - q
+      static const int kT[4] = {-1, 0, 0, 1}, kP[4] = {1, 0, 1, 0};
+      const int q = co / g.cout_tile, c = co % g.cout_tile;
+      if (c >= cout) return 0.f;
+      const int ky = 2 * kT[slot / 4] + kP[slot / 4] - (q >> 1), kx = 2 * kT[slot % 4] + kP[slot % 4] - (q & 1);
+      if (ky < -1 || ky > 1 || kx < -1 || kx > 1) return 0.f;
+      return w[(((size_t)c * cin + ci) * 3 + ky + 1) * 3 + kx + 1];
+    }
     if (L.mode == CONV3 && g.hstack) {                       // row block kx of the weight tile, slot = ky
       const int kx = co / g.cout_tile, c = co % g.cout_tile;
       if (c >= cout) return 0.f;
@@ -334,6 +375,46 @@ void make_noise_tensormap(CUtensorMap* tm, const void* base, int N, int H, int W
     snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled (noise) failed (%d) N=%d H=%d W=%d box=%dx%dx%d", (int)r, N, H, W, boxW, boxH, boxN);
     set_error(buf);
   }
+}
+
+void make_plane_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, int W, int py, int px, int boxW,
+                          int boxH, int boxN, int boxCB) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return; }
+  // pixels (2yb+py, 2xb+px): dim0 = the two 8-byte halves of a pixel, dim1 = xb (pitch 32 B), dim2 = yb (two rows)
+  const char* b = static_cast<const char*>(base) + ((size_t)py * W + px) * 16;
+  const cuuint64_t dims[5] = {2, (cuuint64_t)(W / 2), (cuuint64_t)(H / 2), (cuuint64_t)N, (cuuint64_t)(C / 8)};
+  const cuuint64_t strides[4] = {32, (cuuint64_t)W * 32, (cuuint64_t)H * W * 16, (cuuint64_t)N * H * W * 16};
+  const cuuint32_t box[5] = {2, (cuuint32_t)boxW, (cuuint32_t)boxH, (cuuint32_t)boxN, (cuuint32_t)boxCB};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<char*>(b), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled (plane) failed (%d) C=%d N=%d H=%d W=%d box=%dx%dx%dx%d", (int)r, C, N,
+             H, W, boxW, boxH, boxN, boxCB);
+    set_error(buf);
+  }
+}
+
+void make_input_tensormaps(ConvParams& p, const ConvLayer& L, int N, const void* x0, const void* x1) {
+  const ConvGeom& g = p.g;
+  if (g.s2d) {
+    for (int pl = 0; pl < 4; ++pl) {
+      make_plane_tensormap(&p.tm_pl[0][pl], x0, L.cin0, N, L.H, L.W, pl >> 1, pl & 1, g.BW, g.BH, g.NB, g.CBK);
+      if (L.cin1 > 0) make_plane_tensormap(&p.tm_pl[1][pl], x1, L.cin1, N, L.H, L.W, pl >> 1, pl & 1, g.BW, g.BH, g.NB, g.CBK);
+      else p.tm_pl[1][pl] = p.tm_pl[0][pl];
+    }
+    p.tm[0] = p.tm_pl[0][0];
+    p.tm[1] = p.tm_pl[1][0];
+    return;
+  }
+  make_act_tensormap(&p.tm[0], x0, L.cin0, N, L.H, L.W, g.BW, g.BH, g.NB, g.CBK);
+  if (L.cin1 > 0) make_act_tensormap(&p.tm[1], x1, L.cin1, N, L.H, L.W, g.BW, g.BH, g.NB, g.CBK);
+  else p.tm[1] = p.tm[0];
+  for (int s = 0; s < 2; ++s)
+    for (int pl = 0; pl < 4; ++pl) p.tm_pl[s][pl] = p.tm[0];
 }
 
 void make_act_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, int W, int boxW, int boxH, int boxN,

@@ -21,10 +21,12 @@
 //   * epilogue warps read TMEM (tcgen05.ld 32x32b), fuse noise*scale + bias + leaky-ReLU
 //     (+ residual add, + InstanceNorm sum/sumsq, or + argmax) and store 16-bit activations, 16 B per thread.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2.. = 4*G epilogue warps
-// (G warps per TMEM lane quarter).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (even MMA tiles), warps 2..1+4G = epilogue warps
+// (G warps per TMEM lane quarter), warp 2+4G = second MMA issuer (odd MMA tiles).
 #include "gsx_internal.h"
 #include "ptx.cuh"
+
+#include <cstdlib>
 
 namespace gsx {
 
@@ -82,6 +84,43 @@ __device__ __forceinline__ float warp_reduce_32x32(const float (&s1)[16], const 
   return vals[0];
 }
 
+// argmax over the classes of the output phases held in one 16-column chunk (CT columns per phase): first maximum
+// wins (seg_solver.py:326); mask bytes of the two px phases leave as one 2-byte store.
+template <int CT>
+__device__ __forceinline__ void argmax_phases(const uint32_t (&v)[16], const ConvEpi& e, int cc, int n, int y, int x) {
+  constexpr int PPC = 16 / CT;                      // phases per chunk
+  const size_t plane_out = (size_t)e.Ho * e.Wo;
+  unsigned char arg[PPC];
+#pragma unroll
+  for (int p = 0; p < PPC; ++p) {
+    const int ph = cc * PPC + p;
+    const size_t pix = (size_t)(2 * y + (ph >> 1)) * e.Wo + 2 * x + (ph & 1);
+    float best = __uint_as_float(v[p * CT]) + (e.bias ? __ldg(e.bias) : 0.f);
+    int a = 0;
+    if (e.logits) e.logits[((size_t)n * e.num_classes) * plane_out + pix] = best;
+#pragma unroll
+    for (int c = 1; c < CT; ++c) {
+      if (c < e.num_classes) {
+        const float lv = __uint_as_float(v[p * CT + c]) + (e.bias ? __ldg(e.bias + c) : 0.f);
+        if (e.logits) e.logits[((size_t)n * e.num_classes + c) * plane_out + pix] = lv;
+        if (lv > best) { best = lv; a = c; }
+      }
+    }
+    arg[p] = (unsigned char)a;
+  }
+  if (PPC >= 2) {
+#pragma unroll
+    for (int p = 0; p < PPC; p += 2) {
+      const int ph = cc * PPC + p;
+      const size_t pix = (size_t)(2 * y + (ph >> 1)) * e.Wo + 2 * x;
+      *reinterpret_cast<uchar2*>(e.mask + (size_t)n * plane_out + pix) = make_uchar2(arg[p], arg[p + (PPC >= 2 ? 1 : 0)]);
+    }
+  } else {
+    const int ph = cc;
+    e.mask[(size_t)n * plane_out + (size_t)(2 * y + (ph >> 1)) * e.Wo + 2 * x + (ph & 1)] = arg[0];
+  }
+}
+
 struct TileCoord { int x0, y0, n0, ntile, phase, tile_in_sample; };
 
 // a / d for 0 <= a < 2^24 via the float reciprocal (+ one correction step): ~8 instructions instead of the ~35 of an
@@ -112,7 +151,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int t) {
 // GEN = the generator's conv_2 epilogue (noise, InstanceNorm statistics); the decoder / raw variant compiles those
 // paths out, which is what lets it run 16 epilogue warps inside the 112-register budget.
 template <int G, bool GEN>
-__global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(96 + 128 * G, 1) shiftconv_kernel(const __grid_constant__ ConvParams p) {
   constexpr int kEpiWarps = 4 * G;
   constexpr int kEpiThreads = 128 * G;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -131,10 +170,10 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.stages; ++s) {
       mbar_init(&hdr->full[s], 1);
-      mbar_init(&hdr->empty[s], 1);
+      mbar_init(&hdr->empty[s], 2);               // one commit per MMA issuer warp
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&hdr->tmem_full[b], 1);
+      mbar_init(&hdr->tmem_full[b], 2);
       mbar_init(&hdr->tmem_empty[b], kEpiWarps);
     }
     mbar_init(&hdr->bres_full, 1);
@@ -145,6 +184,9 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     fence_barrier_init();
     tma_prefetch_desc(&p.tm[0]);
     if (g.kch0 < g.n_k) tma_prefetch_desc(&p.tm[1]);
+    if (g.s2d) {
+      for (int pl = 1; pl < 4; ++pl) tma_prefetch_desc(&p.tm_pl[0][pl]);
+    }
     if (g.aux_kind) tma_prefetch_desc(&p.tm_aux);
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + 4 * kMaxSlots) hdr->taps[threadIdx.x - 64] = __ldg(p.taps + threadIdx.x - 64);
@@ -176,27 +218,41 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
           mbar_expect_tx(&hdr->aux_full[ab], (uint32_t)g.aux_bytes_tx);
           uint8_t* dst = smem + g.aux_off + (size_t)ab * g.aux_bytes;
           if (g.aux_kind == 1) tma_load_3d(dst, &p.tm_aux, &hdr->aux_full[ab], tc.x0 << g.aux_up, tc.y0 << g.aux_up, tc.n0);
-          else tma_load_4d(dst, &p.tm_aux, &hdr->aux_full[ab], (tc.x0 >> 1) * 2, tc.y0 >> 1, tc.n0, tc.ntile * (g.cout_tile >> 3));
+          else tma_load_4d(dst, &p.tm_aux, &hdr->aux_full[ab], (tc.x0 >> g.aux_shift) * 2, tc.y0 >> g.aux_shift, tc.n0,
+                           tc.ntile * (g.cout_tile >> 3));
         }
         const act_t* wsrc = p.wpack + ((size_t)(tc.phase * g.n_ntiles + tc.ntile) * g.n_k) * b_stage_elems;
         for (int kc = 0; kc < g.n_k; ++kc, ++it) {
           const int s = it % g.stages;
           const int round = it / g.stages;
           if (round > 0) mbar_wait_relaxed(&hdr->empty[s], (uint32_t)((round - 1) & 1));
+          if (g.dbg & 4) { mbar_arrive(&hdr->full[s]); continue; }
           mbar_expect_tx(&hdr->full[s], stage_bytes);
           const int src = kc < g.kch0 ? 0 : 1;
           const int cb0 = (src ? kc - g.kch0 : kc) * g.CBK;
-          // dim0 is in 8-byte units (2 per pixel) so that the inner box extent reaches 128 pixels
-          tma_load_4d(a_base + (size_t)s * g.a_stage_stride, &p.tm[src], &hdr->full[s], (tc.x0 - 1) * 2, tc.y0 - 1,
-                      tc.n0, cb0);
+          if (g.s2d) {
+            // the 4 input phase planes of the block tile, each a dense [cb][nb][BH][BW] operand plane
+#pragma unroll
+            for (int pl = 0; pl < 4; ++pl)
+              tma_load_5d(a_base + (size_t)s * g.a_stage_stride + (size_t)pl * g.plane_stride, &p.tm_pl[src][pl],
+                          &hdr->full[s], 0, tc.x0 - 1, tc.y0 - 1, tc.n0, cb0);
+          } else {
+            // dim0 is in 8-byte units (2 per pixel) so that the inner box extent reaches 128 pixels
+            tma_load_4d(a_base + (size_t)s * g.a_stage_stride, &p.tm[src], &hdr->full[s], (tc.x0 - 1) * 2, tc.y0 - 1,
+                        tc.n0, cb0);
+          }
           if (!g.b_resident)
             bulk_load(b_base + (size_t)s * g.b_stage_bytes, wsrc + (size_t)kc * b_stage_elems, (uint32_t)g.b_stage_bytes,
                       &hdr->full[s]);
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ===================================
+  } else if (warp == 1 || warp == 2 + kEpiWarps) {
+    // ================================ MMA issuers ==================================
+    // Two warps, each issuing every other 128-row MMA tile: a single thread sustains one tcgen05.mma per ~60 cycles
+    // (descriptor arithmetic on the uniform datapath, no latency hiding), the tensor pipe takes one N<=64 MMA per
+    // 42-50 cycles -- thin layers were bound by the issuing thread.
+    const int iss = (warp == 1) ? 0 : 1;
     uint32_t idesc = umma_idesc_16bit(128, (uint32_t)g.N_tile, GSX_FP16 ? 0u : 1u);
     uint32_t a_hi = (uint32_t)(umma_desc_hi((uint32_t)g.cb_stride_bytes, 128) >> 32);
     uint32_t b_hi = (uint32_t)(umma_desc_hi((uint32_t)g.N_tile * 16, 128) >> 32);
@@ -209,7 +265,9 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     uint32_t kstep_desc = (2u * (uint32_t)g.cb_stride_bytes) >> 4;     // two channel blocks per k16 step, in 16-B units
     uint32_t n_tile = (uint32_t)g.N_tile, b_tile_desc = ((uint32_t)g.N_tile * 32) >> 4;
     uint32_t mt_desc = (uint32_t)g.mt_stride;                          // MMA-tile pitch in 16-B units (= positions)
-    keep_in_reg(mt_desc);
+    uint32_t mt_desc2 = 2 * mt_desc, n_tile2 = 2 * (uint32_t)g.N_tile;
+    uint32_t a_iss = iss ? mt_desc : 0u, d_iss = iss ? (uint32_t)g.N_tile : 0u;
+    keep_in_reg(mt_desc2); keep_in_reg(n_tile2); keep_in_reg(a_iss); keep_in_reg(d_iss);
     keep_in_reg(idesc); keep_in_reg(a_hi); keep_in_reg(b_hi); keep_in_reg(n_k); keep_in_reg(stages); keep_in_reg(n_slots);
     keep_in_reg(n_mtiles); keep_in_reg(k16_per_chunk); keep_in_reg(a_stride); keep_in_reg(b_stride);
     keep_in_reg(kstep_desc); keep_in_reg(n_tile); keep_in_reg(b_tile_desc);
@@ -232,13 +290,13 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
           // descriptor low words: start address (16-B units) | LBO << 16
           const uint32_t a_lo0 = (((a_smem + (uint32_t)s * a_stride) >> 4) & 0x3FFF) | a_lbo;
           uint32_t b_lo = (((b_smem + (uint32_t)(b_res ? kc : s) * b_stride) >> 4) & 0x3FFF) | b_lbo;
-          for (int slot = 0; slot < n_slots; ++slot) {
+          for (int slot = 0; slot < ((g.dbg & 2) ? 0 : n_slots); ++slot) {
             const int4 tp = taps[slot];                            // {shift bytes, -, first, -}
             uint32_t a_k = a_lo0 + ((uint32_t)tp.x >> 4);
             for (int j = 0; j < k16_per_chunk; ++j, b_lo += b_tile_desc, a_k += kstep_desc) {
               const uint32_t acc = (kc > 0 || j > 0 || !tp.z) ? 1u : 0u;
-              uint32_t a_lo = a_k, d = acc_base;
-              for (int mt = 0; mt < n_mtiles; ++mt, a_lo += mt_desc, d += n_tile)
+              uint32_t a_lo = a_k + a_iss, d = acc_base + d_iss;
+              for (int mt = iss; mt < n_mtiles; mt += 2, a_lo += mt_desc2, d += n_tile2)
                 umma_f16kind_lohi(d, a_lo, a_hi, b_lo, b_hi, idesc, acc);
             }
           }
@@ -293,7 +351,24 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         return row < g.mt_stride && nb < g.NB && yl < g.TH && xl < g.TW && n < g.N && y < g.H && x < g.W;
       };
 
-      if (e.flags & EPI_ARGMAX) {
+      if (g.dbg & 1) {
+      } else if ((e.flags & EPI_ARGMAX) && g.up_cols) {
+        // s2d final conv: the 4 output phases of a block are column groups of cout_tile (4, 8 or 16) classes
+        for (int u = egrp; u < n_units; u += G) {
+          int n, y, x;
+          const bool valid = locate(u, n, y, x);
+          for (int cc = 0; cc < n_chunks; ++cc) {
+            uint32_t v[16];
+            tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + cc * 16), v);
+            tmem_ld_wait();
+            if (valid) {
+              if (g.cout_tile == 4) argmax_phases<4>(v, e, cc, n, y, x);
+              else if (g.cout_tile == 8) argmax_phases<8>(v, e, cc, n, y, x);
+              else argmax_phases<16>(v, e, cc, n, y, x);
+            }
+          }
+        }
+      } else if (e.flags & EPI_ARGMAX) {
         for (int mt = egrp; mt < g.n_mtiles; mt += G) {
           uint32_t v[16];
           tmem_ld16(acc_base + (uint32_t)(mt * g.N_tile), v);
@@ -321,6 +396,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         // (full sectors instead of two half-sector writes).  GEN adds the generator's first-half epilogue for the
         // folded deconv+blur: border correction, noise (tile staged at output resolution), statistics.
         const float slope = do_act ? 0.2f : 1.0f;
+        const bool has_res = !GEN && (g.aux_kind == 2 || e.addsrc != nullptr);
         for (int c16 = 0; c16 < cpp; ++c16) {
           const int c0 = tc.ntile * g.cout_tile + c16 * 16;
           float bias_r[16], ns_r[16];
@@ -386,6 +462,16 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
                 act_t* obase = e.out + (((size_t)(c0 >> 3) * g.N + n) * plane_out + pix) * 8;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
+                  // residual (s2d conv_b): one block-resolution vector per 8 channels, shared by the 4 output phases
+                  uint4 rv = make_uint4(0, 0, 0, 0);
+                  if (has_res) {
+                    if (g.aux_kind == 2)
+                      rv = reinterpret_cast<const uint4*>(aux)[((size_t)((c16 * 2 + h) * g.NB + nb_l) * g.aux_bh + yl_l) * g.aux_bw + xl_l];
+                    else if (e.addsrc)
+                      rv = __ldg(reinterpret_cast<const uint4*>(
+                          e.addsrc + ((((size_t)(c0 >> 3) + h) * g.N + n) * (plane_out >> 2) + (size_t)y * (e.Wo >> 1) + x) * 8));
+                  }
+                  const uint32_t r4[4] = {rv.x, rv.y, rv.z, rv.w};
                   uint32_t o[8];
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
@@ -398,6 +484,10 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
                     }
                     a0 = fmaxf(a0, slope * a0); a1 = fmaxf(a1, slope * a1);
                     b0 = fmaxf(b0, slope * b0); b1 = fmaxf(b1, slope * b1);
+                    if (has_res) {
+                      const float2 r2 = unpack_x2(r4[k]);
+                      a0 += r2.x; a1 += r2.y; b0 += r2.x; b1 += r2.y;
+                    }
                     if (GEN) {
                       s1[i0] += a0 + b0; s2[i0] = fmaf(a0, a0, fmaf(b0, b0, s2[i0]));
                       s1[i1] += a1 + b1; s2[i1] = fmaf(a1, a1, fmaf(b1, b1, s2[i1]));
@@ -545,7 +635,7 @@ static void launch_g(const ConvParams& p, int grid, cudaStream_t st) {
     cudaFuncSetAttribute(shiftconv_kernel<G, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured[dev] = true;
   }
-  shiftconv_kernel<G, GEN><<<grid, 64 + 128 * G, p.g.smem_bytes, st>>>(p);
+  shiftconv_kernel<G, GEN><<<grid, 96 + 128 * G, p.g.smem_bytes, st>>>(p);
 }
 
 void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
@@ -555,6 +645,8 @@ void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
   const ConvGeom& g = p.g;
   const int total = g.tiles_x * g.tiles_y * g.tiles_n * g.n_ntiles * (g.phase_grid ? 4 : 1);
   const int grid = total < num_sms[dev] * g.ctas_per_sm ? total : num_sms[dev] * g.ctas_per_sm;
+  static const int dbg = getenv("GSX_DBG") ? atoi(getenv("GSX_DBG")) : 0;
+  if (dbg) const_cast<ConvParams&>(p).g.dbg = dbg;
   const bool gen = p.e.noise != nullptr || p.e.nscale != nullptr || (p.e.flags & EPI_STATS) != 0 || p.e.e_rows != nullptr;
   if (gen) {                                   // generator conv_2: noise + statistics epilogue
     launch_g<2, true>(p, grid, st);

@@ -39,7 +39,7 @@ def conv(mode, x0, weight, x1=None, bias=None, nscale=None, noise=None, flags=0,
     logits = torch.empty((n, num_classes, ho, wo), dtype=torch.float32, device=dev) if argmax else None
     ov = None
     if override:
-        ov = L.PlanOverride(TH=0, TW=0, NB=0, CBK=0, N_tile=0, stages=0, phase_grid=-1, epi_groups=0, acc_bufs=0, max_mtiles=0, hstack=-1)
+        ov = L.PlanOverride(TH=0, TW=0, NB=0, CBK=0, N_tile=0, stages=0, phase_grid=-1, epi_groups=0, acc_bufs=0, max_mtiles=0, hstack=-1, s2d=-1)
         for k, v in override.items():
             setattr(ov, k, v)
     plan = (C.c_int * 16)()

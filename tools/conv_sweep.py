@@ -38,6 +38,7 @@ LAYERS = {
     'd7.cvt': ('CONV3', 32, 0, 32, 512, 512, 'dec'),
     'd7.conv_a': ('UPCONV3', 32, 32, 16, 512, 512, 'dec'),
     'd7.conv_b': ('CONV3', 16, 0, 16, 1024, 1024, 'res'),
+    'd6.conv_b': ('CONV3', 32, 0, 32, 512, 512, 'res'),
     'd7.shortcut': ('CONV1', 32, 32, 16, 512, 512, 'lin'),
     'd6.conv_a': ('UPCONV3', 32, 32, 32, 256, 256, 'dec'),
     'd8.final': ('CONV3', 16, 16, 2, 1024, 1024, 'argmax'),
