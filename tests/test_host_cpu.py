@@ -98,8 +98,9 @@ def test_planner_invariants(gsx_lib, gan, base):
         rows = ((p['NB'] - 1) * (p['TH'] + 2) + p['TH'] - 1) * p['BW'] + p['TW']
         assert rows <= p['n_mtiles'] * 128, tag
         # tiles cover the image
-        tiles_x = -(-w // p['TW'])
-        tiles_y = -(-h // p['TH'])
+        s2d = p['n_slots'] == 16                 # space-to-depth plans tile the grid of 2x2 pixel blocks
+        tiles_x = -(-(w // 2 if s2d else w) // p['TW'])
+        tiles_y = -(-(h // 2 if s2d else h) // p['TH'])
         assert p['tiles'] == tiles_x * tiles_y, tag
 
 
