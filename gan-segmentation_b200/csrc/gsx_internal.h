@@ -102,7 +102,8 @@ struct ConvGeom {
   int a_stage_bytes, b_stage_bytes;
   int a_stage_stride;          // a_stage_bytes rounded up to 128 (TMA destination alignment)
   int plane_stride;            // s2d: bytes between the phase planes of a stage (128-aligned)
-  int dbg;                     // tuning only (env GSX_DBG): 1 skip epilogue work, 2 skip MMAs, 4 skip activation loads
+  int dbg;                     // tuning only (env GSX_DBG): 1 skip epilogue work, 2 skip MMAs, 4 skip activation loads,
+                               //   8 issuers do not wait for operands (with 4: pure MMA issue rate)
   int a_off;                   // byte offset of the A stages in dynamic smem (after header + stats slots)
   int tmem_cols;               // allocated TMEM columns (power of two) = acc_bufs * n_groups*n_mtiles*N_tile rounded up
   int acc_bufs;                // 2: accumulators double buffered (MMA of tile i+1 overlaps epilogue of tile i)

@@ -21,8 +21,8 @@
 //   * epilogue warps read TMEM (tcgen05.ld 32x32b), fuse noise*scale + bias + leaky-ReLU
 //     (+ residual add, + InstanceNorm sum/sumsq, or + argmax) and store 16-bit activations, 16 B per thread.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (even MMA tiles), warps 2..1+4G = epilogue warps
-// (G warps per TMEM lane quarter), warp 2+4G = second MMA issuer (odd MMA tiles).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2.. = 4*G epilogue warps
+// (G warps per TMEM lane quarter).
 #include "gsx_internal.h"
 #include "ptx.cuh"
 
@@ -42,7 +42,7 @@ struct __align__(16) SmemHeader {
   uint64_t aux_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
-  int4 taps[4 * kMaxSlots];   // copy of ConvParams::taps
+  uint2 sched[64 + 16];       // per (phase, slot, k16 step): {A offset, B offset} in 16-byte units (+16: group over-read)
 };
 static_assert(sizeof(SmemHeader) <= kConvHeaderBytes, "header too large");
 
@@ -121,6 +121,18 @@ __device__ __forceinline__ void argmax_phases(const uint32_t (&v)[16], const Con
   }
 }
 
+// CNT MMAs (one schedule group) for every 128-row MMA tile of the work item, as straight-line code.
+template <int CNT>
+__device__ __forceinline__ void issue_group(uint32_t d, int n_mtiles, uint32_t n_tile, uint32_t mt_desc, const uint32_t (&ab)[16],
+                                            const uint32_t (&bk)[16], uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t first_acc) {
+  uint32_t moff = 0;
+  for (int mt = 0; mt < n_mtiles; ++mt, moff += mt_desc, d += n_tile) {
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) umma_f16kind_lohi(d, ab[k] + moff, a_hi, bk[k], b_hi, idesc, k == 0 ? first_acc : 1u);
+  }
+}
+
 struct TileCoord { int x0, y0, n0, ntile, phase, tile_in_sample; };
 
 // a / d for 0 <= a < 2^24 via the float reciprocal (+ one correction step): ~8 instructions instead of the ~35 of an
@@ -151,7 +163,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int t) {
 // GEN = the generator's conv_2 epilogue (noise, InstanceNorm statistics); the decoder / raw variant compiles those
 // paths out, which is what lets it run 16 epilogue warps inside the 112-register budget.
 template <int G, bool GEN>
-__global__ void __launch_bounds__(96 + 128 * G, 1) shiftconv_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid_constant__ ConvParams p) {
   constexpr int kEpiWarps = 4 * G;
   constexpr int kEpiThreads = 128 * G;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -170,10 +182,10 @@ __global__ void __launch_bounds__(96 + 128 * G, 1) shiftconv_kernel(const __grid
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.stages; ++s) {
       mbar_init(&hdr->full[s], 1);
-      mbar_init(&hdr->empty[s], 2);               // one commit per MMA issuer warp
+      mbar_init(&hdr->empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&hdr->tmem_full[b], 2);
+      mbar_init(&hdr->tmem_full[b], 1);
       mbar_init(&hdr->tmem_empty[b], kEpiWarps);
     }
     mbar_init(&hdr->bres_full, 1);
@@ -189,7 +201,19 @@ __global__ void __launch_bounds__(96 + 128 * G, 1) shiftconv_kernel(const __grid
     }
     if (g.aux_kind) tma_prefetch_desc(&p.tm_aux);
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 4 * kMaxSlots) hdr->taps[threadIdx.x - 64] = __ldg(p.taps + threadIdx.x - 64);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 80) {
+    // MMA schedule: entry (phase, slot, j) = {tap shift + j k16-steps of A, (slot * k16_per_chunk + j) B tiles}
+    const int i = threadIdx.x - 64, k16pc = g.CBK >> 1, len = g.n_slots * k16pc;
+    const int nph = g.phase_grid ? 4 : 1;
+    uint2 v = make_uint2(0u, 0u);
+    if (i < nph * len) {
+      const int ph = i / len, idx = i - ph * len, slot = idx / k16pc, j = idx - slot * k16pc;
+      const int4 tp = __ldg(p.taps + ph * kMaxSlots + slot);
+      v.x = ((uint32_t)tp.x >> 4) + (uint32_t)j * ((2u * (uint32_t)g.cb_stride_bytes) >> 4);
+      v.y = (uint32_t)idx * (((uint32_t)g.N_tile * 32) >> 4);
+    }
+    hdr->sched[i] = v;
+  }
   if (warp == 1) {
     tmem_alloc(&hdr->tmem_base, (uint32_t)g.tmem_cols);
     tmem_relinquish();
@@ -247,33 +271,33 @@ __global__ void __launch_bounds__(96 + 128 * G, 1) shiftconv_kernel(const __grid
         }
       }
     }
-  } else if (warp == 1 || warp == 2 + kEpiWarps) {
-    // ================================ MMA issuers ==================================
-    // Two warps, each issuing every other 128-row MMA tile: a single thread sustains one tcgen05.mma per ~60 cycles
-    // (descriptor arithmetic on the uniform datapath, no latency hiding), the tensor pipe takes one N<=64 MMA per
-    // 42-50 cycles -- thin layers were bound by the issuing thread.
-    const int iss = (warp == 1) ? 0 : 1;
+  } else if (warp == 1) {
+    // ================================ MMA issuer ===================================
+    // The issuing thread, not the tensor pipe, bounds thin layers unless its loop is nearly straight-line code: the
+    // pipe takes an M=128,K=16 MMA every 39 / 48 / 64 cycles at N = 16 / 64 / 128 whatever operands change between
+    // instructions (tools/umma_bench4.cu), a loop with dependent descriptor arithmetic sustained one per 65-180.
+    // So the per-chunk schedule {A offset, B offset} of up to 16 (slot, k16) pairs sits in registers (built once in
+    // shared memory, hdr->sched) and each MMA tile replays it fully unrolled.
     uint32_t idesc = umma_idesc_16bit(128, (uint32_t)g.N_tile, GSX_FP16 ? 0u : 1u);
     uint32_t a_hi = (uint32_t)(umma_desc_hi((uint32_t)g.cb_stride_bytes, 128) >> 32);
     uint32_t b_hi = (uint32_t)(umma_desc_hi((uint32_t)g.N_tile * 16, 128) >> 32);
     const uint32_t a_lbo = (((uint32_t)g.cb_stride_bytes >> 4) & 0x3FFF) << 16;      // low-word part of the A descriptor
     const uint32_t b_lbo = ((((uint32_t)g.N_tile * 16) >> 4) & 0x3FFF) << 16;
-    // hoist everything the issue loop needs into registers (and keep it there)
-    int n_k = g.n_k, stages = g.stages, n_slots = g.n_slots, n_mtiles = g.n_mtiles, k16_per_chunk = g.CBK >> 1;
+    int n_k = g.n_k, stages = g.stages, n_mtiles = g.n_mtiles;
+    const int sched_len = (g.dbg & 2) ? 0 : g.n_slots * (g.CBK >> 1);      // MMAs per (k-chunk, MMA tile)
     const int b_res = g.b_resident;
     uint32_t a_stride = (uint32_t)g.a_stage_stride, b_stride = (uint32_t)g.b_stage_bytes;
-    uint32_t kstep_desc = (2u * (uint32_t)g.cb_stride_bytes) >> 4;     // two channel blocks per k16 step, in 16-B units
-    uint32_t n_tile = (uint32_t)g.N_tile, b_tile_desc = ((uint32_t)g.N_tile * 32) >> 4;
+    uint32_t n_tile = (uint32_t)g.N_tile;
     uint32_t mt_desc = (uint32_t)g.mt_stride;                          // MMA-tile pitch in 16-B units (= positions)
-    uint32_t mt_desc2 = 2 * mt_desc, n_tile2 = 2 * (uint32_t)g.N_tile;
-    uint32_t a_iss = iss ? mt_desc : 0u, d_iss = iss ? (uint32_t)g.N_tile : 0u;
-    keep_in_reg(mt_desc2); keep_in_reg(n_tile2); keep_in_reg(a_iss); keep_in_reg(d_iss);
-    keep_in_reg(idesc); keep_in_reg(a_hi); keep_in_reg(b_hi); keep_in_reg(n_k); keep_in_reg(stages); keep_in_reg(n_slots);
-    keep_in_reg(n_mtiles); keep_in_reg(k16_per_chunk); keep_in_reg(a_stride); keep_in_reg(b_stride);
-    keep_in_reg(kstep_desc); keep_in_reg(n_tile); keep_in_reg(b_tile_desc);
+    keep_in_reg(mt_desc); keep_in_reg(idesc); keep_in_reg(a_hi); keep_in_reg(b_hi); keep_in_reg(n_k); keep_in_reg(stages);
+    keep_in_reg(n_mtiles); keep_in_reg(a_stride); keep_in_reg(b_stride); keep_in_reg(n_tile);
     const uint32_t a_smem = smem_u32(a_base), b_smem = smem_u32(b_base);
     if (g.b_resident) mbar_wait(&hdr->bres_full, 0);
     int it = 0, tl = 0;
+    int cur_key = -1;
+    uint32_t aa[16], bb[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { aa[i] = 0; bb[i] = 0; }
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
       const TileCoord tc = decode_tile(g, t);
       const int buf = tl % nbuf;
@@ -281,25 +305,47 @@ __global__ void __launch_bounds__(96 + 128 * G, 1) shiftconv_kernel(const __grid
       if (use > 0) mbar_wait(&hdr->tmem_empty[buf], (uint32_t)((use - 1) & 1));
       tc_fence_after();
       const uint32_t acc_base = tmem_base + (uint32_t)(buf * cols_per_buf);
-      const int4* taps = hdr->taps + tc.phase * kMaxSlots;
       for (int kc = 0; kc < n_k; ++kc, ++it) {
         const int s = it % stages;
-        mbar_wait(&hdr->full[s], (uint32_t)((it / stages) & 1));
+        if (!(g.dbg & 8)) mbar_wait(&hdr->full[s], (uint32_t)((it / stages) & 1));
         tc_fence_after();
-        if (elect_one()) {
-          // descriptor low words: start address (16-B units) | LBO << 16
-          const uint32_t a_lo0 = (((a_smem + (uint32_t)s * a_stride) >> 4) & 0x3FFF) | a_lbo;
-          uint32_t b_lo = (((b_smem + (uint32_t)(b_res ? kc : s) * b_stride) >> 4) & 0x3FFF) | b_lbo;
-          for (int slot = 0; slot < ((g.dbg & 2) ? 0 : n_slots); ++slot) {
-            const int4 tp = taps[slot];                            // {shift bytes, -, first, -}
-            uint32_t a_k = a_lo0 + ((uint32_t)tp.x >> 4);
-            for (int j = 0; j < k16_per_chunk; ++j, b_lo += b_tile_desc, a_k += kstep_desc) {
-              const uint32_t acc = (kc > 0 || j > 0 || !tp.z) ? 1u : 0u;
-              uint32_t a_lo = a_k + a_iss, d = acc_base + d_iss;
-              for (int mt = iss; mt < n_mtiles; mt += 2, a_lo += mt_desc2, d += n_tile2)
-                umma_f16kind_lohi(d, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+        // descriptor low words: start address (16-B units) | LBO << 16
+        const uint32_t a_lo0 = (((a_smem + (uint32_t)s * a_stride) >> 4) & 0x3FFF) | a_lbo;
+        const uint32_t b_lo0 = (((b_smem + (uint32_t)(b_res ? kc : s) * b_stride) >> 4) & 0x3FFF) | b_lbo;
+        for (int g0 = 0; g0 < sched_len; g0 += 16) {
+          const int key = tc.phase * 64 + g0;                           // schedule group held in aa / bb
+          if (key != cur_key) {
+            cur_key = key;
+            const uint2* sc = hdr->sched + tc.phase * sched_len + g0;   // (reads past the end are never issued)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { const uint2 v = sc[i]; aa[i] = v.x; bb[i] = v.y; }
+          }
+          const int cnt = sched_len - g0;
+          // absolute descriptor low words of this chunk's schedule entries (the MMA tile offset is added per MMA)
+          uint32_t ab[16], bk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { ab[i] = a_lo0 + aa[i]; bk[i] = b_lo0 + bb[i]; }
+          if (elect_one()) {
+            const uint32_t first_acc = (kc > 0 || g0 > 0) ? 1u : 0u;   // the very first MMA of a tile overwrites
+            // straight-line bodies for the schedule lengths the planner produces; predicated fallback otherwise
+            if (cnt >= 16)      issue_group<16>(acc_base, n_mtiles, n_tile, mt_desc, ab, bk, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 9)  issue_group<9>(acc_base, n_mtiles, n_tile, mt_desc, ab, bk, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 4)  issue_group<4>(acc_base, n_mtiles, n_tile, mt_desc, ab, bk, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 8)  issue_group<8>(acc_base, n_mtiles, n_tile, mt_desc, ab, bk, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 2)  issue_group<2>(acc_base, n_mtiles, n_tile, mt_desc, ab, bk, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 1)  issue_group<1>(acc_base, n_mtiles, n_tile, mt_desc, ab, bk, a_hi, b_hi, idesc, first_acc);
+            else {
+              uint32_t moff = 0, d = acc_base;
+              for (int mt = 0; mt < n_mtiles; ++mt, moff += mt_desc, d += n_tile) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                  if (k < cnt) umma_f16kind_lohi(d, ab[k] + moff, a_hi, bk[k], b_hi, idesc, k == 0 ? first_acc : 1u);
+              }
             }
           }
+          __syncwarp();
+        }
+        if (elect_one()) {
           umma_commit(&hdr->empty[s]);
           if (kc == n_k - 1) umma_commit(&hdr->tmem_full[buf]);
         }
@@ -635,7 +681,7 @@ static void launch_g(const ConvParams& p, int grid, cudaStream_t st) {
     cudaFuncSetAttribute(shiftconv_kernel<G, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured[dev] = true;
   }
-  shiftconv_kernel<G, GEN><<<grid, 96 + 128 * G, p.g.smem_bytes, st>>>(p);
+  shiftconv_kernel<G, GEN><<<grid, 64 + 128 * G, p.g.smem_bytes, st>>>(p);
 }
 
 void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
