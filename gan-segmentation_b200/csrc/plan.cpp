@@ -89,8 +89,10 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   int max_mt = std::max(1, budget_cols / (G * N_tile));
   max_mt = std::min(max_mt, 32);
   if (ov && ov->max_mtiles > 0) max_mt = std::min(max_mt, ov->max_mtiles);
-  int epi_groups = 2;          // 8 epilogue warps: the 16-warp variants spill under the 112-register cap and lose
-  if (ov && ov->epi_groups > 0) epi_groups = ov->epi_groups;
+  // 8 epilogue warps.  A 16-warp variant was measured in round 1 (with one and with two MMA issuers, dense and
+  // space-to-depth plans): never faster, and it spills under its 112-register cap -- not built.
+  const int epi_groups = 2;
+  if (ov && ov->epi_groups > 0 && ov->epi_groups != 2) { set_error("plan_conv: only epi_groups = 2 is built"); return; }
   const int stats_bytes = (2 * 4 * epi_groups * 2 * cout_tile * 4 + 1023) / 1024 * 1024;
   const int xch_bytes = hstack ? 2 * epi_groups * 5 * 48 * 4 : 0;
   const int hdr_bytes = kHeader + stats_bytes + (xch_bytes + 1023) / 1024 * 1024;

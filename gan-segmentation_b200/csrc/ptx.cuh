@@ -45,12 +45,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 24)) __trap();
   }
 }
-// Same, for the single-thread producer: sleeps between polls so that its spin does not take issue slots from the
-// epilogue warps sharing its scheduler (the producer runs several stages ahead; wake-up latency is hidden).
+// Same, sleeping between polls.  Every poll is a shared-memory access, and tcgen05.mma with SS operands is bound by
+// shared-memory read bandwidth (M=128,K=16: (4 KB of A + N*32 B of B) / 128 B per cycle = 39 / 48 / 64 cycles at
+// N = 16 / 64 / 128, tools/umma_bench4.cu), so spinning warps slow the tensor pipe down.  Used by the producer (runs
+// stages ahead) and by the epilogue warps (a tile is thousands of cycles; the wake-up latency is noise).
+template <int NS = 100>
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(100);
+    __nanosleep(NS);
     if (++spins > (1u << 22)) __trap();
   }
 }

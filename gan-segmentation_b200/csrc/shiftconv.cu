@@ -160,8 +160,8 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int t) {
   return c;
 }
 
-// GEN = the generator's conv_2 epilogue (noise, InstanceNorm statistics); the decoder / raw variant compiles those
-// paths out, which is what lets it run 16 epilogue warps inside the 112-register budget.
+// GEN = the generator's epilogues (noise, InstanceNorm statistics, deconv+blur border correction); the decoder / raw
+// variant compiles those paths out (127 instead of 168 registers).  G = epilogue warps per TMEM lane quarter.
 template <int G, bool GEN>
 __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid_constant__ ConvParams p) {
   constexpr int kEpiWarps = 4 * G;
@@ -377,11 +377,11 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         for (int i = lane; i < slot_floats; i += 32) my_slot[i] = 0.f;
         __syncwarp();
       }
-      mbar_wait(&hdr->tmem_full[buf], (uint32_t)((tl / nbuf) & 1));
+      mbar_wait_relaxed<64>(&hdr->tmem_full[buf], (uint32_t)((tl / nbuf) & 1));
       tc_fence_after();
       const int ab = tl & 1;
       const uint8_t* aux = smem + g.aux_off + (size_t)ab * g.aux_bytes;
-      if (g.aux_kind) mbar_wait(&hdr->aux_full[ab], (uint32_t)((tl >> 1) & 1));
+      if (g.aux_kind) mbar_wait_relaxed<32>(&hdr->aux_full[ab], (uint32_t)((tl >> 1) & 1));
       const uint32_t acc_base = tmem_base + (uint32_t)(buf * cols_per_buf) + lane_base;
 
       // position of this thread's row inside MMA tile `mt`:  q = mt*128 + row  ->  (nb, yl, xl)
@@ -694,13 +694,8 @@ void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
   static const int dbg = getenv("GSX_DBG") ? atoi(getenv("GSX_DBG")) : 0;
   if (dbg) const_cast<ConvParams&>(p).g.dbg = dbg;
   const bool gen = p.e.noise != nullptr || p.e.nscale != nullptr || (p.e.flags & EPI_STATS) != 0 || p.e.e_rows != nullptr;
-  if (gen) {                                   // generator conv_2: noise + statistics epilogue
-    launch_g<2, true>(p, grid, st);
-  } else if (g.epi_groups == 4) {
-    launch_g<4, false>(p, grid, st);
-  } else {
-    launch_g<2, false>(p, grid, st);
-  }
+  if (gen) launch_g<2, true>(p, grid, st);     // generator epilogues: noise + statistics (+ border correction)
+  else launch_g<2, false>(p, grid, st);
 }
 
 }  // namespace gsx

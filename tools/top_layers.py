@@ -2,6 +2,6 @@
 import sys
 sys.path.insert(0, '/root/repo/tools'); sys.path.insert(0, '/root/repo')
 from conv_sweep import run
-for name in ['d8.final', 'd7.conv_a', 'g10.conv2', 'd7.conv_b', 'd8.cvt', 'g10.deconv']:
+for name in ['d7.conv_a', 'g10.deconvb', 'g10.conv2', 'd8.final', 'd7.conv_b', 'd8.cvt']:
     r, by, fl = run(name, 32, None, 0, 'fp16')
     print(name, 'algorithmic_bytes', int(by), 'algorithmic_flops', int(fl), r['plan'], flush=True)
