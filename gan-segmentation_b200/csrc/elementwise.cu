@@ -441,21 +441,25 @@ void launch_fill_noise(float* out, size_t plane_elems, int N, uint64_t seed, uin
   dim3 grid((unsigned)min((size_t)1024, (quads + 255) / 256), N);
   fill_normal_kernel<<<grid, 256, 0, st>>>(out, plane_elems, N, seed, first_sample, (uint32_t)layer);
 }
-// all noise planes of a forward pass in one launch: blockIdx.z = style layer
-__global__ void fill_noise_all_kernel(NoisePlanes pl, int N, uint64_t seed, uint64_t first_sample) {
-  const int layer = blockIdx.z;
-  const size_t per_sample = pl.elems[layer];
-  float* out = pl.ptr[layer];
-  const size_t quads = (per_sample + 3) / 4;
+// all noise planes of a forward pass in one launch: the quads (4 values) of all layers of a sample form one index
+// space, so that every block has the same amount of work (a grid dimension per layer left ~70 % of the blocks of
+// the low-resolution layers empty and the launch cost 0.26 ms for 0.36 GB)
+struct NoiseIndex { size_t qstart[25]; int nlayers; };
+__global__ void __launch_bounds__(256) fill_noise_all_kernel(NoisePlanes pl, NoiseIndex ix, uint64_t seed, uint64_t first_sample) {
   const int n = blockIdx.y;
   const uint64_t gs = first_sample + (uint64_t)n;
-  for (size_t qd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quads; qd += (size_t)gridDim.x * blockDim.x) {
+  const size_t total = ix.qstart[ix.nlayers];
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+    int layer = ix.nlayers - 1;                          // most quads belong to the last layers: scan from the top
+    while (q < ix.qstart[layer]) --layer;
+    const size_t qd = q - ix.qstart[layer];
+    const size_t per_sample = pl.elems[layer];
     uint32_t c[4] = {(uint32_t)qd, (uint32_t)layer, (uint32_t)gs, (uint32_t)(gs >> 32)};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     float z[4];
     box_muller(c[0], c[1], z[0], z[1]);
     box_muller(c[2], c[3], z[2], z[3]);
-    float* dst = out + (size_t)n * per_sample + qd * 4;
+    float* dst = pl.ptr[layer] + (size_t)n * per_sample + qd * 4;
     if (qd * 4 + 3 < per_sample) {
       *reinterpret_cast<float4*>(dst) = make_float4(z[0], z[1], z[2], z[3]);
     } else {
@@ -466,10 +470,15 @@ __global__ void fill_noise_all_kernel(NoisePlanes pl, int N, uint64_t seed, uint
   }
 }
 void launch_fill_noise_all(const NoisePlanes& pl, int nlayers, int N, uint64_t seed, uint64_t first_sample, cudaStream_t st) {
-  size_t maxq = 1;
-  for (int l = 0; l < nlayers; ++l) maxq = pl.elems[l] / 4 > maxq ? pl.elems[l] / 4 : maxq;
-  dim3 grid((unsigned)min((size_t)512, (maxq + 255) / 256), N, nlayers);
-  fill_noise_all_kernel<<<grid, 256, 0, st>>>(pl, N, seed, first_sample);
+  NoiseIndex ix{};
+  ix.nlayers = nlayers;
+  size_t acc = 0;
+  for (int l = 0; l < nlayers; ++l) { ix.qstart[l] = acc; acc += (pl.elems[l] + 3) / 4; }
+  ix.qstart[nlayers] = acc;
+  // ~4 quads per thread; at least one block per sample
+  const size_t blocks = (acc + 1023) / 1024;
+  dim3 grid((unsigned)(blocks < 1 ? 1 : (blocks > 4096 ? 4096 : blocks)), N);
+  fill_noise_all_kernel<<<grid, 256, 0, st>>>(pl, ix, seed, first_sample);
 }
 
 void launch_fill_latents(float* z, int N, int Z, uint64_t seed, uint64_t first_sample, cudaStream_t st) {

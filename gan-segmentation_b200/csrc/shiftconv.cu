@@ -293,30 +293,36 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     keep_in_reg(n_mtiles); keep_in_reg(a_stride); keep_in_reg(b_stride); keep_in_reg(n_tile);
     const uint32_t a_smem = smem_u32(a_base), b_smem = smem_u32(b_base);
     if (g.b_resident) mbar_wait(&hdr->bres_full, 0);
-    int it = 0, tl = 0;
+    // Everything between the last MMA of a chunk and the first of the next is time the tensor pipe may run dry
+    // (measured: ~1 us per work item with integer divisions and the tile decode in this path), so the stage /
+    // buffer bookkeeping is incremental and only the phase (schedule selector, phase_grid layers) is decoded.
+    int tl = 0;
     int cur_key = -1;
+    int s = 0;                       // stage of the next chunk
+    uint32_t full_par = 0;           // parity its "full" barrier completes with
+    int buf = 0;                     // accumulator buffer of the next work item
+    uint32_t empty_par = 1;          // parity of the "tmem_empty" wait = (round - 1) & 1, round = tl / nbuf
+    const int sp_nt = g.tiles_x * g.tiles_y * g.tiles_n * g.n_ntiles;
+    const bool phased = g.phase_grid != 0;
     uint32_t aa[16], bb[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { aa[i] = 0; bb[i] = 0; }
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
-      const TileCoord tc = decode_tile(g, t);
-      const int buf = tl % nbuf;
-      const int use = tl / nbuf;
-      if (use > 0) mbar_wait(&hdr->tmem_empty[buf], (uint32_t)((use - 1) & 1));
+      int phase = 0;
+      if (phased) { int rem; phase = fast_div(t, sp_nt, rem); }
+      if (tl >= nbuf) mbar_wait(&hdr->tmem_empty[buf], empty_par);
       tc_fence_after();
       const uint32_t acc_base = tmem_base + (uint32_t)(buf * cols_per_buf);
-      for (int kc = 0; kc < n_k; ++kc, ++it) {
-        const int s = it % stages;
-        if (!(g.dbg & 8)) mbar_wait(&hdr->full[s], (uint32_t)((it / stages) & 1));
-        tc_fence_after();
+      for (int kc = 0; kc < n_k; ++kc) {
+        if (!(g.dbg & 8)) mbar_wait(&hdr->full[s], full_par);
         // descriptor low words: start address (16-B units) | LBO << 16
         const uint32_t a_lo0 = (((a_smem + (uint32_t)s * a_stride) >> 4) & 0x3FFF) | a_lbo;
         const uint32_t b_lo0 = (((b_smem + (uint32_t)(b_res ? kc : s) * b_stride) >> 4) & 0x3FFF) | b_lbo;
         for (int g0 = 0; g0 < sched_len; g0 += 16) {
-          const int key = tc.phase * 64 + g0;                           // schedule group held in aa / bb
+          const int key = phase * 64 + g0;                              // schedule group held in aa / bb
           if (key != cur_key) {
             cur_key = key;
-            const uint2* sc = hdr->sched + tc.phase * sched_len + g0;   // (reads past the end are never issued)
+            const uint2* sc = hdr->sched + phase * sched_len + g0;      // (reads past the end are never issued)
 #pragma unroll
             for (int i = 0; i < 16; ++i) { const uint2 v = sc[i]; aa[i] = v.x; bb[i] = v.y; }
           }
@@ -325,18 +331,19 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
           uint32_t ab[16], bk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) { ab[i] = a_lo0 + aa[i]; bk[i] = b_lo0 + bb[i]; }
+          const uint32_t mt_step = mt_desc;
           if (elect_one()) {
             const uint32_t first_acc = (kc > 0 || g0 > 0) ? 1u : 0u;   // the very first MMA of a tile overwrites
             // straight-line bodies for the schedule lengths the planner produces; predicated fallback otherwise
-            if (cnt >= 16)      issue_group<16>(acc_base, n_mtiles, n_tile, mt_desc, ab, bk, a_hi, b_hi, idesc, first_acc);
-            else if (cnt == 9)  issue_group<9>(acc_base, n_mtiles, n_tile, mt_desc, ab, bk, a_hi, b_hi, idesc, first_acc);
-            else if (cnt == 4)  issue_group<4>(acc_base, n_mtiles, n_tile, mt_desc, ab, bk, a_hi, b_hi, idesc, first_acc);
-            else if (cnt == 8)  issue_group<8>(acc_base, n_mtiles, n_tile, mt_desc, ab, bk, a_hi, b_hi, idesc, first_acc);
-            else if (cnt == 2)  issue_group<2>(acc_base, n_mtiles, n_tile, mt_desc, ab, bk, a_hi, b_hi, idesc, first_acc);
-            else if (cnt == 1)  issue_group<1>(acc_base, n_mtiles, n_tile, mt_desc, ab, bk, a_hi, b_hi, idesc, first_acc);
+            if (cnt >= 16)      issue_group<16>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 9)  issue_group<9>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 4)  issue_group<4>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 8)  issue_group<8>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 2)  issue_group<2>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 1)  issue_group<1>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, a_hi, b_hi, idesc, first_acc);
             else {
               uint32_t moff = 0, d = acc_base;
-              for (int mt = 0; mt < n_mtiles; ++mt, moff += mt_desc, d += n_tile) {
+              for (int mt = 0; mt < n_mtiles; ++mt, moff += mt_step, d += n_tile) {
 #pragma unroll
                 for (int k = 0; k < 16; ++k)
                   if (k < cnt) umma_f16kind_lohi(d, ab[k] + moff, a_hi, bk[k], b_hi, idesc, k == 0 ? first_acc : 1u);
@@ -350,7 +357,9 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
           if (kc == n_k - 1) umma_commit(&hdr->tmem_full[buf]);
         }
         __syncwarp();
+        if (++s == stages) { s = 0; full_par ^= 1u; }
       }
+      if (++buf == nbuf) { buf = 0; empty_par ^= 1u; }
     }
   } else {
     // ================================ epilogue =====================================

@@ -164,6 +164,44 @@ def test_conv_decoder_residual(gsx_lib, dtype):
     close(r['out'], ref, 'residual')
 
 
+def test_conv_space_to_depth_plan(gsx_lib, dtype):
+    """The space-to-depth plan of thin 3x3 layers (GEMM rows = 2x2 pixel blocks, 4 input phase planes, 4 output
+    phases as column blocks; default only for the final conv) forced on for the raw, generator and residual
+    epilogues, against the same references as the dense plan -- and against the dense plan itself."""
+    use(dtype)
+    from gan_segmentation_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(12)
+    s2d = dict(s2d=1)
+    for (n, cin, cout, h, w) in [(2, 16, 16, 64, 64), (1, 32, 32, 20, 36), (3, 16, 16, 18, 130), (1, 32, 16, 66, 64)]:
+        x = bf(torch.randn((n, cin, h, w), generator=g)).cuda()
+        wt = make_w(L.CONV3, cin, cout, g)
+        r = ops.conv(L.CONV3, x, wt.numpy(), override=s2d, dtype=dtype)
+        assert r['plan']['n_slots'] == 16, r['plan']
+        close(r['out'], F.conv2d(x, wt.cuda(), None, 1, 1), f's2d raw {n, cin, cout, h, w}')
+        r0 = ops.conv(L.CONV3, x, wt.numpy(), override=dict(s2d=0), dtype=dtype)
+        assert r0['plan']['n_slots'] == 9
+        close(r['out'], r0['out'], 's2d vs dense plan', rel=2.0 ** -7 if dtype == 'bf16' else 2.0 ** -10)
+    # generator conv_2 epilogue
+    n, c, h, w = 2, 16, 64, 96
+    x = bf(torch.randn((n, c, h, w), generator=g)).cuda()
+    wt = make_w(L.CONV3, c, c, g)
+    ns = torch.randn(c, generator=g).cuda() * 0.3
+    b = torch.randn(c, generator=g).cuda() * 0.2
+    nz = torch.randn((n, 1, h, w), generator=g).cuda()
+    r = ops.conv(L.CONV3, x, wt.numpy(), bias=b, nscale=ns, noise=nz, flags=L.EPI_LRELU | L.EPI_STATS, override=s2d, dtype=dtype)
+    v = F.leaky_relu(F.conv2d(x, wt.cuda(), None, 1, 1) + ns.view(1, -1, 1, 1) * nz + b.view(1, -1, 1, 1), 0.2)
+    close(r['out'], v, 's2d generator epilogue')
+    s1, s2 = v.sum(dim=(2, 3)), (v * v).sum(dim=(2, 3))
+    rt = 2e-3 if r['plan']['NB'] == 1 else 8e-3
+    assert torch.allclose(r['stats'][:, :, 0], s1, rtol=rt, atol=rt * s2.sqrt().max().item()), r['plan']
+    assert torch.allclose(r['stats'][:, :, 1], s2, rtol=rt), r['plan']
+    # decoder conv_b: residual at block resolution
+    sc = bf(torch.randn((n, c, h // 2, w // 2), generator=g)).cuda()
+    r = ops.conv(L.CONV3, x, wt.numpy(), bias=b, flags=L.EPI_LRELU, addsrc=sc, override=s2d, dtype=dtype)
+    ref = F.leaky_relu(F.conv2d(x, wt.cuda(), b, 1, 1), 0.2) + F.interpolate(sc, scale_factor=2, mode='nearest')
+    close(r['out'], ref, 's2d residual')
+
+
 def test_conv_argmax(gsx_lib, dtype):
     """Final decoder conv + argmax: the mask must equal the first-max argmax of the logits the kernel
     itself produced (bit-exact), and the logits must match the fp32 reference."""

@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, int lbo, Sched
   __shared__ uint64_t bar2;
   __shared__ uint32_t tmem_slot;
   for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = rnd ? (0x38003800u + ((i * 2654435761u) >> 7 & 0x03ff03ffu)) : 0x3c003c00u;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1000000); fence_barrier_init(); }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&bar2, commit_every < 0 ? 1 : 1000000); fence_barrier_init(); }
   if (threadIdx.x < 32) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, int lbo, Sched
       for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) umma_f16kind_lohi(dd[k], aa[k], a_hi, bb[k], b_hi, idesc, 1u);
-        if (commit_every && (i % commit_every) == commit_every - 1) umma_commit(&bar2);
+        if (commit_every > 0 && (i % commit_every) == commit_every - 1) umma_commit(&bar2);
+        if (commit_every < 0 && (i % (-commit_every)) == -commit_every - 1) { umma_commit(&bar2); umma_commit(&bar2); }
       }
       umma_commit(&bar);
     }
@@ -111,13 +112,13 @@ int main() {
       printf("sustained N=%3d data=%s: %.1f cycles/MMA, %.2f ms, SM clock %.0f MHz, %.1f ns/MMA\n", N, rnd ? "random" : "ones",
              (double)cyc / (it2 * 16.0), ms, cyc / (ms * 1e3), ms * 1e6 / (it2 * 16.0));
     }
-  for (int ce : {0, 1, 2, 4, 8}) {
+  for (int ce : {0, 1, 2, 4, 8, -1, -2, -9}) {
     Sched sc;
     for (int i = 0; i < 16; ++i) { sc.d[i] = (i / 4) % 4; sc.a[i] = (i % 9) * 67; sc.b[i] = i % 9; }
     bench<<<148, 128, 200 * 1024>>>(64, 4000, 9504, sc, d, 1, ce);
     cudaDeviceSynchronize();
     long long cyc; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
-    printf("N=64 commit every %2d x16 MMAs: %.1f cycles/MMA\n", ce, (double)cyc / (4000 * 16.0));
+    printf("N=64 commit every %2d x16 MMAs (negative: two commits completing a count-1 barrier): %.1f cycles/MMA\n", ce, (double)cyc / (4000 * 16.0));
   }
   return 0;
 }
