@@ -1,4 +1,4 @@
-"""Drop-in mirror of the predict half of the reference's SegSolver (seg_solver.py:16-132, 307-349)."""
+"""Drop-in mirror of the predict / evaluate half of the reference's SegSolver (seg_solver.py:16-132, 222-349)."""
 from __future__ import annotations
 
 import os
@@ -29,8 +29,9 @@ class SegSolver:
     """``SegSolver(max_res_log2, path_to_data, checkpoints_dir, gpu_ids, keep_weights)`` (seg_solver.py:17).
 
     The generate path needs ``predict`` / ``load`` / ``save`` and the attributes callers read
-    (``is_trained``, ``net``, ``cfg``, ``ctx``, ``params_file``).  ``fit`` / ``evaluate`` (decoder training,
-    seg_solver.py:222-305, 351-465) are outside this round's scope and raise NotImplementedError.
+    (``is_trained``, ``net``, ``cfg``, ``ctx``, ``params_file``); ``evaluate`` runs the decoder and the loss kernel
+    over a directory of annotated samples.  ``fit`` (decoder training, seg_solver.py:351-465) needs the decoder
+    backward pass, which is not built yet, and raises NotImplementedError.
     """
 
     def __init__(self, max_res_log2, path_to_data, checkpoints_dir, gpu_ids, keep_weights=True, *, base_hw=(4, 4),
@@ -130,4 +131,58 @@ class SegSolver:
         raise NotImplementedError('decoder training (seg_solver.py:351-465) is not part of the generate hot path yet')
 
     def evaluate(self, input_dir, output_dir=None):
-        raise NotImplementedError('evaluation (seg_solver.py:222-305) is not part of the generate hot path yet')
+        """seg_solver.py:222-305: pixel accuracy, mean IoU (background skipped) and the mean SoftmaxCE loss over
+        the annotated samples of ``input_dir`` (``feat_*.pickle`` + ``img_*.jpg`` + ``mask_*.png``).  Returns
+        ``[('accuracy', a), ('mean-iou', m), ('total-loss', l)]``; with ``output_dir`` also writes, per sample,
+        the image, predicted / ground-truth masks (255 / 128 / 0) and a metrics line, as the reference does.
+        Batches of ``cfg['val_batch_size']``, an incomplete last batch is discarded (``last_batch='discard'``, :166);
+        the reference shuffles the order, which none of the returned numbers depends on."""
+        from .metrics import SegmentationMetric
+        from .seg_datasets import CollectionDataset
+        from .training import softmax_ce
+        ds = CollectionDataset(input_dir, self.cfg, max_samples=None, load_to_memory=False, output_idx=True)
+        if len(ds) <= 0:
+            print('number of training samples should be > 0')
+            raise ValueError
+        bs = int(self.cfg.get('val_batch_size', 1))
+        print('total eval samples: {}'.format(len(ds)))
+        print('batch size: {}'.format(bs))
+        metric = SegmentationMetric(self.cfg['num_classes'], skip_bg=True)
+        total_loss, total_cnt = 0.0, 0
+        if output_dir is not None:
+            os.makedirs(output_dir, exist_ok=True)
+        for b0 in range(0, len(ds) - bs + 1, bs):
+            items = [ds[i] for i in range(b0, b0 + bs)]
+            idx = [int(it[0]) for it in items]
+            imgs = np.stack([it[1] for it in items])                       # [N,3,H,W] float32 RGB
+            mask = np.stack([it[2] for it in items]).astype(np.int32)      # [N,1,H,W] in {1,0,-1}
+            nfeat = len(items[0]) - 3
+            feats = [np.stack([np.asarray(it[3 + k], np.float32) for it in items]) for k in range(nfeat)]
+            out = self.net.forward(feats, return_logits=True)
+            logits = out['logits']
+            labels = torch.as_tensor(mask, device=logits.device)
+            loss, _ = softmax_ce(logits, labels, want_grad=False)           # weight (mask > -1), :239-242
+            total_loss += float(loss.mean().item())
+            total_cnt += 1
+            pred_ids = out['mask'].cpu().numpy().astype(np.int64)           # first-max argmax of the same logits
+            metric.update(mask[:, 0], pred_ids)
+            if output_dir is not None:
+                import cv2
+                for i in range(bs):
+                    m_i = SegmentationMetric(self.cfg['num_classes'], skip_bg=True)
+                    m_i.update(mask[i:i + 1, 0], pred_ids[i:i + 1])
+                    metric_str = ', '.join(f'{name} {v:.3f}' for name, v in m_i.get_name_value())
+                    imname = ds.get_imname(idx[i])
+                    img_i = np.transpose(imgs[i], (1, 2, 0))
+                    pm = pred_ids[i].astype(np.int32)
+                    gm = mask[i, 0].astype(np.int32).copy()
+                    pm_out = np.where(pm == 1, 255, np.where(pm == 0, 128, pm)).astype(np.int32)
+                    gm_out = np.where(gm == 1, 255, np.where(gm == 0, 128, np.where(gm == -1, 0, gm))).astype(np.int32)
+                    cv2.imwrite(join(output_dir, imname), img_i[:, :, ::-1])
+                    cv2.imwrite(join(output_dir, imname.replace('img', 'mask').replace('.jpg', '.png')), pm_out)
+                    cv2.imwrite(join(output_dir, imname.replace('img', 'gt_mask').replace('.jpg', '.png')), gm_out)
+                    with open(join(output_dir, imname.replace('img', 'metrics').replace('.jpg', '.txt')), 'w') as fp:
+                        fp.write(', '.join(str(w) for w in [imname, img_i.shape, pm_out.shape, gm_out.shape, metric_str]) + '\n')
+        result = metric.get_name_value()
+        result.append(('total-loss', total_loss / total_cnt if total_cnt > 0 else 0.0))
+        return result

@@ -51,3 +51,55 @@ def test_multi_context_matches_single(tmp_path):
         assert np.array_equal(ia, ib) and np.array_equal(ma, mb)
     # and consecutive samples do not share noise
     assert not np.array_equal(a[0][0], a[1][0])
+
+
+def test_evaluate_annotated_samples(tmp_path):
+    """SegSolver.evaluate (seg_solver.py:222-305) over annotated samples written in the reference's format: the
+    returned accuracy / mean-IoU / total-loss equal the reference formulas (metrics.py:549-606, SoftmaxCELoss with
+    weight (mask > -1)) evaluated in numpy/torch on the decoder's own logits, and the per-sample files appear."""
+    import torch.nn.functional as F
+    from gan_segmentation_b200.seg_solver import SegSolver
+    from gan_segmentation_b200.seg_datasets import save_sample
+    from gan_segmentation_b200.params_io import save_params
+    gc, dc = generator_config(6), decoder_config(6)
+    gan_dir, ckpt, data = tmp_path / 'stylegan-models', tmp_path / 'checkpoints', tmp_path / 'data'
+    for d in (gan_dir, ckpt, data):
+        d.mkdir(exist_ok=True)
+    save_params(str(ckpt / 'checkpoint_last.params'), init_decoder_params(dc, seed=2))
+    solver = SegSolver(6, str(data), str(ckpt), gpu_ids=[0], keep_weights=False, verbose=False)
+    from gan_segmentation_b200.networks import Generator
+    G = Generator(gc)
+    G.set_parameters(init_generator_params(gc, seed=0))
+    out = G.forward(n=3, seed=5, return_u8=True, return_features=True)
+    imgs = out['img_u8'].cpu().numpy()
+    feats_all = [f.cpu().numpy() for f in out['features']]
+    rs = np.random.RandomState(1)
+    samples = [(imgs[i], [f[i] for f in feats_all]) for i in range(3)]
+    labels = []
+    for i, (img, feats) in enumerate(samples):
+        lab = rs.randint(-1, 2, img.shape[:2])
+        labels.append(lab)
+        save_sample(str(data), i, img, feats, lab)
+    res = dict(solver.evaluate(str(data), output_dir=str(tmp_path / 'eval_out')))
+    assert set(res) == {'accuracy', 'mean-iou', 'total-loss'}
+    # reference formulas on the decoder's logits
+    tot_c = tot_l = 0
+    inter = np.zeros(2); union = np.zeros(2); losses = []
+    for (img, feats), lab in zip(samples, labels):
+        lg = solver.net.forward([f[None] for f in feats], return_logits=True)['logits'].float().cpu()
+        pred = lg.argmax(1)[0].numpy()
+        valid = lab > -1
+        tot_c += int(((pred == lab) & valid).sum()); tot_l += int(valid.sum())
+        for c in range(2):
+            p_c = (pred == c) & valid; l_c = lab == c
+            inter[c] += (p_c & l_c).sum(); union[c] += (p_c | l_c).sum()
+        lp = F.log_softmax(lg, dim=1)
+        t = torch.as_tensor(lab)[None, None]
+        picked = -torch.gather(lp, 1, t.clamp(min=0)) * (t > -1).float()
+        losses.append(picked.mean().item())
+    assert abs(res['accuracy'] - tot_c / tot_l) < 1e-9
+    assert abs(res['mean-iou'] - (inter / union)[1:].mean()) < 1e-9
+    assert abs(res['total-loss'] - np.mean(losses)) < 1e-5
+    names = sorted(p.name for p in (tmp_path / 'eval_out').iterdir())
+    assert names == sorted([f'{k}_{i:06d}.{e}' for i in range(3) for k, e in
+                            (('img', 'jpg'), ('mask', 'png'), ('gt_mask', 'png'), ('metrics', 'txt'))])
