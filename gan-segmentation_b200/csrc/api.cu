@@ -111,6 +111,7 @@ static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1
   p.g = L.g;
   finish_geom_for_batch(p.g, N);
   p.e = epi;
+  p.e.out_planar = L.out_planar;
   p.wpack = L.wpack_dev;
   p.taps = L.taps_dev;
   set_error("");
@@ -726,6 +727,16 @@ extern "C" int gsx_dec_finalize(gsx_dec* d) {
   const auto& P = d->params;
   const int nf = d->nf;
   const bool bn = d->cfg.use_bn != 0;
+  // The three thin tensors at the output resolution that are produced by a conv epilogue and consumed by a thin
+  // 3x3 conv -- conv_a -> conv_b of the last res-block, conv_b -> final conv, top cvt -> final conv -- are stored
+  // phase-planar, so that the consumers can use the space-to-depth plan with dense TMA boxes (plan.cpp).
+  // GSX_PLANAR: 0 = off, 1 = final conv only, 2 = also the last conv_b (default).
+  const int topH = d->cfg.base_y << (nf - 1), topW = d->cfg.base_x << (nf - 1);
+  const int planar_env = getenv("GSX_PLANAR") ? atoi(getenv("GSX_PLANAR")) : 2;
+  const bool planar_ok = nf >= 2 && topH % 2 == 0 && topW % 2 == 0 && topH >= 16 && topW >= 16 &&
+                         d->cfg.features[nf - 1] <= 16 && !getenv("GSX_NO_S2D");
+  const bool planar_final = planar_ok && planar_env >= 1;
+  const bool planar_cb = planar_ok && planar_env >= 2;
   for (int i = 0; i < nf; ++i) {
     DecLevel l;
     l.H = d->cfg.base_y << i; l.W = d->cfg.base_x << i;
@@ -736,6 +747,7 @@ extern "C" int gsx_dec_finalize(gsx_dec* d) {
     set_error("");
     plan_conv(l.cvt, CONV3, l.H, l.W, l.cin, 0, l.f, 0, nullptr);
     if (*gsx_last_error()) return -1;
+    l.cvt.out_planar = (i == nf - 1 && planar_final) ? 1 : 0;
     if (!upload_conv(l.cvt, w.data())) return -2;
     l.b_cvt = dev_upload(b);
     const int c0 = i > 0 ? l.f : l.f, c1 = i > 0 ? l.f : 0;          // concat(prev, cvt) (networks_seg.py:108-109)
@@ -746,12 +758,16 @@ extern "C" int gsx_dec_finalize(gsx_dec* d) {
       if (!fold_conv_bn(P, mb + ".base_layers.0", bn ? mb + ".base_layers.1" : "", l.fnext, (size_t)cin_main * 9, w, b)) return -1;
       plan_conv(l.conv_a, UPCONV3, l.H, l.W, c0, c1, l.fnext, 0, nullptr);
       if (*gsx_last_error()) return -1;
+      const bool top_block = (i == nf - 2);
+      l.conv_a.out_planar = (top_block && planar_cb) ? 1 : 0;
       if (!upload_conv(l.conv_a, w.data())) return -2;
       l.b_a = dev_upload(b);
       if (!fold_conv_bn(P, mb + ".base_layers." + std::to_string(j_b), bn ? mb + ".base_layers." + std::to_string(j_b + 1) : "",
                         l.fnext, (size_t)l.fnext * 9, w, b)) return -1;
-      plan_conv(l.conv_b, CONV3, l.H * 2, l.W * 2, l.fnext, 0, l.fnext, 0, nullptr, /*aux: residual tile*/ 2);
+      plan_conv(l.conv_b, CONV3, l.H * 2, l.W * 2, l.fnext, 0, l.fnext, 0, nullptr, /*aux: residual tile*/ 2,
+                /*in_planar*/ (top_block && planar_cb) ? 1 : 0);
       if (*gsx_last_error()) return -1;
+      l.conv_b.out_planar = (top_block && planar_final) ? 1 : 0;
       if (!upload_conv(l.conv_b, w.data())) return -2;
       l.b_b = dev_upload(b);
       l.has_shortcut = (l.fnext != cin_main);                        // networks_seg.py:35-41
@@ -768,7 +784,7 @@ extern "C" int gsx_dec_finalize(gsx_dec* d) {
     } else {
       const std::string mb = "main_block_" + std::to_string(i) + ".0";
       if (!fold_conv_bn(P, mb, "", l.fnext, (size_t)cin_main * 9, w, b)) return -1;
-      plan_conv(l.final_, CONV3, l.H, l.W, c0, c1, l.fnext, l.fnext, nullptr);
+      plan_conv(l.final_, CONV3, l.H, l.W, c0, c1, l.fnext, l.fnext, nullptr, 0, /*in_planar*/ planar_final ? 1 : 0);
       if (*gsx_last_error()) return -1;
       if (!upload_conv(l.final_, w.data())) return -2;
       b.resize(16, 0.f);

@@ -102,6 +102,7 @@ struct ConvGeom {
   int a_stage_bytes, b_stage_bytes;
   int a_stage_stride;          // a_stage_bytes rounded up to 128 (TMA destination alignment)
   int plane_stride;            // s2d: bytes between the phase planes of a stage (128-aligned)
+  int in_planar;               // s2d: the inputs are stored phase-planar ([C/8][N][4 phases][H/2][W/2][8]): dense plane boxes
   int dbg;                     // tuning only (env GSX_DBG): 1 skip epilogue work, 2 skip MMAs, 4 skip activation loads,
                                //   8 issuers do not wait for operands (with 4: pure MMA issue rate)
   int a_off;                   // byte offset of the A stages in dynamic smem (after header + stats slots)
@@ -129,6 +130,7 @@ struct ConvEpi {
   float* stats;                // per-tile partial sums [N][stats_T][Cout][2] (sum, sumsq) or null; no atomics,
   int stats_T;                 //   so the InstanceNorm statistics are bit-reproducible (T = tiles per sample)
   const act_t* addsrc;          // blocked [Cout/8][N][Ho/2][Wo/2][8], added after activation, or null
+  int out_planar;              // 1: store the output phase-planar (its only consumer is a space-to-depth conv)
   const float* e_rows;         // DECONV4B border corrections: [N][2 (top,bottom)][Wo][Cout] and
   const float* e_cols;         //   [N][2 (left,right)][Ho][Cout] fp32, subtracted before noise / bias; or null
   unsigned char* mask;         // [N][Ho][Wo]
@@ -154,6 +156,7 @@ struct ConvLayer {
   int mode = CONV3;
   int cin0 = 0, cin1 = 0, cout = 0;   // channels of the two concatenated sources, real out channels
   int H = 0, W = 0;                   // input spatial size the layer was planned for
+  int out_planar = 0;                 // the layer's output goes to a phase-planar tensor (set by the owner of the graph)
   ConvGeom g{};                       // geometry with N-independent fields filled
   act_t* wpack_dev = nullptr;
   size_t wpack_elems = 0;
@@ -170,7 +173,7 @@ struct PlanOverride {
 
 // plan.cpp
 void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cout, int argmax_classes,
-               const PlanOverride* ov, int aux_kind = 0);
+               const PlanOverride* ov, int aux_kind = 0, int in_planar = 0);
 void make_noise_tensormap(CUtensorMap* tm, const void* base, int N, int H, int W, int boxW, int boxH, int boxN);
 void finish_geom_for_batch(ConvGeom& g, int N);
 // weights: CONV3/UPCONV3 (Cout,Cin,3,3); DECONV4 (Cin,Cout,4,4); CONV1 (Cout,Cin,1,1); fp32, already
@@ -181,6 +184,9 @@ void make_act_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, 
 // s2d mode: phase plane (py, px) of a blocked activation tensor, boxes in 2x2-block coordinates
 void make_plane_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, int W, int py, int px, int boxW, int boxH,
                           int boxN, int boxCB);
+// same for a tensor that is already stored phase-planar: a dense 4-D box of plane py*2+px
+void make_planar_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, int W, int plane, int boxW, int boxH,
+                           int boxN, int boxCB);
 // fills p.tm[] (or p.tm_pl[][] in s2d mode) for the layer's input tensors
 void make_input_tensormaps(ConvParams& p, const ConvLayer& L, int N, const void* x0, const void* x1);
 

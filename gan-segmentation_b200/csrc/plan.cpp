@@ -32,7 +32,7 @@ static int pow2_cols(int c) {
 }
 
 void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cout, int argmax_classes,
-               const PlanOverride* ov, int aux_kind) {
+               const PlanOverride* ov, int aux_kind, int in_planar) {
   L.mode = mode; L.H = H; L.W = W; L.cin0 = cin0; L.cin1 = cin1; L.cout = cout;
   ConvGeom& g = L.g;
   std::memset(&g, 0, sizeof(g));
@@ -47,8 +47,9 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   // (0.85 -> 0.73 ms); GSX_S2D=1 enables it for every eligible layer.
   static const int s2d_all = getenv("GSX_S2D") ? atoi(getenv("GSX_S2D")) : 0;
   int s2d = (mode == CONV3 && cin0 + cin1 <= 32 && cout <= 32 && H % 2 == 0 && W % 2 == 0 && H >= 16 && W >= 16 &&
-             (argmax_classes > 0 || (s2d_all && cout <= 16 && aux_kind != 2)) && !getenv("GSX_NO_S2D")) ? 1 : 0;
+             (argmax_classes > 0 || in_planar || (s2d_all && cout <= 16 && aux_kind != 2)) && !getenv("GSX_NO_S2D")) ? 1 : 0;
   if (ov && ov->s2d >= 0 && mode == CONV3 && H % 2 == 0 && W % 2 == 0) s2d = ov->s2d;
+  if (in_planar && !s2d) { set_error("plan_conv: a phase-planar input needs the space-to-depth plan"); return; }
   if (s2d) { H /= 2; W /= 2; }               // from here on H, W, TH, TW count blocks
   g.H = H; g.W = W;
   const bool up = (mode == UPCONV3 || mode == DECONV4 || mode == DECONV4B);
@@ -180,7 +181,7 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   g.hstack = hstack; g.mt_stride = mt_stride; g.xch_off = kHeader + stats_bytes;
   g.cb_stride_bytes = NB * g.BH * BW * 16;
   g.a_stage_bytes = g.cb_stride_bytes * CBK * planes;
-  g.s2d = s2d;
+  g.s2d = s2d; g.in_planar = in_planar;
   g.plane_stride = (g.cb_stride_bytes * CBK + 127) / 128 * 128;
   g.a_stage_stride = planes * g.plane_stride;
   g.b_stage_bytes = n_slots * (CBK / 2) * N_tile * 32;
@@ -400,8 +401,39 @@ void make_plane_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H
   }
 }
 
+void make_planar_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, int W, int plane, int boxW, int boxH,
+                           int boxN, int boxCB) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return; }
+  const int Hb = H / 2, Wb = W / 2;
+  const char* b = static_cast<const char*>(base) + (size_t)plane * Hb * Wb * 16;
+  const cuuint64_t dims[4] = {(cuuint64_t)Wb * 2, (cuuint64_t)Hb, (cuuint64_t)N, (cuuint64_t)(C / 8)};
+  const cuuint64_t strides[3] = {(cuuint64_t)Wb * 16, (cuuint64_t)H * W * 16, (cuuint64_t)N * H * W * 16};
+  const cuuint32_t box[4] = {(cuuint32_t)boxW * 2, (cuuint32_t)boxH, (cuuint32_t)boxN, (cuuint32_t)boxCB};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<char*>(b), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled (planar) failed (%d) C=%d N=%d H=%d W=%d box=%dx%dx%dx%d", (int)r, C, N,
+             H, W, boxW, boxH, boxN, boxCB);
+    set_error(buf);
+  }
+}
+
 void make_input_tensormaps(ConvParams& p, const ConvLayer& L, int N, const void* x0, const void* x1) {
   const ConvGeom& g = p.g;
+  if (g.s2d && g.in_planar) {
+    for (int pl = 0; pl < 4; ++pl) {
+      make_planar_tensormap(&p.tm_pl[0][pl], x0, L.cin0, N, L.H, L.W, pl, g.BW, g.BH, g.NB, g.CBK);
+      if (L.cin1 > 0) make_planar_tensormap(&p.tm_pl[1][pl], x1, L.cin1, N, L.H, L.W, pl, g.BW, g.BH, g.NB, g.CBK);
+      else p.tm_pl[1][pl] = p.tm_pl[0][pl];
+    }
+    p.tm[0] = p.tm_pl[0][0];
+    p.tm[1] = p.tm_pl[1][0];
+    return;
+  }
   if (g.s2d) {
     for (int pl = 0; pl < 4; ++pl) {
       make_plane_tensormap(&p.tm_pl[0][pl], x0, L.cin0, N, L.H, L.W, pl >> 1, pl & 1, g.BW, g.BH, g.NB, g.CBK);

@@ -257,9 +257,13 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
           if (g.s2d) {
             // the 4 input phase planes of the block tile, each a dense [cb][nb][BH][BW] operand plane
 #pragma unroll
-            for (int pl = 0; pl < 4; ++pl)
-              tma_load_5d(a_base + (size_t)s * g.a_stage_stride + (size_t)pl * g.plane_stride, &p.tm_pl[src][pl],
-                          &hdr->full[s], 0, tc.x0 - 1, tc.y0 - 1, tc.n0, cb0);
+            for (int pl = 0; pl < 4; ++pl) {
+              uint8_t* dst = a_base + (size_t)s * g.a_stage_stride + (size_t)pl * g.plane_stride;
+              if (g.in_planar)        // stored phase-planar: dense rows
+                tma_load_4d(dst, &p.tm_pl[src][pl], &hdr->full[s], (tc.x0 - 1) * 2, tc.y0 - 1, tc.n0, cb0);
+              else                    // gathered from the pixel-interleaved layout: 16-byte inner extent (slow)
+                tma_load_5d(dst, &p.tm_pl[src][pl], &hdr->full[s], 0, tc.x0 - 1, tc.y0 - 1, tc.n0, cb0);
+            }
           } else {
             // dim0 is in 8-byte units (2 per pixel) so that the inner box extent reaches 128 pixels
             tma_load_4d(a_base + (size_t)s * g.a_stage_stride, &p.tm[src], &hdr->full[s], (tc.x0 - 1) * 2, tc.y0 - 1,
@@ -550,7 +554,16 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
                     o[k] = pack_x2(a0, a1);
                     o[4 + k] = pack_x2(b0, b1);
                   }
-                  if (c0 + h * 8 < e.Cout) st_global_256(obase + (size_t)h * g.N * plane_out * 8, o);
+                  if (c0 + h * 8 < e.Cout) {
+                    if (e.out_planar) {       // planes (py,0) and (py,1) of the block-resolution grid
+                      act_t* pb = e.out + ((((size_t)(c0 >> 3) + h) * g.N + n) * plane_out +
+                                           ((size_t)(2 * py) * g.H + y) * g.W + x) * 8;
+                      *reinterpret_cast<uint4*>(pb) = make_uint4(o[0], o[1], o[2], o[3]);
+                      *reinterpret_cast<uint4*>(pb + (size_t)g.H * g.W * 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                    } else {
+                      st_global_256(obase + (size_t)h * g.N * plane_out * 8, o);
+                    }
+                  }
                 }
               }
             }
@@ -583,6 +596,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
             const bool valid = locate(mt, n, y, x);
             if (e.up) { y = 2 * y + (ph >> 1); x = 2 * x + (ph & 1); }
             const size_t pix = (size_t)y * e.Wo + x;
+            // phase-planar output: plane (y&1, x&1) of the block grid
+            const size_t pix_st = e.out_planar ? ((size_t)((y & 1) * 2 + (x & 1)) * (e.Ho >> 1) + (y >> 1)) * (e.Wo >> 1) + (x >> 1) : pix;
             float nz = 0.f;
             uint4 add0 = make_uint4(0, 0, 0, 0), add1 = add0;
             if (valid) {
@@ -634,7 +649,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
                   o.y = pack_x2(f[h * 8 + 2], f[h * 8 + 3]);
                   o.z = pack_x2(f[h * 8 + 4], f[h * 8 + 5]);
                   o.w = pack_x2(f[h * 8 + 6], f[h * 8 + 7]);
-                  *reinterpret_cast<uint4*>(e.out + (((size_t)((c0 >> 3) + h) * g.N + n) * plane_out + pix) * 8) = o;
+                  *reinterpret_cast<uint4*>(e.out + (((size_t)((c0 >> 3) + h) * g.N + n) * plane_out + pix_st) * 8) = o;
                 }
               }
             }
