@@ -81,10 +81,8 @@ struct ConvGeom {
   int up_cols;                 // 1: the 4 output phases of an up-conv are column blocks of ONE accumulator
                                //    (N_tile = 4*cout_tile); every distinct input shift is a single MMA whose
                                //    weight tile is zero for the phases that do not use that shift
-  int cout_tile;               // output channels per CTA (= N_tile unless up_cols / hstack)
-  int hstack;                  // always 0 in this build (3 horizontal taps stacked along N: removed, see plan.cpp)
+  int cout_tile;               // output channels per CTA (= N_tile unless up_cols)
   int mt_stride;               // positions between consecutive MMA tiles (128)
-  int xch_off;                 // unused (hstack exchange buffer)
   int aux_kind;                // epilogue operand staged per tile by TMA into smem (2 buffers): 0 none,
                                //   1 = noise plane tile [NB][TH][TW] fp32, 2 = residual tile (blocked, half resolution)
   int aux_off, aux_bytes;      // smem offset of the 2 aux buffers, bytes per buffer (128-aligned)
@@ -167,7 +165,7 @@ void build_tap_table(const ConvGeom& g, int4* out /* 4*kMaxSlots */);
 struct PlanOverride {
   int TH, TW, NB, CBK, N_tile, stages, phase_grid;   // 0 / -1 = keep default
   int epi_groups, acc_bufs, max_mtiles;              // 0 = keep default
-  int hstack;                                        // -1 = keep default, 0/1 force
+  int hstack;                                        // must be <= 0 (variant removed, see plan.cpp)
   int s2d;                                           // -1 = keep default, 0/1 force
 };
 

@@ -69,16 +69,12 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   const int up_cols = ((up && !phase_grid) || s2d) ? 1 : 0;
   const int cout_tile = N_tile;
   if (up_cols) N_tile = 4 * cout_tile;        // phases stacked along the MMA N dimension (<= 256)
-  // every M=128 kind::f16 MMA costs ~60-75 cycles for any N <= 128 (tools/umma_bench.cu), so thin 3x3 layers are
-  // bound by the NUMBER of MMAs.  Stacking the 3 horizontal taps along N (3 MMAs per k16 step instead of 9, the
-  // epilogue forming out[q] = acc[q][0] + acc[q+1][1] + acc[q+2][2] by shuffles) was implemented and parity-green
-  // in round 1 but measured 2-2.5x SLOWER (heavier epilogue: 3x TMEM loads, 32 shuffles, a barrier per unit), and
-  // merely compiling the path in cost the plain epilogue 40 registers -- it was removed from the kernel
-  // (git history: "hstack"); the geometry fields stay for the next attempt.
-  const int hstack = 0;
+  // (A variant stacking the 3 horizontal taps of a 3x3 layer along N -- 3 MMAs per k16 step, the epilogue forming
+  //  out[q] = acc[q][0] + acc[q+1][1] + acc[q+2][2] by shuffles -- was parity-green in round 1 but 2-2.5x slower and cost
+  //  the plain epilogue 40 registers just by being compiled in; removed, git history "hstack".  The override field
+  //  stays in the ABI of the tuning hook.)
   if (ov && ov->hstack > 0) { set_error("plan_conv: hstack mode is not compiled into this build"); return; }
-  if (hstack) N_tile = 3 * cout_tile;
-  const int mt_stride = hstack ? 126 : 128;
+  const int mt_stride = 128;
   const int G = 1;
   const bool thin = (cin0 + cin1) <= 64 && cout <= 64;
   // thin layers: 256 columns per accumulator buffer so that two buffers fit (MMA / epilogue overlap);
@@ -95,8 +91,7 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   const int epi_groups = 2;
   if (ov && ov->epi_groups > 0 && ov->epi_groups != 2) { set_error("plan_conv: only epi_groups = 2 is built"); return; }
   const int stats_bytes = (2 * 4 * epi_groups * 2 * cout_tile * 4 + 1023) / 1024 * 1024;
-  const int xch_bytes = hstack ? 2 * epi_groups * 5 * 48 * 4 : 0;
-  const int hdr_bytes = kHeader + stats_bytes + (xch_bytes + 1023) / 1024 * 1024;
+  const int hdr_bytes = kHeader + stats_bytes;
 
   int TW = (W <= 126) ? W : ((W % 64 == 0) ? 64 : 126);
   if (ov && ov->TW > 0) TW = ov->TW;
@@ -118,7 +113,7 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   if (ov && ov->TH > 0) TH = ov->TH;
   if (ov && ov->NB > 0) NB = ov->NB;
 
-  const int n_slots = s2d ? 16 : (mode == CONV3) ? (hstack ? 3 : 9) : (mode == CONV1 ? 1 : (phase_grid ? 4 : 9));
+  const int n_slots = s2d ? 16 : (mode == CONV3) ? 9 : (mode == CONV1 ? 1 : (phase_grid ? 4 : 9));
   const int planes = s2d ? 4 : 1;
 
   // aux staging: plain 3x3 layers (noise / residual tile) and the folded deconv (noise tile at output resolution);
@@ -178,7 +173,7 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   g.up_cols = up_cols; g.cout_tile = cout_tile;
   g.n_groups = G; g.n_slots = n_slots; g.phase_grid = phase_grid; g.stages = stages;
   g.n_mtiles = ceil_div(((NB - 1) * g.BH + TH - 1) * BW + TW, mt_stride);
-  g.hstack = hstack; g.mt_stride = mt_stride; g.xch_off = kHeader + stats_bytes;
+  g.mt_stride = mt_stride;
   g.cb_stride_bytes = NB * g.BH * BW * 16;
   g.a_stage_bytes = g.cb_stride_bytes * CBK * planes;
   g.s2d = s2d; g.in_planar = in_planar;
@@ -215,10 +210,6 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
         g.slot_shift[0][s] = (kP[sy] * 2 + kP[sx]) * plane_pos + (kT[sy] + 1) * BW + (kT[sx] + 1);
         g.slot_group[s] = 0; g.slot_first[s] = (s == 0);
       }
-  } else if (hstack) {
-    for (int ky = 0; ky < 3; ++ky) {
-      g.slot_shift[0][ky] = (short)(ky * BW); g.slot_group[ky] = 0; g.slot_first[ky] = (ky == 0);
-    }
   } else if (mode == CONV3 || up_cols) {
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx) {
@@ -277,11 +268,6 @@ void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& o
       if (ky < -1 || ky > 1 || kx < -1 || kx > 1) return 0.f;
       return w[(((size_t)c * cin + ci) * 3 + ky + 1) * 3 + kx + 1];
     }
-    if (L.mode == CONV3 && g.hstack) {                       // row block kx of the weight tile, slot = ky
-      const int kx = co / g.cout_tile, c = co % g.cout_tile;
-      if (c >= cout) return 0.f;
-      return w[(((size_t)c * cin + ci) * 3 + slot) * 3 + kx];
-    }
     if (L.mode == CONV3) { const int ky = slot / 3, kx = slot % 3; return w[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx]; }
     if (L.mode == CONV1) return w[(size_t)co * cin + ci];
     if (L.mode == DECONV4B) {
@@ -336,8 +322,8 @@ void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& o
         for (int slot = 0; slot < g.n_slots; ++slot)
           for (int j = 0; j < k16pc; ++j, base += tile)
             for (int nr = 0; nr < g.N_tile; ++nr) {
-              const int co = (g.up_cols || g.hstack) ? nr : nt * g.N_tile + nr;
-              if (!(g.up_cols || g.hstack) && co >= cout) continue;
+              const int co = g.up_cols ? nr : nt * g.N_tile + nr;
+              if (!g.up_cols && co >= cout) continue;
               for (int k = 0; k < 16; ++k) {
                 const int ci = (kc * g.CBK + 2 * j) * 8 + k;
                 out[base + (size_t)(k >> 3) * (g.N_tile * 8) + (size_t)nr * 8 + (k & 7)] =

@@ -50,7 +50,7 @@ typedef struct {
 typedef struct {
   int TH, TW, NB, CBK, N_tile, stages, phase_grid;     /* 0 (phase_grid: -1) keeps the planner's choice */
   int epi_groups, acc_bufs, max_mtiles;
-  int hstack;                                         /* -1 keeps the planner's choice */
+  int hstack;                                         /* must be <= 0: the tap-stacked variant is not built */
   int s2d;                                            /* -1 keeps the planner's choice, 0/1 force (thin 3x3 layers) */
 } gsx_plan_override;
 
