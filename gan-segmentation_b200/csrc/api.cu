@@ -172,6 +172,7 @@ struct gsx_synth {
   act_t* d_const = nullptr;
   int last_n = 0;
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};   // gsx_generate_host pipelining
+  unsigned long long* d_counter = nullptr;   // running global sample index in HBM (gsx_synth_device_counter; CUDA-graph replays)
 
   int nf(int r) const {
     const int f = (int)(cfg.fmap_base / std::pow(2.0, (r - 1) * (double)cfg.fmap_decay));
@@ -279,6 +280,7 @@ extern "C" int gsx_synth_create(const gsx_synth_cfg* cfg, gsx_synth** out) {
 extern "C" void gsx_synth_destroy(gsx_synth* h) {
   if (!h) return;
   for (int i = 0; i < 2; ++i) { if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); }
+  cudaFree(h->d_counter);
   for (int i = 0; i < 8; ++i) { cudaFree(h->d_map_w[i]); cudaFree(h->d_map_b[i]); }
   cudaFree(h->d_aff_w); cudaFree(h->d_aff_b); cudaFree(h->d_unit_layer); cudaFree(h->d_latent_avg);
   cudaFree(h->d_psi); cudaFree(h->d_wrgb); cudaFree(h->d_brgb); cudaFree(h->d_const);
@@ -460,6 +462,14 @@ extern "C" int gsx_synth_finalize(gsx_synth* h) {
   return 0;
 }
 
+extern "C" int gsx_synth_device_counter(gsx_synth* h, int enable, uint64_t start) {
+  if (!h) { set_error("null handle"); return -1; }
+  if (!enable) { cudaFree(h->d_counter); h->d_counter = nullptr; return 0; }
+  if (!h->d_counter && !cuda_ok(cudaMalloc(&h->d_counter, sizeof(unsigned long long)), "counter")) return -2;
+  const unsigned long long v = start;
+  return cuda_ok(cudaMemcpy(h->d_counter, &v, sizeof(v), cudaMemcpyHostToDevice), "counter init") ? 0 : -2;
+}
+
 extern "C" int gsx_synth_workspace_bytes(const gsx_synth* h, int n, size_t* bytes) {
   if (!h || !bytes || n <= 0) { set_error("bad argument"); return -1; }
   *bytes = synth_layout(h, n, nullptr).total;
@@ -488,7 +498,7 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     if (!cuda_ok(cudaMemcpyAsync(w.z, z_dev, (size_t)N * Z * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy z")) return -2;
   } else {
     ProfScope ps("latents", 4.0 * N * Z, 0, st);
-    launch_fill_latents(w.z, N, Z, seed, first_sample, st); g_launches++;
+    launch_fill_latents(w.z, N, Z, seed, first_sample, st, h->d_counter); g_launches++;
   }
   const float* psi = h->d_psi;
   if (psi_host) {
@@ -529,16 +539,17 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
       size_t tot = 0;
       for (int l = 0; l < h->nlayers; ++l) tot += pl.elems[l];
       ProfScope ps("noise", 4.0 * N * tot, 0, st);
-      launch_fill_noise_all(pl, h->nlayers, N, seed, first_sample, st); g_launches++;
+      launch_fill_noise_all(pl, h->nlayers, N, seed, first_sample, st, h->d_counter); g_launches++;
     } else if (any) {
       for (int l = 0; l < h->nlayers; ++l) {
         if (noise[l] != w.noise[l]) continue;
         ProfScope ps("noise", 4.0 * N * pl.elems[l], 0, st);
-        launch_fill_noise(w.noise[l], pl.elems[l], N, seed, first_sample, l, st); g_launches++;
+        launch_fill_noise(w.noise[l], pl.elems[l], N, seed, first_sample, l, st, h->d_counter); g_launches++;
       }
     }
   }
   h->last_n = N;
+  if (h->d_counter) { launch_advance_counter(h->d_counter, (unsigned long long)N, st); g_launches++; }   // after its readers
 
   for (size_t bi = 0; bi < h->blocks.size(); ++bi) {
     const SynthBlock& b = h->blocks[bi];

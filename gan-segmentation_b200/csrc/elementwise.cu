@@ -419,9 +419,10 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
   z0 = r * c; z1 = r * s;
 }
 __global__ void fill_normal_kernel(float* out, size_t per_sample, int N, uint64_t seed, uint64_t first_sample,
-                                   uint32_t stream_id) {
+                                   uint32_t stream_id, const unsigned long long* first_dev) {
   const size_t quads = (per_sample + 3) / 4;
   const int n = blockIdx.y;
+  if (first_dev) first_sample = *first_dev;         // CUDA-graph replays: the running sample index lives in HBM
   const uint64_t gs = first_sample + (uint64_t)n;
   for (size_t qd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quads; qd += (size_t)gridDim.x * blockDim.x) {
     uint32_t c[4] = {(uint32_t)qd, stream_id, (uint32_t)gs, (uint32_t)(gs >> 32)};
@@ -436,17 +437,19 @@ __global__ void fill_normal_kernel(float* out, size_t per_sample, int N, uint64_
   }
 }
 void launch_fill_noise(float* out, size_t plane_elems, int N, uint64_t seed, uint64_t first_sample, int layer,
-                       cudaStream_t st) {
+                       cudaStream_t st, const unsigned long long* first_dev) {
   const size_t quads = (plane_elems + 3) / 4;
   dim3 grid((unsigned)min((size_t)1024, (quads + 255) / 256), N);
-  fill_normal_kernel<<<grid, 256, 0, st>>>(out, plane_elems, N, seed, first_sample, (uint32_t)layer);
+  fill_normal_kernel<<<grid, 256, 0, st>>>(out, plane_elems, N, seed, first_sample, (uint32_t)layer, first_dev);
 }
 // all noise planes of a forward pass in one launch: the quads (4 values) of all layers of a sample form one index
 // space, so that every block has the same amount of work (a grid dimension per layer left ~70 % of the blocks of
 // the low-resolution layers empty and the launch cost 0.26 ms for 0.36 GB)
 struct NoiseIndex { size_t qstart[25]; int nlayers; };
-__global__ void __launch_bounds__(256) fill_noise_all_kernel(NoisePlanes pl, NoiseIndex ix, uint64_t seed, uint64_t first_sample) {
+__global__ void __launch_bounds__(256) fill_noise_all_kernel(NoisePlanes pl, NoiseIndex ix, uint64_t seed, uint64_t first_sample,
+                                                             const unsigned long long* first_dev) {
   const int n = blockIdx.y;
+  if (first_dev) first_sample = *first_dev;
   const uint64_t gs = first_sample + (uint64_t)n;
   const size_t total = ix.qstart[ix.nlayers];
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
@@ -469,7 +472,8 @@ __global__ void __launch_bounds__(256) fill_noise_all_kernel(NoisePlanes pl, Noi
     }
   }
 }
-void launch_fill_noise_all(const NoisePlanes& pl, int nlayers, int N, uint64_t seed, uint64_t first_sample, cudaStream_t st) {
+void launch_fill_noise_all(const NoisePlanes& pl, int nlayers, int N, uint64_t seed, uint64_t first_sample, cudaStream_t st,
+                           const unsigned long long* first_dev) {
   NoiseIndex ix{};
   ix.nlayers = nlayers;
   size_t acc = 0;
@@ -478,12 +482,17 @@ void launch_fill_noise_all(const NoisePlanes& pl, int nlayers, int N, uint64_t s
   // ~4 quads per thread; at least one block per sample
   const size_t blocks = (acc + 1023) / 1024;
   dim3 grid((unsigned)(blocks < 1 ? 1 : (blocks > 4096 ? 4096 : blocks)), N);
-  fill_noise_all_kernel<<<grid, 256, 0, st>>>(pl, ix, seed, first_sample);
+  fill_noise_all_kernel<<<grid, 256, 0, st>>>(pl, ix, seed, first_sample, first_dev);
 }
 
-void launch_fill_latents(float* z, int N, int Z, uint64_t seed, uint64_t first_sample, cudaStream_t st) {
+void launch_fill_latents(float* z, int N, int Z, uint64_t seed, uint64_t first_sample, cudaStream_t st,
+                         const unsigned long long* first_dev) {
   dim3 grid(1, N);
-  fill_normal_kernel<<<grid, 128, 0, st>>>(z, (size_t)Z, N, seed, first_sample, 0xFFFFu);
+  fill_normal_kernel<<<grid, 128, 0, st>>>(z, (size_t)Z, N, seed, first_sample, 0xFFFFu, first_dev);
+}
+__global__ void advance_counter_kernel(unsigned long long* counter, unsigned long long by) { *counter += by; }
+void launch_advance_counter(unsigned long long* counter, unsigned long long by, cudaStream_t st) {
+  advance_counter_kernel<<<1, 1, 0, st>>>(counter, by);
 }
 
 

@@ -226,11 +226,15 @@ void launch_finalize(const float* partial, int T, int N, int C, int HW, const fl
                      int style_off, float* coef, cudaStream_t st);
 void launch_blocked_to_nchw(const act_t* in, float* out, int C, int N, int HW, cudaStream_t st);
 void launch_nchw_to_blocked(const float* in, act_t* out, int C, int N, int HW, cudaStream_t st);
+// first_dev != nullptr: the first sample index is read from device memory (CUDA-graph replays), not from the argument
 void launch_fill_noise(float* out, size_t plane_elems, int N, uint64_t seed, uint64_t first_sample, int layer,
-                       cudaStream_t st);
-void launch_fill_latents(float* z, int N, int Z, uint64_t seed, uint64_t first_sample, cudaStream_t st);
+                       cudaStream_t st, const unsigned long long* first_dev = nullptr);
+void launch_fill_latents(float* z, int N, int Z, uint64_t seed, uint64_t first_sample, cudaStream_t st,
+                         const unsigned long long* first_dev = nullptr);
+void launch_advance_counter(unsigned long long* counter, unsigned long long by, cudaStream_t st);
 struct NoisePlanes { float* ptr[24]; size_t elems[24]; };   // per style layer: plane base, elements per sample (mult. of 4)
-void launch_fill_noise_all(const NoisePlanes& pl, int nlayers, int N, uint64_t seed, uint64_t first_sample, cudaStream_t st);
+void launch_fill_noise_all(const NoisePlanes& pl, int nlayers, int N, uint64_t seed, uint64_t first_sample, cudaStream_t st,
+                           const unsigned long long* first_dev = nullptr);
 
 struct DenseArgs {            // y[n][u] = act( sum_k x'[n][k] W[u][k] + b[u] ), W pre-scaled fp32
   const float* x; const float* W; const float* b; float* y;

@@ -69,6 +69,12 @@ void gsx_synth_destroy(gsx_synth* h);
 int gsx_synth_set_param(gsx_synth* h, const char* name, const float* data, const int64_t* shape, int ndim);
 /* Folds wscale/lr_mult, packs bf16 tensor-core operands, uploads.  Fails if a parameter is missing. */
 int gsx_synth_finalize(gsx_synth* h);
+/* CUDA-graph replays: with the counter enabled, the Philox latents / noise of gsx_synth_forward take their first global
+ * sample index from a device-resident counter (initialised to `start`, advanced by n at every forward) instead of the
+ * `first_sample` argument, so that a captured forward generates fresh samples on every replay.  (The reference draws
+ * fresh noise per call, networks_stylegan.py:300.) */
+int gsx_synth_device_counter(gsx_synth* h, int enable, uint64_t start);
+
 int gsx_synth_workspace_bytes(const gsx_synth* h, int n, size_t* bytes);
 int gsx_synth_num_layers(const gsx_synth* h);                       /* 2*(max_res_log2-1) */
 int gsx_synth_feature_shape(const gsx_synth* h, int level, int* c, int* hgt, int* wid);

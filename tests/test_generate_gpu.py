@@ -216,3 +216,28 @@ def test_ffhq_1024_size_independent_properties():
     p = G.forward(z, seed=1, psi=0.7, return_features=False)['img'].clone()
     q = G.forward(z, seed=2, psi=0.7, return_features=False)['img'].clone()      # different Philox noise
     assert torch.equal(p, q)
+
+
+def test_cuda_graph_replay_matches_plain_calls(gsx_lib, dtype):
+    """A captured generate step replayed k times gives the samples first_sample + k*n .. of the plain calls,
+    bit for bit (device-resident sample counter instead of the first_sample argument)."""
+    from gan_segmentation_b200.config import generator_config, decoder_config
+    from gan_segmentation_b200.networks import Generator, Decoder, GraphedGenerate
+    from gan_segmentation_b200.random_init import init_generator_params, init_decoder_params
+    gc, dc = generator_config(6), decoder_config(6)
+    G = Generator(gc, dtype=dtype); G.set_parameters(init_generator_params(gc, seed=0))
+    D = Decoder(dc, dtype=dtype); D.set_parameters(init_decoder_params(dc, seed=2))
+    n = 2
+    ref = []
+    for k in range(3):
+        out = G.forward(n=n, seed=11, first_sample=5 + k * n, return_u8=True, return_image=False, return_features=False)
+        m = D.forward(generator=G, return_logits=False)['mask']
+        ref.append((out['img_u8'].clone(), m.clone()))
+    gg = GraphedGenerate(G, D, n, seed=11, first_sample=5)
+    for k in range(3):
+        img, mask = gg.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(img, ref[k][0]) and torch.equal(mask, ref[k][1]), k
+    gg.close()
+    out = G.forward(n=n, seed=11, first_sample=5, return_u8=True, return_image=False, return_features=False)
+    assert torch.equal(out['img_u8'], ref[0][0])                 # plain calls use their argument again
