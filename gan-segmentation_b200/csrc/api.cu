@@ -492,6 +492,7 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SynthWs w = synth_layout(h, N, ws);
   if (w.total > ws_bytes) { set_error("workspace too small"); return -1; }
+  { int th, tw; h->hw(h->L, th, tw); pdl_set_for_work((double)N * th * tw); }
   const int Z = h->cfg.latent_size;
   set_error("");
   if (z_dev) {
@@ -830,6 +831,7 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
   const bool own = feats_f32_dev != nullptr;
   DecWs w = dec_layout(d, N, ws, true);
   if (w.total > ws_bytes) { set_error("decoder workspace too small"); return -1; }
+  pdl_set_for_work((double)N * d->levels[nf - 1].H * d->levels[nf - 1].W);
   std::vector<const act_t*> feat(nf);
   if (own) {
     for (int i = 0; i < nf; ++i) {

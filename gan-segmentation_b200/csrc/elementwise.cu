@@ -85,6 +85,8 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(kP1Warps * 32) pass1_kernel(const Pass1Args a, int strips, int rowblocks) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int plane = blockIdx.y;                 // cb * N + n
   const int cb = plane / a.N, n = plane - cb * a.N;
   const int HW = a.H * a.W;
@@ -192,11 +194,13 @@ void launch_pass1(const Pass1Args& a, cudaStream_t st) {
   int strips, rowblocks, blocks;
   pass1_shape(a.H, a.W, strips, rowblocks, blocks);
   dim3 grid(blocks, (a.C / 8) * a.N);
-  pass1_kernel<<<grid, kP1Warps * 32, 0, st>>>(a, strips, rowblocks);
+  launch_pdl(pass1_kernel, grid, dim3(kP1Warps * 32), 0, st, a, strips, rowblocks);
 }
 
 // ------------------------------------------------------------------------------------------ stats
 __global__ void __launch_bounds__(256) stats_kernel(const act_t* in, float* stats, int C, int N, int HW) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int plane = blockIdx.y;
   const int cb = plane / N, n = plane - cb * N;
   const act_t* src = in + (size_t)plane * HW * 8;
@@ -217,7 +221,7 @@ int stats_tiles(int HW) { return min(16, (HW + 255) / 256); }
 
 void launch_stats(const act_t* in, float* stats_partial, int C, int N, int HW, cudaStream_t st) {
   dim3 grid(stats_tiles(HW), (C / 8) * N);
-  stats_kernel<<<grid, 256, 0, st>>>(in, stats_partial, C, N, HW);
+  launch_pdl(stats_kernel, grid, dim3(256), 0, st, in, stats_partial, C, N, HW);
 }
 
 // ------------------------------------------------------------------------------------------ finalize
@@ -226,6 +230,8 @@ void launch_stats(const act_t* in, float* stats_partial, int C, int N, int HW, c
 __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ partial, int T, int N, int C, float inv_hw,
                                                        const float* __restrict__ styles, int style_stride, int style_off,
                                                        float* __restrict__ coef) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // (n, c)
   const int lane = threadIdx.x & 31;
   if (i >= N * C) return;
@@ -256,8 +262,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
 void launch_finalize(const float* partial, int T, int N, int C, int HW, const float* styles, int style_stride,
                      int style_off, float* coef, cudaStream_t st) {
   const int warps = N * C;
-  finalize_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(partial, T, N, C, 1.f / (float)HW, styles, style_stride,
-                                                           style_off, coef);
+  launch_pdl(finalize_kernel, dim3((warps * 32 + 255) / 256), dim3(256), 0, st, partial, T, N, C, 1.f / (float)HW, styles,
+             style_stride, style_off, coef);
 }
 
 // ------------------------------------------------------------------------------------------ apply
@@ -271,6 +277,8 @@ static constexpr int kApThreads = 256;
 static constexpr int kApPixPerThread = 8;
 
 __global__ void __launch_bounds__(kApThreads) apply_kernel(const ApplyArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int plane = blockIdx.y;
   const int cb = plane / a.N, n = plane - cb * a.N;
   const int HW = a.H * a.W;
@@ -306,6 +314,8 @@ __global__ void __launch_bounds__(kApThreads) apply_kernel(const ApplyArgs a) {
 
 // Last layer: all channels of a pixel are needed for ToRGB, so one thread owns a pixel and walks the channel blocks.
 __global__ void __launch_bounds__(256) apply_rgb_kernel(const ApplyArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];                 // ca[C], cc[C], wrgb[nc*C]
   float* s_ca = sm;
   float* s_cc = sm + a.C;
@@ -357,15 +367,17 @@ void launch_apply(const ApplyArgs& a, cudaStream_t st) {
   if (a.wrgb) {
     dim3 grid(min((HW + 255) / 256, 4096), a.N);
     const size_t smem = (size_t)(2 * a.C + a.nc * a.C) * sizeof(float);
-    apply_rgb_kernel<<<grid, 256, smem, st>>>(a);
+    launch_pdl(apply_rgb_kernel, grid, dim3(256), smem, st, a);
   } else {
     dim3 grid((HW + kApThreads * kApPixPerThread - 1) / (kApThreads * kApPixPerThread), (a.C / 8) * a.N);
-    apply_kernel<<<grid, kApThreads, 0, st>>>(a);
+    launch_pdl(apply_kernel, grid, dim3(kApThreads), 0, st, a);
   }
 }
 
 // ------------------------------------------------------------------------------------------ layout
 __global__ void blocked_to_nchw_kernel(const act_t* in, float* out, int C, int N, int HW) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int plane = blockIdx.y;
   const int cb = plane / N, n = plane - cb * N;
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
@@ -376,6 +388,8 @@ __global__ void blocked_to_nchw_kernel(const act_t* in, float* out, int C, int N
   }
 }
 __global__ void nchw_to_blocked_kernel(const float* in, act_t* out, int C, int N, int HW) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int plane = blockIdx.y;
   const int cb = plane / N, n = plane - cb * N;
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
@@ -420,6 +434,8 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
 }
 __global__ void fill_normal_kernel(float* out, size_t per_sample, int N, uint64_t seed, uint64_t first_sample,
                                    uint32_t stream_id, const unsigned long long* first_dev) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t quads = (per_sample + 3) / 4;
   const int n = blockIdx.y;
   if (first_dev) first_sample = *first_dev;         // CUDA-graph replays: the running sample index lives in HBM
@@ -448,6 +464,8 @@ void launch_fill_noise(float* out, size_t plane_elems, int N, uint64_t seed, uin
 struct NoiseIndex { size_t qstart[25]; int nlayers; };
 __global__ void __launch_bounds__(256) fill_noise_all_kernel(NoisePlanes pl, NoiseIndex ix, uint64_t seed, uint64_t first_sample,
                                                              const unsigned long long* first_dev) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.y;
   if (first_dev) first_sample = *first_dev;
   const uint64_t gs = first_sample + (uint64_t)n;
@@ -482,7 +500,7 @@ void launch_fill_noise_all(const NoisePlanes& pl, int nlayers, int N, uint64_t s
   // ~4 quads per thread; at least one block per sample
   const size_t blocks = (acc + 1023) / 1024;
   dim3 grid((unsigned)(blocks < 1 ? 1 : (blocks > 4096 ? 4096 : blocks)), N);
-  fill_noise_all_kernel<<<grid, 256, 0, st>>>(pl, ix, seed, first_sample, first_dev);
+  launch_pdl(fill_noise_all_kernel, grid, dim3(256), 0, st, pl, ix, seed, first_sample, first_dev);
 }
 
 void launch_fill_latents(float* z, int N, int Z, uint64_t seed, uint64_t first_sample, cudaStream_t st,
@@ -490,7 +508,7 @@ void launch_fill_latents(float* z, int N, int Z, uint64_t seed, uint64_t first_s
   dim3 grid(1, N);
   fill_normal_kernel<<<grid, 128, 0, st>>>(z, (size_t)Z, N, seed, first_sample, 0xFFFFu, first_dev);
 }
-__global__ void advance_counter_kernel(unsigned long long* counter, unsigned long long by) { *counter += by; }
+__global__ void advance_counter_kernel(unsigned long long* counter, unsigned long long by) { pdl_launch_dependents(); pdl_wait(); *counter += by; }
 void launch_advance_counter(unsigned long long* counter, unsigned long long by, cudaStream_t st) {
   advance_counter_kernel<<<1, 1, 0, st>>>(counter, by);
 }
@@ -511,6 +529,8 @@ static constexpr int kBorderThreads = 128;
 __global__ void __launch_bounds__(kBorderThreads) deconv_border_kernel(const act_t* __restrict__ x, const float* __restrict__ wt,
                                                                        float* __restrict__ e_rows, float* __restrict__ e_cols,
                                                                        int N, int Cin, int Cout, int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float ring[];                      // [kBorderSeg + 2][Cout]
   const int side = blockIdx.y, n = blockIdx.z;         // 0 top, 1 bottom, 2 left, 3 right
   const int Ho = 2 * H, Wo = 2 * W;
@@ -573,7 +593,7 @@ void launch_deconv_border(const act_t* x, const float* wt, float* e_rows, float*
                           int W, cudaStream_t st) {
   const int len = 2 * (H > W ? H : W);
   dim3 grid((len + kBorderSeg - 1) / kBorderSeg, 4, N);
-  deconv_border_kernel<<<grid, kBorderThreads, (kBorderSeg + 2) * Cout * sizeof(float), st>>>(x, wt, e_rows, e_cols, N, Cin,
+  launch_pdl(deconv_border_kernel, grid, dim3(kBorderThreads), (kBorderSeg + 2) * Cout * sizeof(float), st, x, wt, e_rows, e_cols, N, Cin,
                                                                                              Cout, H, W);
 }
 

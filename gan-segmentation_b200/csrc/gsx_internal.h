@@ -246,6 +246,22 @@ struct DenseArgs {            // y[n][u] = act( sum_k x'[n][k] W[u][k] + b[u] ),
 };
 void launch_dense(const DenseArgs& a, cudaStream_t st);
 
+// Launch with programmatic stream serialization (see ptx.cuh) when the current forward pass is small enough for it to
+// pay (plan.cpp); GSX_NO_PDL=1: never, GSX_PDL=1: always.
+bool pdl_enabled();
+void pdl_set_for_work(double top_level_pixels);   // called at the top of the forward passes
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 void set_error(const std::string& msg);
 bool cuda_ok(cudaError_t e, const char* what);
 

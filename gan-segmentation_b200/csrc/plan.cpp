@@ -20,6 +20,16 @@ bool cuda_ok(cudaError_t e, const char* what) {
   return false;
 }
 
+// Programmatic dependent launch pays when the kernels are short (batch 1 at 256^2: 1.19 -> 1.07 ms per step) and costs
+// ~2 % at the large-batch operating point (the early-resident conv CTAs pin the shared-memory carve-out at its maximum
+// while the HBM-bound passes before them drain), so the forward passes switch it per call on the amount of work.
+static thread_local bool g_pdl_call = false;
+void pdl_set_for_work(double top_level_pixels) {
+  static const int mode = getenv("GSX_NO_PDL") ? 0 : (getenv("GSX_PDL") ? 2 : 1);     // off / by size / always
+  g_pdl_call = mode == 2 || (mode == 1 && top_level_pixels <= 2.0 * 1024 * 1024);
+}
+bool pdl_enabled() { return g_pdl_call; }
+
 static const int kSmemLimit = 227 * 1024;
 static const int kHeader = kConvHeaderBytes;
 static const int kSlack = 8192;     // garbage-tolerant over-read of the last (partial) MMA tile

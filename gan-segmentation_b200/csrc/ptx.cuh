@@ -58,6 +58,15 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the step is launched with cudaLaunchAttributeProgrammaticStreamSerialization (gsx_internal.h,
+// launch_pdl): its CTAs may start -- barrier init, TMEM allocation, resident-weight loads, coefficient staging --
+// while the previous kernel of the stream is still draining, and must execute pdl_wait() before the first access to
+// memory an earlier kernel wrote (or still reads).  pdl_launch_dependents() at the top lets the next kernel do the same.
+// Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");

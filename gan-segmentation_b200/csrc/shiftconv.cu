@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
   uint8_t* a_base = smem + g.a_off;
   uint8_t* b_base = a_base + (size_t)g.stages * g.a_stage_stride;
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = g.tiles_x * g.tiles_y * g.tiles_n * g.n_ntiles * (g.phase_grid ? 4 : 1);
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         bulk_load(b_base, p.wpack, (uint32_t)(g.n_k * g.b_stage_bytes), &hdr->bres_full);
       }
       const uint32_t stage_bytes = (uint32_t)(g.a_stage_bytes + (g.b_resident ? 0 : g.b_stage_bytes));
+      pdl_wait();                                   // activations / aux tiles come from earlier kernels of the stream
       int it = 0, tlp = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tlp) {
         const TileCoord tc = decode_tile(g, t);
@@ -380,6 +382,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     const int n_units = g.n_mtiles;
     const int slot_floats = 2 * g.cout_tile;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    pdl_wait();                                     // before the first global read / write of this role
 
     int tl = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
@@ -705,7 +708,7 @@ static void launch_g(const ConvParams& p, int grid, cudaStream_t st) {
     cudaFuncSetAttribute(shiftconv_kernel<G, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured[dev] = true;
   }
-  shiftconv_kernel<G, GEN><<<grid, 64 + 128 * G, p.g.smem_bytes, st>>>(p);
+  launch_pdl(shiftconv_kernel<G, GEN>, dim3(grid), dim3(64 + 128 * G), (size_t)p.g.smem_bytes, st, p);
 }
 
 void launch_shiftconv(const ConvParams& p, cudaStream_t st) {

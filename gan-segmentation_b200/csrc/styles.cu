@@ -5,6 +5,7 @@
 // 4.2 + 10.4 MFLOP per sample: latency/bandwidth-bound on the fp32 weights, so CUDA cores, one warp per
 // output unit, weights in registers, the (transformed) activations of up to 32 samples in shared memory.
 #include "gsx_internal.h"
+#include "ptx.cuh"
 
 namespace gsx {
 
@@ -13,6 +14,7 @@ static constexpr int kDnSamples = 32;        // samples staged per pass
 static constexpr int kDnMaxK = 512;
 
 __global__ void __launch_bounds__(kDnThreads) dense_kernel(const DenseArgs a) {
+  pdl_launch_dependents();
   extern __shared__ float xs[];              // [kDnSamples][K]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u = blockIdx.x * 8 + warp;
@@ -21,6 +23,7 @@ __global__ void __launch_bounds__(kDnThreads) dense_kernel(const DenseArgs a) {
 #pragma unroll
   for (int j = 0; j < kDnMaxK / 32; ++j) wr[j] = (u < a.U && lane + 32 * j < K) ? a.W[(size_t)u * K + lane + 32 * j] : 0.f;
   const float bu = (u < a.U && a.b) ? a.b[u] : 0.f;
+  pdl_wait();                                  // x (and a per-call psi) come from earlier work in the stream
   float psi = 1.f;
   if (a.psi) psi = a.psi[a.unit_layer[blockIdx.x * 8]];
 
@@ -73,7 +76,7 @@ void launch_dense(const DenseArgs& a, cudaStream_t st) {
     cudaFuncSetAttribute(dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     configured[dev] = true;
   }
-  dense_kernel<<<(a.U + 7) / 8, kDnThreads, smem, st>>>(a);
+  launch_pdl(dense_kernel, dim3((a.U + 7) / 8), dim3(kDnThreads), smem, st, a);
 }
 
 }  // namespace gsx
