@@ -248,18 +248,24 @@ void launch_dense(const DenseArgs& a, cudaStream_t st);
 
 // Launch with programmatic stream serialization (see ptx.cuh) when the current forward pass is small enough for it to
 // pay (plan.cpp); GSX_NO_PDL=1: never, GSX_PDL=1: always.
-bool pdl_enabled();
+// kind: 1 = shiftconv (one persistent CTA per SM holding most of the shared memory), 0 = everything else.
+bool pdl_enabled(int kind);
 void pdl_set_for_work(double top_level_pixels);   // called at the top of the forward passes
 template <class... KArgs, class... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+inline cudaError_t launch_pdl_kind(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl_enabled(kind) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  return launch_pdl_kind(0, kernel, grid, block, smem, st, args...);
 }
 
 void set_error(const std::string& msg);

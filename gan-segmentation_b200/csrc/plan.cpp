@@ -20,15 +20,23 @@ bool cuda_ok(cudaError_t e, const char* what) {
   return false;
 }
 
-// Programmatic dependent launch pays when the kernels are short (batch 1 at 256^2: 1.19 -> 1.07 ms per step) and costs
-// ~2 % at the large-batch operating point (the early-resident conv CTAs pin the shared-memory carve-out at its maximum
-// while the HBM-bound passes before them drain), so the forward passes switch it per call on the amount of work.
-static thread_local bool g_pdl_call = false;
+// Programmatic dependent launch pays when the kernels are short (batch 1 at 256^2: 1.19 -> 1.07 ms per step).  At the
+// large-batch operating point it costs ~2 % when applied everywhere: a conv CTA that becomes resident early pins the
+// shared-memory carve-out at its maximum while the HBM-bound pass before it drains.  So: small forward passes use it
+// for every kernel; large ones only for a shift-GEMM conv that directly follows another one (the decoder is a chain
+// of them) -- those cannot co-reside anyway, the successor's CTA takes over an SM when the predecessor's CTA exits
+// and does its prologue (barriers, TMEM, resident weights) under the predecessor's tail.
+static thread_local bool g_pdl_small = false, g_pdl_chain = false, g_prev_conv = false;
 void pdl_set_for_work(double top_level_pixels) {
   static const int mode = getenv("GSX_NO_PDL") ? 0 : (getenv("GSX_PDL") ? 2 : 1);     // off / by size / always
-  g_pdl_call = mode == 2 || (mode == 1 && top_level_pixels <= 2.0 * 1024 * 1024);
+  g_pdl_small = mode == 2 || (mode == 1 && top_level_pixels <= 2.0 * 1024 * 1024);
+  g_pdl_chain = mode != 0 && !getenv("GSX_NO_PDL_CHAIN");
 }
-bool pdl_enabled() { return g_pdl_call; }
+bool pdl_enabled(int kind) {
+  const bool on = g_pdl_small || (g_pdl_chain && kind == 1 && g_prev_conv);
+  g_prev_conv = (kind == 1);
+  return on;
+}
 
 static const int kSmemLimit = 227 * 1024;
 static const int kHeader = kConvHeaderBytes;

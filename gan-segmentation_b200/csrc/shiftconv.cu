@@ -708,7 +708,7 @@ static void launch_g(const ConvParams& p, int grid, cudaStream_t st) {
     cudaFuncSetAttribute(shiftconv_kernel<G, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured[dev] = true;
   }
-  launch_pdl(shiftconv_kernel<G, GEN>, dim3(grid), dim3(64 + 128 * G), (size_t)p.g.smem_bytes, st, p);
+  launch_pdl_kind(1, shiftconv_kernel<G, GEN>, dim3(grid), dim3(64 + 128 * G), (size_t)p.g.smem_bytes, st, p);
 }
 
 void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
