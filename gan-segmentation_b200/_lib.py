@@ -10,6 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # One shared library per 16-bit storage / tensor-core operand type (csrc/Makefile):
 #   fp16 -> libgsx.so (default: meets the image tolerance), bf16 -> libgsx_bf16.so (the north star's type)
 LIB_PATHS = {'fp16': os.path.join(_HERE, 'libgsx.so'), 'bf16': os.path.join(_HERE, 'libgsx_bf16.so')}
+if os.environ.get('GSX_LIB'):                      # development hook: an alternative build of the fp16 library
+    LIB_PATHS['fp16'] = os.environ['GSX_LIB']
 LIB_PATH = LIB_PATHS['fp16']
 DEFAULT_DTYPE = os.environ.get('GSX_DTYPE', 'fp16')
 CSRC = os.path.join(_HERE, 'csrc')

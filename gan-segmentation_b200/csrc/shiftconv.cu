@@ -28,6 +28,11 @@
 
 #include <cstdlib>
 
+// tuning builds only: -DGSX_EPI_LITE=1 compiles every epilogue body out (code-size experiments)
+#ifndef GSX_EPI_LITE
+#define GSX_EPI_LITE 0
+#endif
+
 namespace gsx {
 
 static constexpr int kMaxStages = 8;
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         return row < g.mt_stride && nb < g.NB && yl < g.TH && xl < g.TW && n < g.N && y < g.H && x < g.W;
       };
 
-      if (g.dbg & 1) {
+      if (GSX_EPI_LITE || (g.dbg & 1)) {
       } else if ((e.flags & EPI_ARGMAX) && g.up_cols) {
         // s2d final conv: the 4 output phases of a block are column groups of cout_tile (4, 8 or 16) classes
         for (int u = egrp; u < n_units; u += G) {
