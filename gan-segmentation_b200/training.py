@@ -80,3 +80,12 @@ class FlatAdam:
         L.check(lib.gsx_adam_step(L.ptr(self.w), L.ptr(self.g), L.ptr(self.m), L.ptr(self.v), self.count, self.t, self.lr,
                                   self.beta1, self.beta2, self.eps, self.wd, 1.0 / float(global_batch), _stream()),
                 'gsx_adam_step', self.dtype)
+
+
+def dgrad_weights(weight):
+    """Weights that turn the forward 3x3 / 1x1 conv kernel into its own data gradient:
+    ``dX = conv(dY, dgrad_weights(W))`` for ``Y = conv(X, W)`` (stride 1, 'same' padding) -- channels swapped,
+    taps flipped.  The decoder's dgrad therefore runs on the existing tcgen05 shift-GEMM kernel; only the weight
+    gradient and the BatchNorm backward need new kernels (not built yet).  weight: [Cout,Cin,k,k] numpy."""
+    w = np.asarray(weight, np.float32)
+    return np.ascontiguousarray(np.transpose(w, (1, 0, 2, 3))[:, :, ::-1, ::-1])

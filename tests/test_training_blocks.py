@@ -87,3 +87,22 @@ def test_flat_bucket_allreduce_gloo_two_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert np.array_equal(g, np.arange(17, dtype=np.float32) * 3)
+
+
+@pytest.mark.gpu
+def test_conv_dgrad_runs_on_the_forward_kernel(gsx_lib):
+    """dX of a 3x3 / 1x1 'same' conv == the forward shift-GEMM kernel applied to dY with transposed, flipped weights
+    (training.dgrad_weights), checked against autograd."""
+    from gan_segmentation_b200 import _lib as L, ops
+    from gan_segmentation_b200.training import dgrad_weights
+    g = torch.Generator().manual_seed(3)
+    for (mode, k, n, cin, cout, h, w) in [(L.CONV3, 3, 2, 32, 16, 40, 56), (L.CONV3, 3, 1, 64, 64, 16, 16), (L.CONV1, 1, 2, 64, 16, 24, 24)]:
+        x = torch.randn((n, cin, h, w), generator=g).cuda().requires_grad_(True)
+        wt = (torch.randn((cout, cin, k, k), generator=g) / np.sqrt(cin * k * k)).half().float()
+        dy = torch.randn((n, cout, h, w), generator=g).half().float().cuda()
+        y = F.conv2d(x, wt.cuda(), None, 1, k // 2)
+        y.backward(dy)
+        r = ops.conv(mode, dy, dgrad_weights(wt.numpy()))
+        ref = x.grad
+        err = (r['out'] - ref).abs().max().item()
+        assert err <= 2e-3 * ref.abs().max().item() + 1e-3, (mode, err)
