@@ -80,7 +80,143 @@ __global__ void adam_step_kernel(float* __restrict__ w, const float* __restrict_
 
 }  // namespace gsx
 
+namespace gsx {
+
+// ----------------------------------------------------------------------------------------------------------------
+// Weight gradient of a 'same' 3x3 / 1x1 convolution on blocked 16-bit tensors (first version: CUDA cores, fp32
+// accumulation, deterministic).   dW[co][ci][ky][kx] = sum_{n,y,x} dY[n,co,y,x] * X[n,ci,y+ky-P,x+kx-P],  db[co] = sum dY.
+// grid (pixel tiles, N, (Cout/8)*(Cin/8)); a block owns one 8x8 (co,ci) block over a 16x32 pixel tile: thread =
+// (co,ci) pair x 4 row phases, partial sums per (tile, sample) go to HBM and a second kernel adds them in fixed order.
+// ----------------------------------------------------------------------------------------------------------------
+static constexpr int kWgTY = 16, kWgTX = 32, kWgThreads = 256;
+
+__device__ __forceinline__ void wg_unpack8(uint4 v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#if GSX_FP16
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+#else
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+#endif
+    f[2 * k] = t.x; f[2 * k + 1] = t.y;
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kWgThreads) conv_wgrad_kernel(const act_t* __restrict__ x, const act_t* __restrict__ dy,
+                                                               float* __restrict__ partial, int N, int H, int W,
+                                                               int CinB, int CoutB, int tiles_x) {
+  constexpr int P = K / 2, SY = kWgTY + 2 * P, SX = kWgTX + 2 * P;
+  __shared__ float sx[SY][SX][8];
+  __shared__ float sdy[kWgTY][kWgTX][8];
+  __shared__ float red[4][64][10];
+  const int tile = blockIdx.x, n = blockIdx.y;
+  const int cob = blockIdx.z / CinB, cib = blockIdx.z - cob * CinB;
+  const int ty0 = (tile / tiles_x) * kWgTY, tx0 = (tile % tiles_x) * kWgTX;
+  const size_t plane = (size_t)H * W;
+  const act_t* xb = x + ((size_t)cib * N + n) * plane * 8;
+  const act_t* db = dy + ((size_t)cob * N + n) * plane * 8;
+  for (int i = threadIdx.x; i < SY * SX; i += kWgThreads) {
+    const int r = i / SX, c = i - r * SX;
+    const int yy = ty0 + r - P, xx = tx0 + c - P;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) wg_unpack8(__ldg(reinterpret_cast<const uint4*>(xb + ((size_t)yy * W + xx) * 8)), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sx[r][c][k] = f[k];
+  }
+  for (int i = threadIdx.x; i < kWgTY * kWgTX; i += kWgThreads) {
+    const int r = i / kWgTX, c = i - r * kWgTX;
+    const int yy = ty0 + r, xx = tx0 + c;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (yy < H && xx < W) wg_unpack8(__ldg(reinterpret_cast<const uint4*>(db + ((size_t)yy * W + xx) * 8)), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sdy[r][c][k] = f[k];
+  }
+  __syncthreads();
+  const int pair = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  const int co = pair >> 3, ci = pair & 7;
+  float acc[K * K], accb = 0.f;
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) acc[t] = 0.f;
+  for (int r = sub; r < kWgTY; r += 4) {
+    for (int c = 0; c < kWgTX; ++c) {
+      const float d = sdy[r][c][co];
+      accb += d;
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) acc[ky * K + kx] = fmaf(d, sx[r + ky][c + kx][ci], acc[ky * K + kx]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) red[sub][pair][t] = acc[t];
+  red[sub][pair][9] = accb;
+  __syncthreads();
+  // fixed-order sum of the 4 row phases; entry 9 = bias partial (meaningful for ci == 0 of the first input block)
+  for (int i = threadIdx.x; i < 64 * 10; i += kWgThreads) {
+    const int pr = i / 10, t = i - pr * 10;
+    if (t < K * K || t == 9) {
+      const float v = red[0][pr][t] + red[1][pr][t] + red[2][pr][t] + red[3][pr][t];
+      const size_t E = (size_t)CoutB * CinB * 640;
+      partial[((size_t)tile * N + n) * E + ((size_t)blockIdx.z * 64 + pr) * 10 + t] = v;
+    }
+  }
+}
+
+template <int K>
+__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ dbias,
+                                         int P, int Cin, int Cout) {
+  const int CinB = Cin / 8, CoutB = Cout / 8;
+  const size_t E = (size_t)CoutB * CinB * 640;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((size_t)e >= E) return;
+  const int t = e % 10, pr = (e / 10) % 64, blk = e / 640;
+  const int cob = blk / CinB, cib = blk - cob * CinB;
+  const int co = cob * 8 + (pr >> 3), ci = cib * 8 + (pr & 7);
+  const bool is_w = t < K * K, is_b = (t == 9 && cib == 0 && (pr & 7) == 0);
+  if (!is_w && !is_b) return;
+  float s = 0.f;
+  for (int p = 0; p < P; ++p) s += partial[(size_t)p * E + e];          // fixed order: bit-reproducible
+  if (is_w) dw[((size_t)co * Cin + ci) * K * K + t] = s;
+  else if (dbias) dbias[co] = s;
+}
+
+}  // namespace gsx
+
 using namespace gsx;
+
+extern "C" int gsx_op_conv_wgrad(int k, int n, int h, int w, int cin, int cout, const float* x_dev, const float* dy_dev,
+                                 float* dw_dev, float* db_dev, gsx_stream stream) {
+  if ((k != 1 && k != 3) || cin % 8 || cout % 8 || n <= 0 || !x_dev || !dy_dev || !dw_dev) { set_error("bad argument"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int tiles_x = (w + kWgTX - 1) / kWgTX, tiles_y = (h + kWgTY - 1) / kWgTY, tiles = tiles_x * tiles_y;
+  const int CinB = cin / 8, CoutB = cout / 8;
+  const size_t E = (size_t)CoutB * CinB * 640, P = (size_t)tiles * n;
+  act_t *xb = nullptr, *dyb = nullptr;
+  float* partial = nullptr;
+  bool ok = cuda_ok(cudaMalloc(&xb, (size_t)n * cin * h * w * sizeof(act_t)), "wgrad x") &&
+            cuda_ok(cudaMalloc(&dyb, (size_t)n * cout * h * w * sizeof(act_t)), "wgrad dy") &&
+            cuda_ok(cudaMalloc(&partial, P * E * sizeof(float)), "wgrad partials");
+  if (ok) {
+    cudaMemsetAsync(partial, 0, P * E * sizeof(float), st);
+    launch_nchw_to_blocked(x_dev, xb, cin, n, h * w, st);
+    launch_nchw_to_blocked(dy_dev, dyb, cout, n, h * w, st);
+    dim3 grid(tiles, n, CoutB * CinB);
+    const int rb = (int)((E + 255) / 256);
+    if (k == 3) {
+      conv_wgrad_kernel<3><<<grid, kWgThreads, 0, st>>>(xb, dyb, partial, n, h, w, CinB, CoutB, tiles_x);
+      conv_wgrad_reduce_kernel<3><<<rb, 256, 0, st>>>(partial, dw_dev, db_dev, (int)P, cin, cout);
+    } else {
+      conv_wgrad_kernel<1><<<grid, kWgThreads, 0, st>>>(xb, dyb, partial, n, h, w, CinB, CoutB, tiles_x);
+      conv_wgrad_reduce_kernel<1><<<rb, 256, 0, st>>>(partial, dw_dev, db_dev, (int)P, cin, cout);
+    }
+    g_launches += 4;
+    ok = cuda_ok(cudaStreamSynchronize(st), "conv_wgrad");
+  }
+  cudaFree(xb); cudaFree(dyb); cudaFree(partial);
+  return ok ? 0 : -2;
+}
 
 extern "C" int gsx_softmax_ce(const float* logits_dev, const int* labels_dev, int n, int num_classes, int h, int w,
                               float* loss_dev, float* dlogits_dev, float* scratch_dev, size_t scratch_floats,

@@ -89,3 +89,18 @@ def dgrad_weights(weight):
     gradient and the BatchNorm backward need new kernels (not built yet).  weight: [Cout,Cin,k,k] numpy."""
     w = np.asarray(weight, np.float32)
     return np.ascontiguousarray(np.transpose(w, (1, 0, 2, 3))[:, :, ::-1, ::-1])
+
+
+def conv_wgrad(x, dy, k, dtype=None):
+    """Weight and bias gradient of a stride-1 'same' k x k conv (k = 1 or 3): x [N,Cin,H,W], dy [N,Cout,H,W] fp32 cuda
+    -> (dW [Cout,Cin,k,k], db [Cout]).  First (CUDA-core, deterministic) version of the decoder's wgrad."""
+    lib = L.lib(dtype)
+    n, cin, h, w = x.shape
+    cout = dy.shape[1]
+    x = x.contiguous().float()
+    dy = dy.contiguous().float()
+    dw = torch.empty((cout, cin, k, k), dtype=torch.float32, device=x.device)
+    db = torch.empty((cout,), dtype=torch.float32, device=x.device)
+    L.check(lib.gsx_op_conv_wgrad(k, n, h, w, cin, cout, L.ptr(x), L.ptr(dy), L.ptr(dw), L.ptr(db), _stream()),
+            'gsx_op_conv_wgrad', dtype)
+    return dw, db

@@ -123,6 +123,11 @@ int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z_host, cons
  *   if dlogits_dev != NULL, d(sum_n loss_n)/dlogits.  scratch_dev: n*256 floats.
  * gsx_adam_step: MXNet Adam on one flat fp32 bucket after the single gradient all-reduce (seg_solver.py:56,421):
  *   lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t), g' = g*rescale_grad + wd*w. ---- */
+/* Weight / bias gradient of a stride-1 'same' k x k conv (k = 1 or 3), fp32 NCHW in (converted to the blocked 16-bit
+ * layout internally), dw [cout][cin][k][k] and db [cout] (may be NULL) out; deterministic.  Tuning / test hook of the
+ * first, CUDA-core version of the decoder's weight gradient (seg_solver.py:411-412 err.backward()). */
+int gsx_op_conv_wgrad(int k, int n, int h, int w, int cin, int cout, const float* x_dev, const float* dy_dev,
+                      float* dw_dev, float* db_dev, gsx_stream stream);
 int gsx_softmax_ce(const float* logits_dev, const int* labels_dev, int n, int num_classes, int h, int w,
                    float* loss_dev, float* dlogits_dev, float* scratch_dev, size_t scratch_floats, gsx_stream stream);
 int gsx_adam_step(float* w_dev, const float* g_dev, float* m_dev, float* v_dev, size_t count, int t, float lr, float beta1,

@@ -106,3 +106,23 @@ def test_conv_dgrad_runs_on_the_forward_kernel(gsx_lib):
         ref = x.grad
         err = (r['out'] - ref).abs().max().item()
         assert err <= 2e-3 * ref.abs().max().item() + 1e-3, (mode, err)
+
+
+@pytest.mark.gpu
+def test_conv_wgrad_matches_autograd(gsx_lib):
+    """dW / db of the decoder's convs (3x3 and the 1x1 shortcut) against autograd on the same fp16-rounded operands;
+    bit-reproducible (per-tile partials summed in a fixed order)."""
+    from gan_segmentation_b200.training import conv_wgrad
+    g = torch.Generator().manual_seed(4)
+    for (k, n, cin, cout, h, w) in [(3, 2, 16, 16, 40, 72), (3, 1, 64, 32, 16, 16), (1, 2, 64, 16, 24, 40), (3, 3, 8, 8, 5, 7)]:
+        x = torch.randn((n, cin, h, w), generator=g).half().float().cuda()
+        dy = torch.randn((n, cout, h, w), generator=g).half().float().cuda()
+        wt = torch.zeros((cout, cin, k, k), device='cuda', requires_grad=True)
+        b = torch.zeros((cout,), device='cuda', requires_grad=True)
+        F.conv2d(x, wt, b, 1, k // 2).backward(dy)
+        dw, db = conv_wgrad(x, dy, k)
+        scale = wt.grad.abs().max().item()
+        assert (dw - wt.grad).abs().max().item() <= 2e-4 * scale + 1e-3, (k, n, cin, cout, h, w)
+        assert torch.allclose(db, b.grad, rtol=1e-4, atol=1e-2)
+        dw2, db2 = conv_wgrad(x, dy, k)
+        assert torch.equal(dw, dw2) and torch.equal(db, db2)
