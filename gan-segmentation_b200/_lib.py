@@ -80,6 +80,10 @@ _SIGS = {
     'gsx_generate_host': (_i, [_vp, _vp, _i, _fp, _fp, _u64, _u64, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _i]),
     'gsx_synth_device_counter': (_i, [_vp, _i, C.c_uint64]),
     'gsx_op_conv_wgrad': (_i, [_i, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _vp]),
+    'gsx_op_upsample2': (_i, [_fp, _fp, _i, _i, _i, _i, _vp]),
+    'gsx_op_sumpool2': (_i, [_fp, _fp, _i, _i, _i, _i, _vp]),
+    'gsx_op_bn_lrelu_fwd': (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
+    'gsx_op_bn_lrelu_bwd': (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
     'gsx_softmax_ce': (_i, [_fp, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _sz, _vp]),
     'gsx_adam_step': (_i, [_fp, _fp, _fp, _fp, _sz, _i, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
     'gsx_profile_enable': (_i, [_i]),

@@ -182,6 +182,107 @@ __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ partial, floa
   else if (dbias) dbias[co] = s;
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// Train-mode BatchNorm + LeakyReLU(0.2) (+ Dropout(0.5) mask) forward / backward and the nearest-x2 upsample pair, on
+// fp32 NCHW tensors (first version of the decoder training path: the single-operator hooks work on fp32 NCHW).
+// Per-channel reductions: per-block double partials, summed in a fixed order -> bit-reproducible.
+// ----------------------------------------------------------------------------------------------------------------
+static constexpr int kRedThreads = 256, kRedBlocks = 32;
+
+struct BnArgs {
+  const float* z; const float* dy; const float* drop; const float* gamma; const float* beta;
+  const float* mean; const float* rstd;
+  int N, C, HW;
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(kRedThreads) chan_reduce_kernel(BnArgs a, double* __restrict__ partial) {
+  const int c = blockIdx.y;
+  const size_t total = (size_t)a.N * a.HW;
+  double s0 = 0.0, s1 = 0.0;
+  float mu = 0.f, rs = 0.f, ga = 0.f, be = 0.f;
+  if (BWD) { mu = a.mean[c]; rs = a.rstd[c]; ga = a.gamma[c]; be = a.beta[c]; }
+  for (size_t i = (size_t)blockIdx.x * kRedThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kRedThreads) {
+    const size_t n = i / a.HW, p = i - n * a.HW;
+    const size_t off = (n * a.C + c) * a.HW + p;
+    const float z = a.z[off];
+    if (!BWD) { s0 += z; s1 += (double)z * z; }
+    else {
+      const float xh = (z - mu) * rs;
+      float g = a.dy[off] * ((ga * xh + be) > 0.f ? 1.f : 0.2f);
+      if (a.drop) g *= 2.f * a.drop[off];
+      s0 += g; s1 += (double)g * xh;
+    }
+  }
+  __shared__ double r0[kRedThreads], r1[kRedThreads];
+  r0[threadIdx.x] = s0; r1[threadIdx.x] = s1;
+  __syncthreads();
+  for (int o = kRedThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { r0[threadIdx.x] += r0[threadIdx.x + o]; r1[threadIdx.x] += r1[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { partial[((size_t)c * gridDim.x + blockIdx.x) * 2] = r0[0]; partial[((size_t)c * gridDim.x + blockIdx.x) * 2 + 1] = r1[0]; }
+}
+
+// STATS: out0 = mean, out1 = biased variance, out2 = rstd (eps 1e-5).  BWD: out0 = dbeta, out1 = dgamma.
+template <bool BWD>
+__global__ void chan_finalize_kernel(const double* __restrict__ partial, int blocks, int C, double count, float* out0, float* out1,
+                                     float* out2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int b = 0; b < blocks; ++b) { s0 += partial[((size_t)c * blocks + b) * 2]; s1 += partial[((size_t)c * blocks + b) * 2 + 1]; }
+  if (BWD) { out0[c] = (float)s0; out1[c] = (float)s1; }
+  else {
+    const double m = s0 / count, v = fmax(s1 / count - m * m, 0.0);
+    out0[c] = (float)m; out1[c] = (float)v; out2[c] = (float)(1.0 / sqrt(v + 1e-5));
+  }
+}
+
+__global__ void bn_lrelu_fwd_kernel(BnArgs a, float* __restrict__ y) {
+  const size_t total = (size_t)a.N * a.C * a.HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / a.HW) % a.C);
+    const float pre = a.gamma[c] * ((a.z[i] - a.mean[c]) * a.rstd[c]) + a.beta[c];
+    float v = pre > 0.f ? pre : 0.2f * pre;
+    if (a.drop) v *= 2.f * a.drop[i];
+    y[i] = v;
+  }
+}
+
+__global__ void bn_lrelu_bwd_kernel(BnArgs a, const float* __restrict__ dbeta, const float* __restrict__ dgamma, float* __restrict__ dz) {
+  const size_t total = (size_t)a.N * a.C * a.HW;
+  const float m = (float)a.N * (float)a.HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / a.HW) % a.C);
+    const float xh = (a.z[i] - a.mean[c]) * a.rstd[c];
+    float g = a.dy[i] * ((a.gamma[c] * xh + a.beta[c]) > 0.f ? 1.f : 0.2f);
+    if (a.drop) g *= 2.f * a.drop[i];
+    dz[i] = a.gamma[c] * a.rstd[c] / m * (m * g - dbeta[c] - xh * dgamma[c]);
+  }
+}
+
+__global__ void upsample2_kernel(const float* __restrict__ x, float* __restrict__ y, size_t planes, int H, int W) {
+  const size_t total = planes * (size_t)(2 * H) * (2 * W);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % (2 * W)), Y = (int)((i / (2 * W)) % (2 * H));
+    const size_t pl = i / ((size_t)4 * H * W);
+    y[i] = x[(pl * H + (Y >> 1)) * W + (X >> 1)];
+  }
+}
+__global__ void sumpool2_kernel(const float* __restrict__ dy, float* __restrict__ dx, size_t planes, int H, int W) {
+  const size_t total = planes * (size_t)H * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W), Y = (int)((i / W) % H);
+    const size_t pl = i / ((size_t)H * W);
+    const float* r0 = dy + (pl * 2 * H + 2 * Y) * 2 * W + 2 * X;
+    dx[i] = (r0[0] + r0[1]) + (r0[2 * W] + r0[2 * W + 1]);
+  }
+}
+
+static int ew_blocks(size_t total) { return (int)std::min<size_t>(148 * 8, (total + 255) / 256); }
+
 }  // namespace gsx
 
 using namespace gsx;
@@ -215,6 +316,54 @@ extern "C" int gsx_op_conv_wgrad(int k, int n, int h, int w, int cin, int cout, 
     ok = cuda_ok(cudaStreamSynchronize(st), "conv_wgrad");
   }
   cudaFree(xb); cudaFree(dyb); cudaFree(partial);
+  return ok ? 0 : -2;
+}
+
+extern "C" int gsx_op_upsample2(const float* x_dev, float* y_dev, int n, int c, int h, int w, gsx_stream stream) {
+  if (!x_dev || !y_dev) { set_error("bad argument"); return -1; }
+  const size_t total = (size_t)n * c * 4 * h * w;
+  upsample2_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, y_dev, (size_t)n * c, h, w);
+  g_launches++;
+  return cuda_ok(cudaGetLastError(), "upsample2") ? 0 : -2;
+}
+extern "C" int gsx_op_sumpool2(const float* dy_dev, float* dx_dev, int n, int c, int h, int w, gsx_stream stream) {
+  if (!dy_dev || !dx_dev) { set_error("bad argument"); return -1; }
+  const size_t total = (size_t)n * c * h * w;
+  sumpool2_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy_dev, dx_dev, (size_t)n * c, h, w);
+  g_launches++;
+  return cuda_ok(cudaGetLastError(), "sumpool2") ? 0 : -2;
+}
+// stats_dev: [3][C] = mean, biased variance, rstd (written by fwd, read by bwd).  drop_dev: {0,1} mask or NULL.
+extern "C" int gsx_op_bn_lrelu_fwd(const float* z_dev, const float* gamma_dev, const float* beta_dev, const float* drop_dev,
+                                   float* y_dev, float* stats_dev, int n, int c, int hw, gsx_stream stream) {
+  if (!z_dev || !gamma_dev || !beta_dev || !y_dev || !stats_dev) { set_error("bad argument"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* partial = nullptr;
+  if (!cuda_ok(cudaMalloc(&partial, (size_t)c * kRedBlocks * 2 * sizeof(double)), "bn partials")) return -2;
+  BnArgs a{z_dev, nullptr, drop_dev, gamma_dev, beta_dev, stats_dev, stats_dev + 2 * c, n, c, hw};
+  chan_reduce_kernel<false><<<dim3(kRedBlocks, c), kRedThreads, 0, st>>>(a, partial);
+  chan_finalize_kernel<false><<<(c + 127) / 128, 128, 0, st>>>(partial, kRedBlocks, c, (double)n * hw, stats_dev, stats_dev + c, stats_dev + 2 * c);
+  bn_lrelu_fwd_kernel<<<ew_blocks((size_t)n * c * hw), 256, 0, st>>>(a, y_dev);
+  g_launches += 3;
+  const bool ok = cuda_ok(cudaStreamSynchronize(st), "bn_lrelu_fwd");
+  cudaFree(partial);
+  return ok ? 0 : -2;
+}
+// dparam_dev: [2][C] = dbeta, dgamma.
+extern "C" int gsx_op_bn_lrelu_bwd(const float* dy_dev, const float* z_dev, const float* stats_dev, const float* gamma_dev,
+                                   const float* beta_dev, const float* drop_dev, float* dz_dev, float* dparam_dev, int n, int c,
+                                   int hw, gsx_stream stream) {
+  if (!dy_dev || !z_dev || !stats_dev || !gamma_dev || !beta_dev || !dz_dev || !dparam_dev) { set_error("bad argument"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* partial = nullptr;
+  if (!cuda_ok(cudaMalloc(&partial, (size_t)c * kRedBlocks * 2 * sizeof(double)), "bn partials")) return -2;
+  BnArgs a{z_dev, dy_dev, drop_dev, gamma_dev, beta_dev, stats_dev, stats_dev + 2 * c, n, c, hw};
+  chan_reduce_kernel<true><<<dim3(kRedBlocks, c), kRedThreads, 0, st>>>(a, partial);
+  chan_finalize_kernel<true><<<(c + 127) / 128, 128, 0, st>>>(partial, kRedBlocks, c, (double)n * hw, dparam_dev, dparam_dev + c, nullptr);
+  bn_lrelu_bwd_kernel<<<ew_blocks((size_t)n * c * hw), 256, 0, st>>>(a, dparam_dev, dparam_dev + c, dz_dev);
+  g_launches += 3;
+  const bool ok = cuda_ok(cudaStreamSynchronize(st), "bn_lrelu_bwd");
+  cudaFree(partial);
   return ok ? 0 : -2;
 }
 

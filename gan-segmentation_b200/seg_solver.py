@@ -30,8 +30,8 @@ class SegSolver:
 
     The generate path needs ``predict`` / ``load`` / ``save`` and the attributes callers read
     (``is_trained``, ``net``, ``cfg``, ``ctx``, ``params_file``); ``evaluate`` runs the decoder and the loss kernel
-    over a directory of annotated samples.  ``fit`` (decoder training, seg_solver.py:351-465) needs the decoder
-    backward pass, which is not built yet, and raises NotImplementedError.
+    over a directory of annotated samples; ``fit`` trains the decoder (first, functional version on the
+    single-operator kernels, see ``decoder_training.py``).
     """
 
     def __init__(self, max_res_log2, path_to_data, checkpoints_dir, gpu_ids, keep_weights=True, *, base_hw=(4, 4),
@@ -127,8 +127,69 @@ class SegSolver:
             return True
         return False
 
-    def fit(self, epoch_end_callback=None):
-        raise NotImplementedError('decoder training (seg_solver.py:351-465) is not part of the generate hot path yet')
+    def fit(self, epoch_end_callback=None, *, max_iters=None):
+        """seg_solver.py:351-465: train the decoder on the annotated samples of ``path_to_data`` (generator frozen).
+        Train-mode forward (BatchNorm batch statistics, Dropout(0.5) after every cvt block), SoftmaxCE with weight
+        ``mask > -1``, backward, one all-reduce of the flat gradient bucket when ``torch.distributed`` is initialised
+        (one process per GPU; the reference's in-process KVStore('nccl') sum), Adam(base_lr) with
+        ``rescale_grad = 1/global batch``; ``epoch_end_callback()`` after every epoch; saves ``checkpoint_last.params``
+        and returns ``[]`` like the reference.  Runs on this repo's CUDA kernels through ``decoder_training.CudaBackend``
+        (first, functional version: single-operator hooks, not yet fast).  ``max_iters`` bounds the run (tests)."""
+        import logging
+        import time
+        from .decoder_training import CudaBackend, DecoderTrainer
+        from .seg_datasets import CollectionDataset
+        cfg = self.cfg
+        if not self.keep_weights:
+            self.net = self.init_net()
+        ds = CollectionDataset(self.path_to_data, cfg, max_samples=None, load_to_memory=False)
+        if len(ds) <= 0:
+            print('number of training samples should be > 0')
+            raise SystemExit(-1)
+        bs = int(cfg['train_batch_size'])
+        iters_per_epoch = int(len(ds) / bs)
+        print('total train samples: {}'.format(len(ds)))
+        print('batch size: {}'.format(bs))
+        print('epoch size: {}'.format(iters_per_epoch))
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+        with torch.cuda.device(self.ctx[0]):
+            trainer = DecoderTrainer(cfg, self.net.get_parameters(), CudaBackend(self.ctx[0]))
+            rng = np.random.RandomState(cfg['seed'])
+            gen = torch.Generator(device=self.ctx[0]).manual_seed(int(cfg['seed']))
+            display = cfg['train_display_iters']
+            done = 0
+            for epoch in range(int(cfg['train_epochs'])):
+                tic = speed_tic = time.time()
+                order = rng.permutation(len(ds))                       # DataLoader(shuffle=True, last_batch='discard')
+                for nbatch in range(1, iters_per_epoch + 1):
+                    items = [ds[int(j)] for j in order[(nbatch - 1) * bs:nbatch * bs]]
+                    mask = np.stack([it[1] for it in items]).astype(np.int32)
+                    nfeat = len(items[0]) - 2
+                    feats = [np.stack([np.asarray(it[2 + k], np.float32) for it in items]) for k in range(nfeat)]
+                    drops = None
+                    if cfg.get('use_dropout', False):
+                        drops = [(torch.rand((bs, cfg['features'][k]) + tuple(feats[k].shape[2:]), generator=gen, device=self.ctx[0]) > 0.5).float()
+                                 for k in range(nfeat)]
+                    loss = trainer.step(feats, mask, drops, global_batch=bs * world)
+                    done += 1
+                    if display is not None and nbatch % display == 0:
+                        speed = 1.0 * display * bs / (time.time() - speed_tic)
+                        logging.info('Epoch[%03d] Batch[%04d] Speed: % 9.2f samples/sec total-loss=%f', epoch, nbatch, speed,
+                                     float(loss.mean().item()))
+                        speed_tic = time.time()
+                    if max_iters is not None and done >= max_iters:
+                        break
+                logging.info('Epoch[%d] Time cost=%.3f', epoch + 1, time.time() - tic)
+                if epoch_end_callback is not None:
+                    epoch_end_callback()
+                if max_iters is not None and done >= max_iters:
+                    break
+            self.set_parameters(trainer.state())
+        self.is_trained = True
+        self.save()
+        return []
 
     def evaluate(self, input_dir, output_dir=None):
         """seg_solver.py:222-305: pixel accuracy, mean IoU (background skipped) and the mean SoftmaxCE loss over

@@ -128,6 +128,16 @@ int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z_host, cons
  * first, CUDA-core version of the decoder's weight gradient (seg_solver.py:411-412 err.backward()). */
 int gsx_op_conv_wgrad(int k, int n, int h, int w, int cin, int cout, const float* x_dev, const float* dy_dev,
                       float* dw_dev, float* db_dev, gsx_stream stream);
+/* Train-mode BatchNorm (batch statistics, eps 1e-5) + LeakyReLU(0.2) (+ Dropout(0.5) mask) forward / backward and the
+ * nearest-x2 upsample / its adjoint, fp32 NCHW (networks_seg.py:14-29, 70-78, 87).  stats_dev [3][C] = mean, biased
+ * variance, rstd; dparam_dev [2][C] = dbeta, dgamma.  Deterministic (fixed-order double partial sums). */
+int gsx_op_upsample2(const float* x_dev, float* y_dev, int n, int c, int h, int w, gsx_stream stream);
+int gsx_op_sumpool2(const float* dy_dev, float* dx_dev, int n, int c, int h, int w, gsx_stream stream);
+int gsx_op_bn_lrelu_fwd(const float* z_dev, const float* gamma_dev, const float* beta_dev, const float* drop_dev, float* y_dev,
+                        float* stats_dev, int n, int c, int hw, gsx_stream stream);
+int gsx_op_bn_lrelu_bwd(const float* dy_dev, const float* z_dev, const float* stats_dev, const float* gamma_dev,
+                        const float* beta_dev, const float* drop_dev, float* dz_dev, float* dparam_dev, int n, int c, int hw,
+                        gsx_stream stream);
 int gsx_softmax_ce(const float* logits_dev, const int* labels_dev, int n, int num_classes, int h, int w,
                    float* loss_dev, float* dlogits_dev, float* scratch_dev, size_t scratch_floats, gsx_stream stream);
 int gsx_adam_step(float* w_dev, const float* g_dev, float* m_dev, float* v_dev, size_t count, int t, float lr, float beta1,

@@ -103,3 +103,35 @@ def test_evaluate_annotated_samples(tmp_path):
     names = sorted(p.name for p in (tmp_path / 'eval_out').iterdir())
     assert names == sorted([f'{k}_{i:06d}.{e}' for i in range(3) for k, e in
                             (('img', 'jpg'), ('mask', 'png'), ('gt_mask', 'png'), ('metrics', 'txt'))])
+
+
+def test_fit_trains_the_decoder(tmp_path):
+    """SegSolver.fit (seg_solver.py:351-465) on annotated samples: runs on the CUDA kernels, lowers the evaluation loss,
+    marks the solver trained and writes checkpoint_last.params that a fresh solver loads."""
+    from gan_segmentation_b200.seg_solver import SegSolver
+    from gan_segmentation_b200.seg_datasets import save_sample
+    from gan_segmentation_b200.networks import Generator
+    gc = generator_config(6)
+    ckpt, data = tmp_path / 'checkpoints', tmp_path / 'data'
+    ckpt.mkdir(); data.mkdir()
+    G = Generator(gc)
+    G.set_parameters(init_generator_params(gc, seed=0))
+    out = G.forward(n=4, seed=5, return_u8=True, return_features=True)
+    imgs = out['img_u8'].cpu().numpy()
+    feats_all = [f.cpu().numpy() for f in out['features']]
+    for i in range(4):
+        lab = (feats_all[-1][i, 0] > np.median(feats_all[-1][i, 0])).astype(np.int64)      # a learnable target
+        save_sample(str(data), i, imgs[i], [f[i] for f in feats_all], lab)
+    solver = SegSolver(6, str(data), str(ckpt), gpu_ids=[0], keep_weights=True, verbose=False)
+    assert not solver.is_trained
+    solver.cfg['train_epochs'] = 6
+    solver.cfg['base_lr'] = 2e-3
+    before = dict(solver.evaluate(str(data)))['total-loss']
+    calls = []
+    assert solver.fit(epoch_end_callback=lambda: calls.append(1)) == []
+    after = dict(solver.evaluate(str(data)))
+    assert len(calls) == 6 and solver.is_trained and solver.params_file == 'checkpoint_last.params'
+    assert after['total-loss'] < 0.8 * before, (before, after)
+    solver2 = SegSolver(6, str(data), str(ckpt), gpu_ids=[0], keep_weights=True, verbose=False)
+    assert solver2.is_trained
+    assert abs(dict(solver2.evaluate(str(data)))['total-loss'] - after['total-loss']) < 1e-5

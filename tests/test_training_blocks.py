@@ -126,3 +126,69 @@ def test_conv_wgrad_matches_autograd(gsx_lib):
         assert torch.allclose(db, b.grad, rtol=1e-4, atol=1e-2)
         dw2, db2 = conv_wgrad(x, dy, k)
         assert torch.equal(dw, dw2) and torch.equal(db, db2)
+
+
+@pytest.mark.gpu
+def test_bn_lrelu_and_upsample_kernels(gsx_lib):
+    """Train-mode BatchNorm + LeakyReLU (+ dropout mask) forward / backward and the nearest-x2 pair against the
+    hand-written torch formulas of the test backend (which the CPU suite checks against autograd)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from torch_backend import TorchBackend
+    from gan_segmentation_b200.decoder_training import CudaBackend
+    cb, tb = CudaBackend(), TorchBackend()
+    g = torch.Generator().manual_seed(9)
+    for (n, c, h, w, use_drop) in [(2, 32, 12, 20, False), (1, 16, 33, 17, True), (3, 512, 4, 4, True)]:
+        z = torch.randn((n, c, h, w), generator=g) * 2 + 0.5
+        dy = torch.randn((n, c, h, w), generator=g)
+        gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.3
+        drop = (torch.rand((n, c, h, w), generator=g) > 0.5).float() if use_drop else None
+        y_ref, c_ref = tb.bn_lrelu_fwd(z, gamma, beta, drop)
+        dz_ref, dg_ref, db_ref = tb.bn_lrelu_bwd(dy, z, c_ref, gamma, beta, drop)
+        zc, dyc, gc_, bc = z.cuda(), dy.cuda(), gamma.cuda(), beta.cuda()
+        dc = drop.cuda() if drop is not None else None
+        y, cc = cb.bn_lrelu_fwd(zc, gc_, bc, dc)
+        assert torch.allclose(cc['mean'].cpu(), c_ref['mean'], atol=1e-5) and torch.allclose(cc['var'].cpu(), c_ref['var'], rtol=1e-4, atol=1e-6)
+        assert torch.allclose(y.cpu(), y_ref, rtol=1e-4, atol=1e-5)
+        dz, dg, db = cb.bn_lrelu_bwd(dyc, zc, cc, gc_, bc, dc)
+        assert torch.allclose(dg.cpu(), dg_ref, rtol=1e-4, atol=1e-3) and torch.allclose(db.cpu(), db_ref, rtol=1e-4, atol=1e-3)
+        assert torch.allclose(dz.cpu(), dz_ref, rtol=1e-3, atol=1e-5)
+        assert torch.equal(cb.upsample2(zc).cpu(), tb.upsample2(z))
+        z2 = torch.randn((n, c, 2 * h, 2 * w), generator=g)
+        assert torch.allclose(cb.sumpool2(z2.cuda()).cpu(), tb.sumpool2(z2), atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_decoder_training_step_on_cuda_kernels(gsx_lib):
+    """One and several steps of DecoderTrainer on the CUDA backend: loss and gradients agree with the same trainer on the
+    fp32 torch test backend up to the 16-bit conv operands, and the loss goes down."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from torch_backend import TorchBackend
+    from gan_segmentation_b200.config import decoder_config
+    from gan_segmentation_b200.decoder_training import CudaBackend, DecoderTrainer
+    from gan_segmentation_b200.random_init import init_decoder_params
+    res, n = 5, 2
+    cfg = dict(decoder_config(res), use_dropout=True, base_lr=2e-3)
+    params = init_decoder_params(cfg, seed=2)
+    rs = np.random.RandomState(0)
+    feats = [rs.randn(n, c, 4 << i, 4 << i).astype(np.float32) for i, c in enumerate(cfg['in_channels'][:res - 1])]
+    mask = rs.randint(-1, 2, (n, 1, 32, 32))
+    drops = [(rs.rand(n, cfg['features'][i], 4 << i, 4 << i) > 0.5).astype(np.float32) for i in range(res - 1)]
+    ref = DecoderTrainer(cfg, params, TorchBackend())
+    loss_ref, g_ref = ref.loss_and_grads(feats, mask, drops)
+    tr = DecoderTrainer(cfg, params, CudaBackend())
+    loss, grads = tr.loss_and_grads(feats, mask, drops)
+    assert np.allclose(loss.cpu().numpy(), loss_ref.numpy(), rtol=2e-2, atol=1e-3)
+    # (the bias of a conv that feeds a BatchNorm has an exactly-zero gradient: compare on an absolute scale there)
+    gscale = max(float(np.abs(v.numpy()).max()) for v in g_ref.values())
+    for k in g_ref:
+        a, b = grads[k].cpu().numpy(), g_ref[k].numpy()
+        err = np.abs(a - b).max() / max(float(np.abs(b).max()), 2e-3 * gscale)
+        assert err < 6e-2, (k, err, float(np.abs(b).max()), gscale)
+    losses = [float(loss.mean())]
+    for _ in range(8):
+        losses.append(float(tr.step(feats, mask, drops).mean()))
+    assert losses[-1] < 0.85 * losses[0], losses
+    st = tr.state()
+    assert set(st) == set(params) and all(st[k].shape == np.asarray(params[k]).shape for k in params)
