@@ -14,6 +14,13 @@ class _Adam:
         self.v = {k: torch.zeros(s, dtype=torch.float64) for k, s in shapes.items()}
 
     def apply(self, grads, batch, group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            grads = dict(grads)
+            for k in self.names:                      # (the product all-reduces ONE flat bucket, training.FlatAdam)
+                g = grads[k].clone()
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+                grads[k] = g
         self.t += 1
         lr_t = self.lr * np.sqrt(1 - 0.999 ** self.t) / (1 - 0.9 ** self.t)
         for k in self.names:
