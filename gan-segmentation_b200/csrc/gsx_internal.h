@@ -268,6 +268,13 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return launch_pdl_kind(0, kernel, grid, block, smem, st, args...);
 }
 
+// Scratch memory of the single-operator hooks (gsx_op_*): blocks are kept and reused across calls (every hook
+// synchronises its stream before returning, so a block is free again when the call ends); cudaMalloc / cudaFree per
+// call dominated the hook-based training step.  Thread-local; gsx_op_release_cache() returns everything.
+void* pool_get(size_t bytes);
+void pool_put(void* p);
+void pool_release();
+
 void set_error(const std::string& msg);
 bool cuda_ok(cudaError_t e, const char* what);
 

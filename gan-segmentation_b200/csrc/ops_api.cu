@@ -12,10 +12,10 @@ extern std::atomic<uint64_t> g_launches;
 
 struct Tmp {
   std::vector<void*> ptrs;
-  ~Tmp() { for (void* p : ptrs) cudaFree(p); }
+  ~Tmp() { for (void* p : ptrs) pool_put(p); }
   template <class T> T* get(size_t n) {
-    void* p = nullptr;
-    if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    void* p = pool_get(std::max<size_t>(n, 1) * sizeof(T));
+    if (!p) return nullptr;
     ptrs.push_back(p);
     return static_cast<T*>(p);
   }
@@ -126,6 +126,8 @@ extern "C" int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, in
   }
   return 0;
 }
+
+extern "C" void gsx_op_release_cache(void) { pool_release(); }
 
 extern "C" int gsx_plan_query(int mode, int h, int w, int cin0, int cin1, int cout, int num_classes,
                               const gsx_plan_override* ov, int* plan_out) {

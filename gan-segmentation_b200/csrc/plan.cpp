@@ -38,6 +38,42 @@ bool pdl_enabled(int kind) {
   return on;
 }
 
+namespace {
+struct PoolBlock { void* p; size_t size; bool used; };
+thread_local std::vector<PoolBlock> g_pool;
+}
+void* pool_get(size_t bytes) {
+  if (bytes == 0) bytes = 256;
+  int best = -1;
+  for (int i = 0; i < (int)g_pool.size(); ++i) {
+    const PoolBlock& b = g_pool[i];
+    if (!b.used && b.size >= bytes && b.size <= 2 * bytes + (1 << 20) && (best < 0 || b.size < g_pool[best].size)) best = i;
+  }
+  if (best >= 0) { g_pool[best].used = true; return g_pool[best].p; }
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    pool_release();                                   // out of memory: drop the cached blocks and retry once
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  }
+  g_pool.push_back({p, bytes, true});
+  return p;
+}
+void pool_put(void* p) {
+  if (!p) return;
+  for (auto& b : g_pool)
+    if (b.p == p) { b.used = false; return; }
+  cudaFree(p);
+}
+void pool_release() {
+  std::vector<PoolBlock> keep;
+  for (auto& b : g_pool) {
+    if (b.used) keep.push_back(b);
+    else cudaFree(b.p);
+  }
+  g_pool.swap(keep);
+}
+
 static const int kSmemLimit = 227 * 1024;
 static const int kHeader = kConvHeaderBytes;
 static const int kSlack = 8192;     // garbage-tolerant over-read of the last (partial) MMA tile

@@ -296,11 +296,12 @@ extern "C" int gsx_op_conv_wgrad(int k, int n, int h, int w, int cin, int cout, 
   const size_t E = (size_t)CoutB * CinB * 640, P = (size_t)tiles * n;
   act_t *xb = nullptr, *dyb = nullptr;
   float* partial = nullptr;
-  bool ok = cuda_ok(cudaMalloc(&xb, (size_t)n * cin * h * w * sizeof(act_t)), "wgrad x") &&
-            cuda_ok(cudaMalloc(&dyb, (size_t)n * cout * h * w * sizeof(act_t)), "wgrad dy") &&
-            cuda_ok(cudaMalloc(&partial, P * E * sizeof(float)), "wgrad partials");
+  xb = static_cast<act_t*>(pool_get((size_t)n * cin * h * w * sizeof(act_t)));
+  dyb = static_cast<act_t*>(pool_get((size_t)n * cout * h * w * sizeof(act_t)));
+  partial = static_cast<float*>(pool_get(P * E * sizeof(float)));
+  bool ok = xb && dyb && partial;
+  if (!ok) set_error("conv_wgrad: out of device memory");
   if (ok) {
-    cudaMemsetAsync(partial, 0, P * E * sizeof(float), st);
     launch_nchw_to_blocked(x_dev, xb, cin, n, h * w, st);
     launch_nchw_to_blocked(dy_dev, dyb, cout, n, h * w, st);
     dim3 grid(tiles, n, CoutB * CinB);
@@ -315,7 +316,7 @@ extern "C" int gsx_op_conv_wgrad(int k, int n, int h, int w, int cin, int cout, 
     g_launches += 4;
     ok = cuda_ok(cudaStreamSynchronize(st), "conv_wgrad");
   }
-  cudaFree(xb); cudaFree(dyb); cudaFree(partial);
+  pool_put(xb); pool_put(dyb); pool_put(partial);
   return ok ? 0 : -2;
 }
 
@@ -338,15 +339,15 @@ extern "C" int gsx_op_bn_lrelu_fwd(const float* z_dev, const float* gamma_dev, c
                                    float* y_dev, float* stats_dev, int n, int c, int hw, gsx_stream stream) {
   if (!z_dev || !gamma_dev || !beta_dev || !y_dev || !stats_dev) { set_error("bad argument"); return -1; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  double* partial = nullptr;
-  if (!cuda_ok(cudaMalloc(&partial, (size_t)c * kRedBlocks * 2 * sizeof(double)), "bn partials")) return -2;
+  double* partial = static_cast<double*>(pool_get((size_t)c * kRedBlocks * 2 * sizeof(double)));
+  if (!partial) { set_error("bn_lrelu_fwd: out of device memory"); return -2; }
   BnArgs a{z_dev, nullptr, drop_dev, gamma_dev, beta_dev, stats_dev, stats_dev + 2 * c, n, c, hw};
   chan_reduce_kernel<false><<<dim3(kRedBlocks, c), kRedThreads, 0, st>>>(a, partial);
   chan_finalize_kernel<false><<<(c + 127) / 128, 128, 0, st>>>(partial, kRedBlocks, c, (double)n * hw, stats_dev, stats_dev + c, stats_dev + 2 * c);
   bn_lrelu_fwd_kernel<<<ew_blocks((size_t)n * c * hw), 256, 0, st>>>(a, y_dev);
   g_launches += 3;
   const bool ok = cuda_ok(cudaStreamSynchronize(st), "bn_lrelu_fwd");
-  cudaFree(partial);
+  pool_put(partial);
   return ok ? 0 : -2;
 }
 // dparam_dev: [2][C] = dbeta, dgamma.
@@ -355,15 +356,15 @@ extern "C" int gsx_op_bn_lrelu_bwd(const float* dy_dev, const float* z_dev, cons
                                    int hw, gsx_stream stream) {
   if (!dy_dev || !z_dev || !stats_dev || !gamma_dev || !beta_dev || !dz_dev || !dparam_dev) { set_error("bad argument"); return -1; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  double* partial = nullptr;
-  if (!cuda_ok(cudaMalloc(&partial, (size_t)c * kRedBlocks * 2 * sizeof(double)), "bn partials")) return -2;
+  double* partial = static_cast<double*>(pool_get((size_t)c * kRedBlocks * 2 * sizeof(double)));
+  if (!partial) { set_error("bn_lrelu_bwd: out of device memory"); return -2; }
   BnArgs a{z_dev, dy_dev, drop_dev, gamma_dev, beta_dev, stats_dev, stats_dev + 2 * c, n, c, hw};
   chan_reduce_kernel<true><<<dim3(kRedBlocks, c), kRedThreads, 0, st>>>(a, partial);
   chan_finalize_kernel<true><<<(c + 127) / 128, 128, 0, st>>>(partial, kRedBlocks, c, (double)n * hw, dparam_dev, dparam_dev + c, nullptr);
   bn_lrelu_bwd_kernel<<<ew_blocks((size_t)n * c * hw), 256, 0, st>>>(a, dparam_dev, dparam_dev + c, dz_dev);
   g_launches += 3;
   const bool ok = cuda_ok(cudaStreamSynchronize(st), "bn_lrelu_bwd");
-  cudaFree(partial);
+  pool_put(partial);
   return ok ? 0 : -2;
 }
 

@@ -131,6 +131,8 @@ int gsx_op_conv_wgrad(int k, int n, int h, int w, int cin, int cout, const float
 /* Train-mode BatchNorm (batch statistics, eps 1e-5) + LeakyReLU(0.2) (+ Dropout(0.5) mask) forward / backward and the
  * nearest-x2 upsample / its adjoint, fp32 NCHW (networks_seg.py:14-29, 70-78, 87).  stats_dev [3][C] = mean, biased
  * variance, rstd; dparam_dev [2][C] = dbeta, dgamma.  Deterministic (fixed-order double partial sums). */
+/* The gsx_op_* hooks keep their scratch device memory between calls; this returns it. */
+void gsx_op_release_cache(void);
 int gsx_op_upsample2(const float* x_dev, float* y_dev, int n, int c, int h, int w, gsx_stream stream);
 int gsx_op_sumpool2(const float* dy_dev, float* dx_dev, int n, int c, int h, int w, gsx_stream stream);
 int gsx_op_bn_lrelu_fwd(const float* z_dev, const float* gamma_dev, const float* beta_dev, const float* drop_dev, float* y_dev,
