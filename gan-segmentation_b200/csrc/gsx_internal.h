@@ -103,7 +103,8 @@ struct ConvGeom {
   int in_planar;               // s2d: the inputs are stored phase-planar ([C/8][N][4 phases][H/2][W/2][8]): dense plane boxes
   int dbg;                     // tuning only (env GSX_DBG): 1 skip epilogue work, 2 skip MMAs, 4 skip activation loads,
                                //   8 issuers do not wait for operands (with 4: pure MMA issue rate)
-  int a_off;                   // byte offset of the A stages in dynamic smem (after header + stats slots)
+  int chan_off, chan_n;        // smem table of the per-channel epilogue operands: [2][chan_n] floats (bias, noise scale)
+  int a_off;                   // byte offset of the A stages in dynamic smem (after header + stats slots + channel table + aux)
   int tmem_cols;               // allocated TMEM columns (power of two) = acc_bufs * n_groups*n_mtiles*N_tile rounded up
   int acc_bufs;                // 2: accumulators double buffered (MMA of tile i+1 overlaps epilogue of tile i)
   int b_resident;              // 1: the whole packed weight set is loaded once per CTA and stays in smem

@@ -145,7 +145,10 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   const int epi_groups = 2;
   if (ov && ov->epi_groups > 0 && ov->epi_groups != 2) { set_error("plan_conv: only epi_groups = 2 is built"); return; }
   const int stats_bytes = (2 * 4 * epi_groups * 2 * cout_tile * 4 + 1023) / 1024 * 1024;
-  const int hdr_bytes = kHeader + stats_bytes;
+  // per-channel epilogue operands of every output channel (bias, noise scale), staged once per CTA
+  const int chan_n = std::max(16, ceil_div(argmax_classes > 0 ? argmax_classes : cout, cout_tile) * cout_tile);
+  const int chan_bytes = (2 * chan_n * 4 + 1023) / 1024 * 1024;
+  const int hdr_bytes = kHeader + stats_bytes + chan_bytes;
 
   int TW = (W <= 126) ? W : ((W % 64 == 0) ? 64 : 126);
   if (ov && ov->TW > 0) TW = ov->TW;
@@ -242,6 +245,7 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   g.b_resident = b_resident;
   g.epi_groups = epi_groups;
   g.ctas_per_sm = 1;
+  g.chan_off = kHeader + stats_bytes; g.chan_n = chan_n;
   g.aux_kind = aux_kind; g.aux_off = hdr_bytes; g.aux_bytes = (int)aux_bytes;
   g.aux_bw = s2d ? TW : TW / 2; g.aux_bh = s2d ? TH : TH / 2 + 1;
   g.aux_up = aux_up; g.aux_shift = s2d ? 0 : 1;

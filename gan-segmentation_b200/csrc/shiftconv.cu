@@ -139,6 +139,7 @@ __device__ __forceinline__ void issue_group(uint32_t d, int n_mtiles, uint32_t n
 }
 
 struct TileCoord { int x0, y0, n0, ntile, phase, tile_in_sample; };
+struct Loc { int nb, yl, xl, n, y, x; bool valid; };     // a GEMM row of a tile: tile-local and global coordinates
 
 // a / d for 0 <= a < 2^24 via the float reciprocal (+ one correction step): ~8 instructions instead of the ~35 of an
 // integer division -- decode_tile runs once per work item in all three roles.
@@ -389,6 +390,18 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     pdl_wait();                                     // before the first global read / write of this role
 
+    // per-channel epilogue operands (bias, noise scale) of all output channels of the layer: staged once per CTA in
+    // shared memory and read as packed fp32 pairs (broadcast LDS.128) -- 32 registers less than holding the current
+    // 16-channel block in registers, and no reload per tile
+    float* chan_s = reinterpret_cast<float*>(smem + g.chan_off);      // [2][chan_n]: bias, noise scale
+    for (int i = threadIdx.x - 64; i < g.chan_n; i += kEpiThreads) {
+      chan_s[i] = (e.bias && i < e.Cout) ? __ldg(e.bias + i) : 0.f;
+      chan_s[g.chan_n + i] = (GEN && e.nscale && i < e.Cout) ? __ldg(e.nscale + i) : 0.f;
+    }
+    named_bar_sync(1, kEpiThreads);
+    const ulonglong2* const bias_s2 = reinterpret_cast<const ulonglong2*>(chan_s);
+    const ulonglong2* const ns_s2 = reinterpret_cast<const ulonglong2*>(chan_s + g.chan_n);
+
     int tl = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
       const TileCoord tc = decode_tile(g, t);
@@ -406,24 +419,25 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
       const uint32_t acc_base = tmem_base + (uint32_t)(buf * cols_per_buf) + lane_base;
 
       // position of this thread's row inside MMA tile `mt`:  q = mt*128 + row  ->  (nb, yl, xl)
-      int nb_l = 0, yl_l = 0, xl_l = 0;            // tile-local coordinates of the last located row
-      auto locate = [&](int mt, int& n, int& y, int& x) -> bool {
+      auto locate = [&](int mt) -> Loc {
+        Loc l;
         const int q = mt * g.mt_stride + row;
-        const int nb = (int)__umulhi((uint32_t)q, g.magic_box);
-        const int rem = q - nb * (g.BH * g.BW);
-        const int yl = (int)__umulhi((uint32_t)rem, g.magic_bw);
-        const int xl = rem - yl * g.BW;
-        nb_l = nb; yl_l = yl; xl_l = xl;
-        n = tc.n0 + nb; y = tc.y0 + yl; x = tc.x0 + xl;
-        return row < g.mt_stride && nb < g.NB && yl < g.TH && xl < g.TW && n < g.N && y < g.H && x < g.W;
+        l.nb = (int)__umulhi((uint32_t)q, g.magic_box);
+        const int rem = q - l.nb * (g.BH * g.BW);
+        l.yl = (int)__umulhi((uint32_t)rem, g.magic_bw);
+        l.xl = rem - l.yl * g.BW;
+        l.n = tc.n0 + l.nb; l.y = tc.y0 + l.yl; l.x = tc.x0 + l.xl;
+        l.valid = row < g.mt_stride && l.nb < g.NB && l.yl < g.TH && l.xl < g.TW && l.n < g.N && l.y < g.H && l.x < g.W;
+        return l;
       };
 
       if (GSX_EPI_LITE || (g.dbg & 1)) {
       } else if ((e.flags & EPI_ARGMAX) && g.up_cols) {
         // s2d final conv: the 4 output phases of a block are column groups of cout_tile (4, 8 or 16) classes
         for (int u = egrp; u < n_units; u += G) {
-          int n, y, x;
-          const bool valid = locate(u, n, y, x);
+          const Loc lc = locate(u);
+          const bool valid = lc.valid;
+          const int n = lc.n, y = lc.y, x = lc.x;
           for (int cc = 0; cc < n_chunks; ++cc) {
             uint32_t v[16];
             tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + cc * 16), v);
@@ -440,8 +454,9 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
           uint32_t v[16];
           tmem_ld16(acc_base + (uint32_t)(mt * g.N_tile), v);
           tmem_ld_wait();
-          int n, y, x;
-          if (locate(mt, n, y, x)) {
+          const Loc lc = locate(mt);
+          const int n = lc.n, y = lc.y, x = lc.x;
+          if (lc.valid) {
             float best = __uint_as_float(v[0]) + (e.bias ? __ldg(e.bias) : 0.f);
             int arg = 0;
             const size_t pix = (size_t)y * e.Wo + x;
@@ -462,209 +477,218 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         // the output row, so both phases are processed together and leave as ONE 32-byte store per channel block
         // (full sectors instead of two half-sector writes).  GEN adds the generator's first-half epilogue for the
         // folded deconv+blur: border correction, noise (tile staged at output resolution), statistics.
-        const float slope = do_act ? 0.2f : 1.0f;
+        // Instruction-count notes (ncu r01: this loop issued 24 thread-instructions per output value): the row is
+        // located once per MMA tile (not per phase), the per-channel operands are (re)loaded only when the channel
+        // block changes, the border test is a per-tile flag, and the arithmetic runs on packed fp32 pairs.
+        const f32x2 slope2 = pk2(do_act ? 0.2f : 1.0f, do_act ? 0.2f : 1.0f);
         const bool has_res = !GEN && (g.aux_kind == 2 || e.addsrc != nullptr);
+        const bool tile_border = GEN && e.e_rows != nullptr &&
+                                 (tc.y0 == 0 || tc.y0 + g.TH >= g.H || tc.x0 == 0 || tc.x0 + g.TW >= g.W);
         for (int c16 = 0; c16 < cpp; ++c16) {
           const int c0 = tc.ntile * g.cout_tile + c16 * 16;
-          float bias_r[16], ns_r[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            bias_r[i] = e.bias ? __ldg(e.bias + c0 + i) : 0.f;
-            ns_r[i] = (GEN && e.nscale) ? __ldg(e.nscale + c0 + i) : 0.f;
-          }
-          float s1[16], s2[16];
+          if (c0 >= e.Cout) break;
+          f32x2 s1[8], s2[8];
           if (GEN) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+            for (int i = 0; i < 8; ++i) { s1[i] = 0ull; s2[i] = 0ull; }
           }
-          for (int py = 0; py < 2; ++py) {
-            const int col0 = ((2 * py) * cpp + c16) * 16, col1 = ((2 * py + 1) * cpp + c16) * 16;
-            for (int u = egrp; u < n_units; u += G) {
+          for (int u = egrp; u < n_units; u += G) {
+            const Loc lc = locate(u);
+            const uint32_t tbase = acc_base + (uint32_t)(u * g.N_tile + c16 * 16);
+            // output pixel (2y+py, 2x) of this row; the noise tile is staged at output resolution
+            const size_t pix0 = (size_t)(2 * lc.y) * e.Wo + 2 * lc.x;
+            act_t* const obase = e.out + ((size_t)(c0 >> 3) * g.N + lc.n) * plane_out * 8;
+            const float* const nzp = reinterpret_cast<const float*>(aux) + ((size_t)(lc.nb * 2 * g.TH + 2 * lc.yl) * (2 * g.TW) + 2 * lc.xl);
+#pragma unroll
+            for (int py = 0; py < 2; ++py) {
               uint32_t va[16], vb[16];
-              tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + col0), va);
-              tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + col1), vb);
-              int n, y, x;
-              const bool valid = locate(u, n, y, x);
-              const int Y = 2 * y + py;
-              const size_t pix = (size_t)Y * e.Wo + 2 * x;
-              float nz0 = 0.f, nz1 = 0.f;
-              if (GEN && valid) {
-                if (g.aux_kind == 1) {
-                  const float2 t2 = *reinterpret_cast<const float2*>(
-                      reinterpret_cast<const float*>(aux) + ((size_t)(nb_l * 2 * g.TH + 2 * yl_l + py) * (2 * g.TW) + 2 * xl_l));
-                  nz0 = t2.x; nz1 = t2.y;
-                } else if (e.noise) {
-                  const float2 t2 = __ldg(reinterpret_cast<const float2*>(e.noise + (size_t)n * plane_out + pix));
-                  nz0 = t2.x; nz1 = t2.y;
-                }
+              tmem_ld16(tbase + (uint32_t)((2 * py) * cpp * 16), va);
+              tmem_ld16(tbase + (uint32_t)((2 * py + 1) * cpp * 16), vb);
+              const int Y = 2 * lc.y + py;
+              const size_t pix = pix0 + (size_t)py * e.Wo;
+              f32x2 nz0 = 0ull, nz1 = 0ull;
+              if (GEN && lc.valid) {
+                float2 t2 = make_float2(0.f, 0.f);
+                if (g.aux_kind == 1) t2 = *reinterpret_cast<const float2*>(nzp + (size_t)py * (2 * g.TW));
+                else if (e.noise) t2 = __ldg(reinterpret_cast<const float2*>(e.noise + (size_t)lc.n * plane_out + pix));
+                nz0 = pk2(t2.x, t2.x); nz1 = pk2(t2.y, t2.y);
               }
               tmem_ld_wait();
-              if (GEN && e.e_rows) {
+              if (tile_border) {
                 // 1-pixel output border of the folded deconv+blur: subtract what the blur would have read from
-                // outside the cropped deconv output.  The vote keeps this a real (warp-uniform, rarely taken) branch.
-                const bool brow = valid && (Y == 0 || Y == e.Ho - 1);
-                const bool bl = valid && x == 0, br = valid && x == g.W - 1;
-                if (__any_sync(0xffffffffu, brow || bl || br)) {
-                  if (brow) {
-                    const float* er = e.e_rows + (((size_t)n * 2 + (Y ? 1 : 0)) * e.Wo + 2 * x) * e.Cout + c0;
+                // outside the cropped deconv output (only tiles on the image border get here)
+                const bool brow = lc.valid && (Y == 0 || Y == e.Ho - 1);
+                const bool bl = lc.valid && lc.x == 0, br = lc.valid && lc.x == g.W - 1;
+                if (brow) {
+                  const float* er = e.e_rows + (((size_t)lc.n * 2 + (Y ? 1 : 0)) * e.Wo + 2 * lc.x) * e.Cout + c0;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                      va[i] = __float_as_uint(__uint_as_float(va[i]) - __ldg(er + i));
-                      vb[i] = __float_as_uint(__uint_as_float(vb[i]) - __ldg(er + e.Cout + i));
-                    }
-                  }
-                  if (bl) {
-                    const float* ec = e.e_cols + (((size_t)n * 2) * e.Ho + Y) * e.Cout + c0;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) - __ldg(ec + i));
-                  }
-                  if (br) {
-                    const float* ec = e.e_cols + (((size_t)n * 2 + 1) * e.Ho + Y) * e.Cout + c0;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) vb[i] = __float_as_uint(__uint_as_float(vb[i]) - __ldg(ec + i));
+                  for (int i = 0; i < 16; ++i) {
+                    va[i] = __float_as_uint(__uint_as_float(va[i]) - __ldg(er + i));
+                    vb[i] = __float_as_uint(__uint_as_float(vb[i]) - __ldg(er + e.Cout + i));
                   }
                 }
+                if (bl) {
+                  const float* ec = e.e_cols + (((size_t)lc.n * 2) * e.Ho + Y) * e.Cout + c0;
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) - __ldg(ec + i));
+                }
+                if (br) {
+                  const float* ec = e.e_cols + (((size_t)lc.n * 2 + 1) * e.Ho + Y) * e.Cout + c0;
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) vb[i] = __float_as_uint(__uint_as_float(vb[i]) - __ldg(ec + i));
+                }
               }
-              if (valid) {
-                act_t* obase = e.out + (((size_t)(c0 >> 3) * g.N + n) * plane_out + pix) * 8;
+              if (lc.valid) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   // residual (s2d conv_b): one block-resolution vector per 8 channels, shared by the 4 output phases
                   uint4 rv = make_uint4(0, 0, 0, 0);
                   if (has_res) {
                     if (g.aux_kind == 2)
-                      rv = reinterpret_cast<const uint4*>(aux)[((size_t)((c16 * 2 + h) * g.NB + nb_l) * g.aux_bh + yl_l) * g.aux_bw + xl_l];
-                    else if (e.addsrc)
+                      rv = reinterpret_cast<const uint4*>(aux)[((size_t)((c16 * 2 + h) * g.NB + lc.nb) * g.aux_bh + lc.yl) * g.aux_bw + lc.xl];
+                    else
                       rv = __ldg(reinterpret_cast<const uint4*>(
-                          e.addsrc + ((((size_t)(c0 >> 3) + h) * g.N + n) * (plane_out >> 2) + (size_t)y * (e.Wo >> 1) + x) * 8));
+                          e.addsrc + ((((size_t)(c0 >> 3) + h) * g.N + lc.n) * (plane_out >> 2) + (size_t)lc.y * (e.Wo >> 1) + lc.x) * 8));
                   }
                   const uint32_t r4[4] = {rv.x, rv.y, rv.z, rv.w};
+                  const ulonglong2 bq0 = bias_s2[(c0 >> 2) + 2 * h], bq1 = bias_s2[(c0 >> 2) + 2 * h + 1];
+                  const f32x2 bias4[4] = {bq0.x, bq0.y, bq1.x, bq1.y};
+                  f32x2 ns4[4] = {0ull, 0ull, 0ull, 0ull};
+                  if (GEN) {
+                    const ulonglong2 nq0 = ns_s2[(c0 >> 2) + 2 * h], nq1 = ns_s2[(c0 >> 2) + 2 * h + 1];
+                    ns4[0] = nq0.x; ns4[1] = nq0.y; ns4[2] = nq1.x; ns4[3] = nq1.y;
+                  }
                   uint32_t o[8];
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    const int i0 = h * 8 + 2 * k, i1 = i0 + 1;
-                    float a0 = __uint_as_float(va[i0]) + bias_r[i0], a1 = __uint_as_float(va[i1]) + bias_r[i1];
-                    float b0 = __uint_as_float(vb[i0]) + bias_r[i0], b1 = __uint_as_float(vb[i1]) + bias_r[i1];
-                    if (GEN) {
-                      a0 = fmaf(ns_r[i0], nz0, a0); a1 = fmaf(ns_r[i1], nz0, a1);
-                      b0 = fmaf(ns_r[i0], nz1, b0); b1 = fmaf(ns_r[i1], nz1, b1);
-                    }
-                    a0 = fmaxf(a0, slope * a0); a1 = fmaxf(a1, slope * a1);
-                    b0 = fmaxf(b0, slope * b0); b1 = fmaxf(b1, slope * b1);
+                    const int j = h * 4 + k, i0 = 2 * j;
+                    f32x2 a = add2(pk2u(va[i0], va[i0 + 1]), bias4[k]);
+                    f32x2 b = add2(pk2u(vb[i0], vb[i0 + 1]), bias4[k]);
+                    if (GEN) { a = fma2(ns4[k], nz0, a); b = fma2(ns4[k], nz1, b); }
+                    const f32x2 am = mul2(a, slope2), bm = mul2(b, slope2);
+                    float a0, a1, b0, b1, m0, m1, m2, m3;
+                    upk2(a, a0, a1); upk2(b, b0, b1); upk2(am, m0, m1); upk2(bm, m2, m3);
+                    a0 = fmaxf(a0, m0); a1 = fmaxf(a1, m1); b0 = fmaxf(b0, m2); b1 = fmaxf(b1, m3);
                     if (has_res) {
                       const float2 r2 = unpack_x2(r4[k]);
                       a0 += r2.x; a1 += r2.y; b0 += r2.x; b1 += r2.y;
                     }
                     if (GEN) {
-                      s1[i0] += a0 + b0; s2[i0] = fmaf(a0, a0, fmaf(b0, b0, s2[i0]));
-                      s1[i1] += a1 + b1; s2[i1] = fmaf(a1, a1, fmaf(b1, b1, s2[i1]));
+                      const f32x2 ar = pk2(a0, a1), br2 = pk2(b0, b1);
+                      s1[j] = add2(s1[j], add2(ar, br2));
+                      s2[j] = fma2(ar, ar, fma2(br2, br2, s2[j]));
                     }
                     o[k] = pack_x2(a0, a1);
                     o[4 + k] = pack_x2(b0, b1);
                   }
-                  if (c0 + h * 8 < e.Cout) {
-                    if (e.out_planar) {       // planes (py,0) and (py,1) of the block-resolution grid
-                      act_t* pb = e.out + ((((size_t)(c0 >> 3) + h) * g.N + n) * plane_out +
-                                           ((size_t)(2 * py) * g.H + y) * g.W + x) * 8;
-                      *reinterpret_cast<uint4*>(pb) = make_uint4(o[0], o[1], o[2], o[3]);
-                      *reinterpret_cast<uint4*>(pb + (size_t)g.H * g.W * 8) = make_uint4(o[4], o[5], o[6], o[7]);
-                    } else {
-                      st_global_256(obase + (size_t)h * g.N * plane_out * 8, o);
-                    }
+                  if (e.out_planar) {       // planes (py,0) and (py,1) of the block-resolution grid
+                    act_t* pb = obase + ((size_t)h * g.N * plane_out + ((size_t)(2 * py) * g.H + lc.y) * g.W + lc.x) * 8;
+                    *reinterpret_cast<uint4*>(pb) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(pb + (size_t)g.H * g.W * 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                  } else {
+                    st_global_256(obase + ((size_t)h * g.N * plane_out + pix) * 8, o);
                   }
-                }
-              }
-            }
-          }
-          if (do_stats) my_slot[(c16 * 16 + (lane & 15)) * 2 + (lane >> 4)] += warp_reduce_32x32(s1, s2, lane);
-        }
-      } else {
-        for (int cc = 0; cc < n_chunks; ++cc) {
-          const int ph = g.up_cols ? cc / cpp : tc.phase;        // output phase of this column chunk
-          const int cl = (cc - (g.up_cols ? ph * cpp : 0)) * 16; // first channel of the chunk inside the CTA's block
-          const int c0 = tc.ntile * g.cout_tile + cl;            // first output channel of this chunk
-          float bias_r[16], ns_r[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            bias_r[i] = e.bias ? __ldg(e.bias + c0 + i) : 0.f;
-            ns_r[i] = (GEN && e.nscale) ? __ldg(e.nscale + c0 + i) : 0.f;
-          }
-          float s1[16], s2[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-
-          // MMA tiles are dealt round-robin to the G warps of a quarter.  The per-pixel operands of the epilogue
-          // (noise value, residual vectors) come from the tile the producer staged in smem by TMA; the global
-          // loads below are only the fallback for layers the planner could not stage.
-          for (int u = egrp; u < n_units; u += G) {
-            const int mt = u;
-            uint32_t v[16];
-            tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + cc * 16), v);
-            int n, y, x;
-            const bool valid = locate(mt, n, y, x);
-            if (e.up) { y = 2 * y + (ph >> 1); x = 2 * x + (ph & 1); }
-            const size_t pix = (size_t)y * e.Wo + x;
-            // phase-planar output: plane (y&1, x&1) of the block grid
-            const size_t pix_st = e.out_planar ? ((size_t)((y & 1) * 2 + (x & 1)) * (e.Ho >> 1) + (y >> 1)) * (e.Wo >> 1) + (x >> 1) : pix;
-            float nz = 0.f;
-            uint4 add0 = make_uint4(0, 0, 0, 0), add1 = add0;
-            if (valid) {
-              if (GEN) {
-                if (g.aux_kind == 1) nz = reinterpret_cast<const float*>(aux)[(nb_l * g.TH + yl_l) * g.TW + xl_l];
-                else if (e.noise) nz = __ldg(e.noise + (size_t)n * plane_out + pix);
-              }
-              if (g.aux_kind == 2) {
-                // residual tile [cb][nb][row/2][col/2] of 16-B vectors at half resolution
-                const int yy = (y >> 1) - (tc.y0 >> 1), xx = (x >> 1) - (tc.x0 >> 1);
-                const uint4* ap = reinterpret_cast<const uint4*>(aux) +
-                                  ((size_t)((cl >> 3) * g.NB + nb_l) * g.aux_bh + yy) * g.aux_bw + xx;
-                add0 = ap[0];
-                add1 = ap[(size_t)g.NB * g.aux_bh * g.aux_bw];
-              } else if (e.addsrc) {
-                const size_t plane_lo = (size_t)(e.Ho >> 1) * (e.Wo >> 1);
-                const size_t pl = (size_t)(y >> 1) * (e.Wo >> 1) + (x >> 1);
-                const act_t* ap = e.addsrc + (((size_t)(c0 >> 3) * g.N + n) * plane_lo + pl) * 8;
-                add0 = __ldg(reinterpret_cast<const uint4*>(ap));
-                add1 = __ldg(reinterpret_cast<const uint4*>(ap + (size_t)g.N * plane_lo * 8));
-              }
-            }
-            tmem_ld_wait();
-            if (valid) {
-              float f[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float a = GEN ? fmaf(ns_r[i], nz, __uint_as_float(v[i]) + bias_r[i]) : __uint_as_float(v[i]) + bias_r[i];
-                f[i] = do_act ? lrelu02(a) : a;
-              }
-              if (e.addsrc || g.aux_kind == 2) {
-                const uint32_t w8[8] = {add0.x, add0.y, add0.z, add0.w, add1.x, add1.y, add1.z, add1.w};
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  const float2 b2 = unpack_x2(w8[k]);
-                  f[2 * k] += b2.x;
-                  f[2 * k + 1] += b2.y;
-                }
-              }
-              if (do_stats) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { s1[i] += f[i]; s2[i] = fmaf(f[i], f[i], s2[i]); }
-              }
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                if (c0 + h * 8 < e.Cout) {
-                  uint4 o;
-                  o.x = pack_x2(f[h * 8 + 0], f[h * 8 + 1]);
-                  o.y = pack_x2(f[h * 8 + 2], f[h * 8 + 3]);
-                  o.z = pack_x2(f[h * 8 + 4], f[h * 8 + 5]);
-                  o.w = pack_x2(f[h * 8 + 6], f[h * 8 + 7]);
-                  *reinterpret_cast<uint4*>(e.out + (((size_t)((c0 >> 3) + h) * g.N + n) * plane_out + pix_st) * 8) = o;
                 }
               }
             }
           }
           if (do_stats) {
+            float f1[16], f2[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { upk2(s1[j], f1[2 * j], f1[2 * j + 1]); upk2(s2[j], f2[2 * j], f2[2 * j + 1]); }
+            my_slot[(c16 * 16 + (lane & 15)) * 2 + (lane >> 4)] += warp_reduce_32x32(f1, f2, lane);
+          }
+        }
+      } else {
+        const f32x2 slope2 = pk2(do_act ? 0.2f : 1.0f, do_act ? 0.2f : 1.0f);
+        const bool has_res = g.aux_kind == 2 || e.addsrc != nullptr;
+        for (int cc = 0; cc < n_chunks; ++cc) {
+          const int cl = cc * 16;                                // first channel of the chunk inside the CTA's block
+          const int c0 = tc.ntile * g.cout_tile + cl;            // first output channel of this chunk
+          if (c0 >= e.Cout) break;
+          f32x2 s1[8], s2[8];
+          if (GEN) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s1[i] = 0ull; s2[i] = 0ull; }
+          }
+          // MMA tiles are dealt round-robin to the G warps of a quarter.  The per-pixel operands of the epilogue
+          // (noise value, residual vectors) come from the tile the producer staged in smem by TMA; the global
+          // loads below are only the fallback for layers the planner could not stage.
+          for (int u = egrp; u < n_units; u += G) {
+            uint32_t v[16];
+            tmem_ld16(acc_base + (uint32_t)(u * g.N_tile + cc * 16), v);
+            const Loc lc = locate(u);
+            int y = lc.y, x = lc.x;
+            if (e.up) { y = 2 * y + (tc.phase >> 1); x = 2 * x + (tc.phase & 1); }
+            const size_t pix = (size_t)y * e.Wo + x;
+            // phase-planar output: plane (y&1, x&1) of the block grid
+            const size_t pix_st = e.out_planar ? ((size_t)((y & 1) * 2 + (x & 1)) * (e.Ho >> 1) + (y >> 1)) * (e.Wo >> 1) + (x >> 1) : pix;
+            f32x2 nz = 0ull;
+            uint4 add0 = make_uint4(0, 0, 0, 0), add1 = add0;
+            if (lc.valid) {
+              if (GEN) {
+                float t1 = 0.f;
+                if (g.aux_kind == 1) t1 = reinterpret_cast<const float*>(aux)[(lc.nb * g.TH + lc.yl) * g.TW + lc.xl];
+                else if (e.noise) t1 = __ldg(e.noise + (size_t)lc.n * plane_out + pix);
+                nz = pk2(t1, t1);
+              }
+              if (g.aux_kind == 2) {
+                // residual tile [cb][nb][row/2][col/2] of 16-B vectors at half resolution
+                const int yy = (y >> 1) - (tc.y0 >> 1), xx = (x >> 1) - (tc.x0 >> 1);
+                const uint4* ap = reinterpret_cast<const uint4*>(aux) +
+                                  ((size_t)((cl >> 3) * g.NB + lc.nb) * g.aux_bh + yy) * g.aux_bw + xx;
+                add0 = ap[0];
+                add1 = ap[(size_t)g.NB * g.aux_bh * g.aux_bw];
+              } else if (e.addsrc) {
+                const size_t plane_lo = (size_t)(e.Ho >> 1) * (e.Wo >> 1);
+                const size_t pl = (size_t)(y >> 1) * (e.Wo >> 1) + (x >> 1);
+                const act_t* ap = e.addsrc + (((size_t)(c0 >> 3) * g.N + lc.n) * plane_lo + pl) * 8;
+                add0 = __ldg(reinterpret_cast<const uint4*>(ap));
+                add1 = __ldg(reinterpret_cast<const uint4*>(ap + (size_t)g.N * plane_lo * 8));
+              }
+            }
+            tmem_ld_wait();
+            if (lc.valid) {
+              const uint32_t w8[8] = {add0.x, add0.y, add0.z, add0.w, add1.x, add1.y, add1.z, add1.w};
+              uint32_t o[8];
+              f32x2 bias8[8], ns8[8];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const ulonglong2 bq = bias_s2[(c0 >> 2) + q];
+                bias8[2 * q] = bq.x; bias8[2 * q + 1] = bq.y;
+                ns8[2 * q] = 0ull; ns8[2 * q + 1] = 0ull;
+                if (GEN) { const ulonglong2 nq = ns_s2[(c0 >> 2) + q]; ns8[2 * q] = nq.x; ns8[2 * q + 1] = nq.y; }
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                f32x2 a = add2(pk2u(v[2 * j], v[2 * j + 1]), bias8[j]);
+                if (GEN) a = fma2(ns8[j], nz, a);
+                const f32x2 am = mul2(a, slope2);
+                float a0, a1, m0, m1;
+                upk2(a, a0, a1); upk2(am, m0, m1);
+                a0 = fmaxf(a0, m0); a1 = fmaxf(a1, m1);
+                if (has_res) {
+                  const float2 b2 = unpack_x2(w8[j]);
+                  a0 += b2.x; a1 += b2.y;
+                }
+                if (GEN) {
+                  const f32x2 ar = pk2(a0, a1);
+                  s1[j] = add2(s1[j], ar);
+                  s2[j] = fma2(ar, ar, s2[j]);
+                }
+                o[j] = pack_x2(a0, a1);
+              }
+              act_t* op = e.out + (((size_t)(c0 >> 3) * g.N + lc.n) * plane_out + pix_st) * 8;
+              *reinterpret_cast<uint4*>(op) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(op + (size_t)g.N * plane_out * 8) = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+          }
+          if (do_stats) {
             // value index = lane: 0..15 channel sums, 16..31 sums of squares; this warp's own slot: plain add
-            my_slot[(cl + (lane & 15)) * 2 + (lane >> 4)] += warp_reduce_32x32(s1, s2, lane);
+            float f1[16], f2[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { upk2(s1[j], f1[2 * j], f1[2 * j + 1]); upk2(s2[j], f2[2 * j], f2[2 * j + 1]); }
+            my_slot[(cl + (lane & 15)) * 2 + (lane >> 4)] += warp_reduce_32x32(f1, f2, lane);
           }
         }
       }

@@ -190,6 +190,25 @@ def test_config2_ffhq_1024_parity_one_sample():
     check(ref, out, dec, 'ffhq1024 n=1 psi=.7 fp16', 'fp16_1024')
 
 
+def test_config2_ffhq_1024_parity_two_latents():
+    """Same network, two distinct latents in one batch (seed 47): every sample is held to the full-size bounds."""
+    ref, out, dec, _ = run_both(10, 2, seed=47, psi=0.7)
+    check(ref, out, dec, 'ffhq1024 n=2 psi=.7 fp16', 'fp16_1024')
+    a = np.clip(out['img'].cpu().numpy(), -1, 1)
+    b = np.clip(ref['img_f32'], -1, 1)
+    for i in range(2):
+        assert psnr(a[i], b[i]) >= IMG_PSNR_DB
+    assert not np.array_equal(a[0], a[1])
+
+
+def test_config3_cars_384x512_full_size(dtype):
+    """BASELINE config 3 at its full size: StyleGAN-cars generator with the 3x4 base (max_res_log2 = 9 -> 384x512,
+    16 style layers) + decoder [32]*8+[2], two latents, against the CPU oracle."""
+    ref, out, dec, _ = run_both(9, 2, base=(3, 4), seed=51, psi=0.7, dtype=dtype)
+    assert out['img'].shape == (2, 3, 384, 512) and dec['mask'].shape == (2, 384, 512)
+    check(ref, out, dec, f'cars384x512 n=2 psi=.7 {dtype}', dtype)
+
+
 def test_ffhq_1024_size_independent_properties():
     """Full-size properties that need no oracle: batch-split invariance, mask == first-max argmax of the logits,
     uint8 image == the reference transform of the fp32 image, zero noise scale => noise has no effect."""
