@@ -85,7 +85,7 @@ _SIGS = {
     'gsx_op_sumpool2': (_i, [_fp, _fp, _i, _i, _i, _i, _vp]),
     'gsx_op_bn_lrelu_fwd': (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
     'gsx_op_bn_lrelu_bwd': (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
-    'gsx_softmax_ce': (_i, [_fp, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _sz, _vp]),
+    'gsx_softmax_ce': (_i, [_fp, _vp, _i, _i, _i, _i, _fp, _fp, C.c_float, _fp, _sz, _vp]),
     'gsx_adam_step': (_i, [_fp, _fp, _fp, _fp, _sz, _i, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
     'gsx_profile_enable': (_i, [_i]),
     'gsx_profile_dump': (_i, [C.c_char_p, _sz]),

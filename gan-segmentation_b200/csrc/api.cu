@@ -250,7 +250,7 @@ static int synth_stats_tiles(const gsx_synth* h, int l) {
 }
 
 extern "C" const char* gsx_last_error(void) { return last_error_cstr(); }
-extern "C" int gsx_abi_version(void) { return 1; }
+extern "C" int gsx_abi_version(void) { return 2; }
 extern "C" uint64_t gsx_launch_count(void) { return g_launches.load(); }
 
 extern "C" int gsx_synth_create(const gsx_synth_cfg* cfg, gsx_synth** out) {
@@ -399,7 +399,7 @@ extern "C" int gsx_synth_finalize(gsx_synth* h) {
       // epilogue into the conv -- removes the separate blur/noise/bias/lrelu/stats pass over the largest tensors
       // (measured r01: 16-channel 1024^2 layer 1.01 -> 0.81 ms; at 32 channels the heavier epilogue cancels the gain,
       //  GSX_FOLD_MAXC raises the limit for experiments)
-      const char* fm = getenv("GSX_FOLD_MAXC");
+      const char* fm = tune_env("GSX_FOLD_MAXC");
       const int fold_maxc = fm ? atoi(fm) : 16;
       if (deconv && b.C <= fold_maxc && b.C < 64) {
         set_error("");
@@ -430,7 +430,7 @@ extern "C" int gsx_synth_finalize(gsx_synth* h) {
       // after a folded deconv+blur the block's first half lives in a conv-produced tensor: store it phase-planar
       // (the in-place AdaIN pass does not care) and let conv_2 use the space-to-depth plan with dense boxes
       // (measured: conv_2 0.67 -> 0.58 ms, the producer's split stores cost 0.03 ms; GSX_PLANAR_G=0 turns it off)
-      const bool planar_in = b.fold && !(getenv("GSX_PLANAR_G") && atoi(getenv("GSX_PLANAR_G")) == 0) && !getenv("GSX_NO_S2D");
+      const bool planar_in = b.fold && !(tune_env("GSX_PLANAR_G") && atoi(tune_env("GSX_PLANAR_G")) == 0) && !tune_env("GSX_NO_S2D");
       plan_conv(b.conv2, CONV3, b.H, b.W, b.C, 0, b.C, 0, nullptr, /*aux: noise tile*/ 1, planar_in ? 1 : 0);
       if (*gsx_last_error()) return -1;
       if (planar_in) b.conv1.out_planar = 1;
@@ -749,9 +749,9 @@ extern "C" int gsx_dec_finalize(gsx_dec* d) {
   // phase-planar, so that the consumers can use the space-to-depth plan with dense TMA boxes (plan.cpp).
   // GSX_PLANAR: 0 = off, 1 = final conv only, 2 = also the last conv_b (default).
   const int topH = d->cfg.base_y << (nf - 1), topW = d->cfg.base_x << (nf - 1);
-  const int planar_env = getenv("GSX_PLANAR") ? atoi(getenv("GSX_PLANAR")) : 2;
+  const int planar_env = tune_env("GSX_PLANAR") ? atoi(tune_env("GSX_PLANAR")) : 2;
   const bool planar_ok = nf >= 2 && topH % 2 == 0 && topW % 2 == 0 && topH >= 16 && topW >= 16 &&
-                         d->cfg.features[nf - 1] <= 16 && !getenv("GSX_NO_S2D");
+                         d->cfg.features[nf - 1] <= 16 && !tune_env("GSX_NO_S2D");
   const bool planar_final = planar_ok && planar_env >= 1;
   const bool planar_cb = planar_ok && planar_env >= 2;
   for (int i = 0; i < nf; ++i) {

@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -36,6 +37,13 @@ __host__ __device__ inline act_t to_act(float v) {
   return __float2bfloat16(v);
 #endif
 }
+
+// Tuning builds (make TUNING=1): the GSX_* environment switches of the planner / forward passes and the kernel's role-
+// isolation switches (GSX_DBG) are live.  The release build ignores the environment and compiles the switches out.
+#ifndef GSX_TUNING
+#define GSX_TUNING 0
+#endif
+inline const char* tune_env(const char* name) { return GSX_TUNING ? std::getenv(name) : nullptr; }
 
 static const int kConvHeaderBytes = 2048;    // shiftconv smem header: mbarriers + tmem slot
 

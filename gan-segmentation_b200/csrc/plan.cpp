@@ -28,9 +28,9 @@ bool cuda_ok(cudaError_t e, const char* what) {
 // and does its prologue (barriers, TMEM, resident weights) under the predecessor's tail.
 static thread_local bool g_pdl_small = false, g_pdl_chain = false, g_prev_conv = false;
 void pdl_set_for_work(double top_level_pixels) {
-  static const int mode = getenv("GSX_NO_PDL") ? 0 : (getenv("GSX_PDL") ? 2 : 1);     // off / by size / always
+  static const int mode = tune_env("GSX_NO_PDL") ? 0 : (tune_env("GSX_PDL") ? 2 : 1);     // off / by size / always
   g_pdl_small = mode == 2 || (mode == 1 && top_level_pixels <= 2.0 * 1024 * 1024);
-  g_pdl_chain = mode != 0 && !getenv("GSX_NO_PDL_CHAIN");
+  g_pdl_chain = mode != 0 && !tune_env("GSX_NO_PDL_CHAIN");
 }
 bool pdl_enabled(int kind) {
   const bool on = g_pdl_small || (g_pdl_chain && kind == 1 && g_prev_conv);
@@ -99,9 +99,9 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   // Measured (r01, FFHQ batch 32): the phase-plane gather (TMA boxes with a 16-byte inner extent) is slow -- loads
   // alone take as long as the whole dense-layout kernel -- so by default only the final conv + argmax uses it
   // (0.85 -> 0.73 ms); GSX_S2D=1 enables it for every eligible layer.
-  static const int s2d_all = getenv("GSX_S2D") ? atoi(getenv("GSX_S2D")) : 0;
+  static const int s2d_all = tune_env("GSX_S2D") ? atoi(tune_env("GSX_S2D")) : 0;
   int s2d = (mode == CONV3 && cin0 + cin1 <= 32 && cout <= 32 && H % 2 == 0 && W % 2 == 0 && H >= 16 && W >= 16 &&
-             (argmax_classes > 0 || in_planar || (s2d_all && cout <= 16 && aux_kind != 2)) && !getenv("GSX_NO_S2D")) ? 1 : 0;
+             (argmax_classes > 0 || in_planar || (s2d_all && cout <= 16 && aux_kind != 2)) && !tune_env("GSX_NO_S2D")) ? 1 : 0;
   if (ov && ov->s2d >= 0 && mode == CONV3 && H % 2 == 0 && W % 2 == 0) s2d = ov->s2d;
   if (in_planar && !s2d) { set_error("plan_conv: a phase-planar input needs the space-to-depth plan"); return; }
   if (s2d) { H /= 2; W /= 2; }               // from here on H, W, TH, TW count blocks

@@ -28,7 +28,11 @@
 
 #include <cstdlib>
 
-// tuning builds only: -DGSX_EPI_LITE=1 compiles every epilogue body out (code-size experiments)
+// tuning builds only (make TUNING=1 -> -DGSX_TUNING=1): the role-isolation switches of g.dbg (env GSX_DBG, tools/roles.sh)
+// exist in the kernel; the release build compiles them out.  -DGSX_EPI_LITE=1 compiles every epilogue body out.
+#ifndef GSX_TUNING
+#define GSX_TUNING 0
+#endif
 #ifndef GSX_EPI_LITE
 #define GSX_EPI_LITE 0
 #endif
@@ -46,7 +50,7 @@ struct __align__(16) SmemHeader {
   uint64_t aux_full[2];
   uint64_t aux_empty[2];
   uint32_t tmem_base;
-  uint32_t pad;
+  uint32_t stats_cnt[2];      // epilogue warps that have finished the statistics of the tile in slot buffer 0 / 1
   uint2 sched[64 + 16];       // per (phase, slot, k16 step): {A offset, B offset} in 16-byte units (+16: group over-read)
 };
 static_assert(sizeof(SmemHeader) <= kConvHeaderBytes, "header too large");
@@ -168,7 +172,10 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int t) {
 
 // GEN = the generator's epilogues (noise, InstanceNorm statistics, deconv+blur border correction); the decoder / raw
 // variant compiles those paths out (127 instead of 168 registers).  G = epilogue warps per TMEM lane quarter.
-template <int G, bool GEN>
+// MODE = which epilogue the instantiation contains (one per kernel: the three bodies together cost instruction-cache
+// misses -- 11 % of the warp stalls of the r01 kernel were "no instruction").
+enum { kEpiGeneric = 0, kEpiUpCols = 1, kEpiArgmax = 2 };
+template <int G, bool GEN, int MODE>
 __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid_constant__ ConvParams p) {
   constexpr int kEpiWarps = 4 * G;
   constexpr int kEpiThreads = 128 * G;
@@ -196,6 +203,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
       mbar_init(&hdr->tmem_empty[b], kEpiWarps);
     }
     mbar_init(&hdr->bres_full, 1);
+    hdr->stats_cnt[0] = 0; hdr->stats_cnt[1] = 0;
     for (int b = 0; b < 2; ++b) {
       mbar_init(&hdr->aux_full[b], 1);
       mbar_init(&hdr->aux_empty[b], kEpiWarps);
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
           const int s = it % g.stages;
           const int round = it / g.stages;
           if (round > 0) mbar_wait_relaxed(&hdr->empty[s], (uint32_t)((round - 1) & 1));
-          if (g.dbg & 4) { mbar_arrive(&hdr->full[s]); continue; }
+          if (GSX_TUNING && (g.dbg & 4)) { mbar_arrive(&hdr->full[s]); continue; }
           mbar_expect_tx(&hdr->full[s], stage_bytes);
           const int src = kc < g.kch0 ? 0 : 1;
           const int cb0 = (src ? kc - g.kch0 : kc) * g.CBK;
@@ -296,7 +304,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     const uint32_t a_lbo = (((uint32_t)g.cb_stride_bytes >> 4) & 0x3FFF) << 16;      // low-word part of the A descriptor
     const uint32_t b_lbo = ((((uint32_t)g.N_tile * 16) >> 4) & 0x3FFF) << 16;
     int n_k = g.n_k, stages = g.stages, n_mtiles = g.n_mtiles;
-    const int sched_len = (g.dbg & 2) ? 0 : g.n_slots * (g.CBK >> 1);      // MMAs per (k-chunk, MMA tile)
+    const int sched_len = (GSX_TUNING && (g.dbg & 2)) ? 0 : g.n_slots * (g.CBK >> 1);      // MMAs per (k-chunk, MMA tile)
     const int b_res = g.b_resident;
     uint32_t a_stride = (uint32_t)g.a_stage_stride, b_stride = (uint32_t)g.b_stage_bytes;
     uint32_t n_tile = (uint32_t)g.N_tile;
@@ -326,7 +334,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
       tc_fence_after();
       const uint32_t acc_base = tmem_base + (uint32_t)(buf * cols_per_buf);
       for (int kc = 0; kc < n_k; ++kc) {
-        if (!(g.dbg & 8)) mbar_wait(&hdr->full[s], full_par);
+        if (!(GSX_TUNING && (g.dbg & 8))) mbar_wait(&hdr->full[s], full_par);
         // descriptor low words: start address (16-B units) | LBO << 16
         const uint32_t a_lo0 = (((a_smem + (uint32_t)s * a_stride) >> 4) & 0x3FFF) | a_lbo;
         const uint32_t b_lo0 = (((b_smem + (uint32_t)(b_res ? kc : s) * b_stride) >> 4) & 0x3FFF) | b_lbo;
@@ -407,12 +415,14 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
       const TileCoord tc = decode_tile(g, t);
       const int buf = tl % nbuf;
       float* my_slot = stats_slots + ((size_t)(tl & 1) * kEpiWarps + ew) * slot_floats;
+      mbar_wait_relaxed<64>(&hdr->tmem_full[buf], (uint32_t)((tl / nbuf) & 1));
+      tc_fence_after();
       if (do_stats) {
+        // (after the wait: the accumulators of this tile exist only once every warp has handed back the tile two
+        //  before -- i.e. after the last reader of this slot buffer has finished, see the combine below)
         for (int i = lane; i < slot_floats; i += 32) my_slot[i] = 0.f;
         __syncwarp();
       }
-      mbar_wait_relaxed<64>(&hdr->tmem_full[buf], (uint32_t)((tl / nbuf) & 1));
-      tc_fence_after();
       const int ab = tl & 1;
       const uint8_t* aux = smem + g.aux_off + (size_t)ab * g.aux_bytes;
       if (g.aux_kind) mbar_wait_relaxed<32>(&hdr->aux_full[ab], (uint32_t)((tl >> 1) & 1));
@@ -431,8 +441,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         return l;
       };
 
-      if (GSX_EPI_LITE || (g.dbg & 1)) {
-      } else if ((e.flags & EPI_ARGMAX) && g.up_cols) {
+      if (GSX_EPI_LITE || (GSX_TUNING && (g.dbg & 1))) {
+      } else if (MODE == kEpiArgmax && g.up_cols) {
         // s2d final conv: the 4 output phases of a block are column groups of cout_tile (4, 8 or 16) classes
         for (int u = egrp; u < n_units; u += G) {
           const Loc lc = locate(u);
@@ -449,7 +459,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
             }
           }
         }
-      } else if (e.flags & EPI_ARGMAX) {
+      } else if (MODE == kEpiArgmax) {
         for (int mt = egrp; mt < g.n_mtiles; mt += G) {
           uint32_t v[16];
           tmem_ld16(acc_base + (uint32_t)(mt * g.N_tile), v);
@@ -472,7 +482,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
             e.mask[(size_t)n * plane_out + pix] = (unsigned char)arg;
           }
         }
-      } else if (g.up_cols) {
+      } else if (MODE == kEpiUpCols) {
         // up-conv with the 4 phases as column blocks: the px=0 / px=1 outputs of a low-res pixel are adjacent in
         // the output row, so both phases are processed together and leave as ONE 32-byte store per channel block
         // (full sectors instead of two half-sector writes).  GEN adds the generator's first-half epilogue for the
@@ -693,26 +703,37 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         }
       }
 
+      if (do_stats) {
+        // Fused stats need a single sample per CTA tile (NB == 1); enforced by the callers.  One partial per
+        // (sample, tile), summed over the per-warp slots in a fixed order by whichever warp finishes the tile last
+        // (a counter instead of a barrier: nobody waits) -> bit-reproducible, finalize_kernel adds the tiles up.
+        // The slot buffer (tl & 1) is reused two tiles later; by then every warp has handed this tile's accumulator
+        // back (below, AFTER the combine), which the MMAs of that later tile wait for.
+        __syncwarp();
+        uint32_t arrived = 0;
+        if (lane == 0) { __threadfence_block(); arrived = atomicAdd(&hdr->stats_cnt[tl & 1], 1u); }
+        arrived = __shfl_sync(0xffffffffu, arrived, 0);
+        if (arrived == (uint32_t)kEpiWarps - 1) {
+          __threadfence_block();
+          const float* slots = stats_slots + (size_t)(tl & 1) * kEpiWarps * slot_floats;
+          for (int i = lane; i < slot_floats; i += 32) {
+            const int ch = tc.ntile * g.cout_tile + (i >> 1);
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kEpiWarps; ++w) s += slots[w * slot_floats + i];
+            if (ch < e.Cout) e.stats[(((size_t)tc.n0 * e.stats_T + tc.tile_in_sample) * e.Cout + ch) * 2 + (i & 1)] = s;
+          }
+          __syncwarp();
+          if (lane == 0) hdr->stats_cnt[tl & 1] = 0;
+        }
+      }
+
       // accumulator buffer drained -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&hdr->tmem_empty[buf]);
         if (g.aux_kind) mbar_arrive(&hdr->aux_empty[ab]);
-      }
-
-      if (do_stats) {
-        named_bar_sync(1, kEpiThreads);                          // all epilogue warps finished this tile
-        // fused stats need a single sample per CTA tile (NB == 1); enforced by the callers.  Fixed summation
-        // order + one partial per (sample, tile): bit-reproducible, finalize_kernel adds the tiles up.
-        const float* slots = stats_slots + (size_t)(tl & 1) * kEpiWarps * slot_floats;
-        for (int i = threadIdx.x - 64; i < slot_floats; i += kEpiThreads) {
-          const int ch = tc.ntile * g.cout_tile + (i >> 1);
-          float s = 0.f;
-#pragma unroll
-          for (int w = 0; w < kEpiWarps; ++w) s += slots[w * slot_floats + i];
-          if (ch < e.Cout) e.stats[(((size_t)tc.n0 * e.stats_T + tc.tile_in_sample) * e.Cout + ch) * 2 + (i & 1)] = s;
-        }
       }
     }
   }
@@ -729,15 +750,15 @@ static int current_device() {
   return dev < 0 ? 0 : (dev > 63 ? 63 : dev);
 }
 
-template <int G, bool GEN>
+template <int G, bool GEN, int MODE>
 static void launch_g(const ConvParams& p, int grid, cudaStream_t st) {
   static bool configured[64] = {false};
   const int dev = current_device();
   if (!configured[dev]) {
-    cudaFuncSetAttribute(shiftconv_kernel<G, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(shiftconv_kernel<G, GEN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured[dev] = true;
   }
-  launch_pdl_kind(1, shiftconv_kernel<G, GEN>, dim3(grid), dim3(64 + 128 * G), (size_t)p.g.smem_bytes, st, p);
+  launch_pdl_kind(1, shiftconv_kernel<G, GEN, MODE>, dim3(grid), dim3(64 + 128 * G), (size_t)p.g.smem_bytes, st, p);
 }
 
 void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
@@ -747,11 +768,20 @@ void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
   const ConvGeom& g = p.g;
   const int total = g.tiles_x * g.tiles_y * g.tiles_n * g.n_ntiles * (g.phase_grid ? 4 : 1);
   const int grid = total < num_sms[dev] * g.ctas_per_sm ? total : num_sms[dev] * g.ctas_per_sm;
+#if GSX_TUNING
   static const int dbg = getenv("GSX_DBG") ? atoi(getenv("GSX_DBG")) : 0;
-  if (dbg) const_cast<ConvParams&>(p).g.dbg = dbg;
+  ConvParams q = p;
+  if (dbg) q.g.dbg = dbg;
+  const ConvParams& pp = q;
+#else
+  const ConvParams& pp = p;
+#endif
   const bool gen = p.e.noise != nullptr || p.e.nscale != nullptr || (p.e.flags & EPI_STATS) != 0 || p.e.e_rows != nullptr;
-  if (gen) launch_g<2, true>(p, grid, st);     // generator epilogues: noise + statistics (+ border correction)
-  else launch_g<2, false>(p, grid, st);
+  if (p.e.flags & EPI_ARGMAX) launch_g<2, false, kEpiArgmax>(pp, grid, st);
+  else if (gen && g.up_cols) launch_g<2, true, kEpiUpCols>(pp, grid, st);    // generator epilogues: noise + statistics (+ border)
+  else if (gen) launch_g<2, true, kEpiGeneric>(pp, grid, st);
+  else if (g.up_cols) launch_g<2, false, kEpiUpCols>(pp, grid, st);
+  else launch_g<2, false, kEpiGeneric>(pp, grid, st);
 }
 
 }  // namespace gsx

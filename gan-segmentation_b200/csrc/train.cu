@@ -1,8 +1,11 @@
-// Building blocks of decoder training (reference seg_solver.py:351-465).  Round 1
-// ships the loss and the optimizer step; the decoder backward pass (dgrad / wgrad / BatchNorm) is not built yet.
+// Building blocks of decoder training (reference seg_solver.py:351-465): loss, weight
+// gradient, BatchNorm / upsample forward+backward kernels and the optimizer step; gan-segmentation_b200/decoder_training.py
+// composes them (with the conv kernel of shiftconv.cu for the forward pass and the data gradients).
 //   softmax_ce : SoftmaxCELoss(axis=1) with sample_weight = (mask > -1) (seg_solver.py:404-407): per-sample loss =
 //                mean over ALL H*W pixels of -w * log_softmax(logits)[label] (ignored pixels stay in the denominator),
-//                and its gradient w * (softmax - onehot) / (H*W).
+//                and its gradient w * (softmax - onehot) / (H*W), times `grad_scale`: the backward pass runs its data
+//                gradients through 16-bit tensors, 1/(H*W) = 9.5e-7 at 1024^2 is below the fp16 normal range, so the
+//                caller passes grad_scale = H*W and folds 1/grad_scale into Adam's rescale_grad.
 //   adam_step  : MXNet Adam on one flat fp32 bucket (all decoder parameters): bias correction folded into the
 //                learning rate, rescale_grad = 1/batch (trainer.step(batch), seg_solver.py:421), eps 1e-8.
 //                Runs right after the single all-reduce of the flat gradient bucket.
@@ -20,12 +23,13 @@ static constexpr int kCeThreads = 256;
 // grid (blocks, N); each block reduces its pixels to one partial loss (fixed order), summed by a second tiny kernel
 __global__ void __launch_bounds__(kCeThreads) softmax_ce_kernel(const float* __restrict__ logits, const int* __restrict__ labels,
                                                                 float* __restrict__ dlogits, float* __restrict__ partial,
-                                                                int K, int HW) {
+                                                                int K, int HW, float grad_scale) {
   const int n = blockIdx.y;
   const float* lg = logits + (size_t)n * K * HW;
   float* dl = dlogits ? dlogits + (size_t)n * K * HW : nullptr;
   const int* lab = labels + (size_t)n * HW;
   const float inv_hw = 1.f / (float)HW;
+  const float gs = grad_scale * inv_hw;       // grad_scale = H*W keeps the gradient O(1) for the 16-bit backward pass
   float acc = 0.f;
   for (int p = blockIdx.x * kCeThreads + threadIdx.x; p < HW; p += gridDim.x * kCeThreads) {
     const int l = lab[p];
@@ -40,7 +44,7 @@ __global__ void __launch_bounds__(kCeThreads) softmax_ce_kernel(const float* __r
     if (dl) {
       for (int k = 0; k < K; ++k) {
         const float sm = expf(lg[(size_t)k * HW + p] - lse);
-        dl[(size_t)k * HW + p] = w * (sm - (k == lc ? 1.f : 0.f)) * inv_hw;
+        dl[(size_t)k * HW + p] = w * (sm - (k == lc ? 1.f : 0.f)) * gs;
       }
     }
   }
@@ -369,14 +373,14 @@ extern "C" int gsx_op_bn_lrelu_bwd(const float* dy_dev, const float* z_dev, cons
 }
 
 extern "C" int gsx_softmax_ce(const float* logits_dev, const int* labels_dev, int n, int num_classes, int h, int w,
-                              float* loss_dev, float* dlogits_dev, float* scratch_dev, size_t scratch_floats,
-                              gsx_stream stream) {
+                              float* loss_dev, float* dlogits_dev, float grad_scale, float* scratch_dev,
+                              size_t scratch_floats, gsx_stream stream) {
   if (!logits_dev || !labels_dev || !loss_dev || !scratch_dev || n <= 0) { set_error("bad argument"); return -1; }
   const int HW = h * w;
   const int blocks = std::min(256, (HW + kCeThreads - 1) / kCeThreads);
   if (scratch_floats < (size_t)n * blocks) { set_error("scratch too small (needs n*256 floats)"); return -1; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  softmax_ce_kernel<<<dim3(blocks, n), kCeThreads, 0, st>>>(logits_dev, labels_dev, dlogits_dev, scratch_dev, num_classes, HW);
+  softmax_ce_kernel<<<dim3(blocks, n), kCeThreads, 0, st>>>(logits_dev, labels_dev, dlogits_dev, scratch_dev, num_classes, HW, grad_scale);
   ce_finish_kernel<<<n, 32, 0, st>>>(scratch_dev, loss_dev, blocks);
   g_launches += 2;
   return cuda_ok(cudaGetLastError(), "softmax_ce") ? 0 : -2;

@@ -62,7 +62,8 @@ class DecoderTrainer:
 
     # ---- forward + backward ----------------------------------------------------------------------------------
     def loss_and_grads(self, feats, mask, dropout_masks=None):
-        """feats: list of [N,C_i,H_i,W_i]; mask [N,1,H,W] int in {-1,0..K-1}.  Returns (per-sample loss, grads dict)."""
+        """feats: list of [N,C_i,H_i,W_i]; mask [N,1,H,W] int in {-1,0..K-1}.  Returns (per-sample loss, grads dict);
+        the gradients are ``self._grad_scale`` times d(sum of the per-sample losses)/d(parameter)."""
         be, P, nf = self.be, self.P, self.nf
         self._new_stats = {}
         feats = [be.tensor(f) for f in feats]
@@ -96,7 +97,9 @@ class DecoderTrainer:
                 p = f'main_block_{i}.0'
                 logits = be.conv(xin, P[f'{p}.weight'], P[f'{p}.bias'], 3)
                 lv.append(dict(xin=xin, p=p))
-        loss, dlog = be.softmax_ce(logits, mask)
+        # the backend may return the gradient multiplied by a power-of-two-ish scale (H*W on the CUDA backend: its data
+        # gradients travel through 16-bit tensors); every later step is linear in it, the optimizer divides it out
+        loss, dlog, self._grad_scale = be.softmax_ce(logits, mask)
 
         # backward
         d_prev = None
@@ -148,7 +151,7 @@ class DecoderTrainer:
         (trainer.step(batch), seg_solver.py:421).  Returns the per-sample loss of this rank."""
         loss, grads = self.loss_and_grads(feats, mask, dropout_masks)
         n = int(np.asarray(mask).shape[0]) if not torch.is_tensor(mask) else int(mask.shape[0])
-        self.opt.apply(grads, global_batch or n, group)
+        self.opt.apply(grads, global_batch or n, group, self._grad_scale)
         for k, v in self._new_stats.items():
             self.P[k] = v
         return loss
@@ -264,8 +267,9 @@ class CudaBackend:
 
     def softmax_ce(self, logits, mask):
         m = torch.as_tensor(np.asarray(mask) if not torch.is_tensor(mask) else mask).to(self.device)
-        loss, dl = self.tr.softmax_ce(logits, m.int(), want_grad=True, dtype=self.dtype)
-        return loss, dl
+        scale = float(logits.shape[2] * logits.shape[3])
+        loss, dl = self.tr.softmax_ce(logits, m.int(), want_grad=True, dtype=self.dtype, grad_scale=scale)
+        return loss, dl, scale
 
     # -- optimizer: one flat bucket, one all-reduce, one fused Adam kernel
     def make_adam(self, shapes, P, lr, wd):
@@ -280,10 +284,10 @@ class _FlatAdamAdapter:
             P[k] = self.flat.view(self.flat.w, k)
         self.names = list(shapes)
 
-    def apply(self, grads, batch, group=None):
+    def apply(self, grads, batch, group=None, grad_scale=1.0):
         for k in self.names:
             self.flat.view(self.flat.g, k).copy_(grads[k])
-        self.flat.step(batch, group)
+        self.flat.step(batch, group, grad_scale)
 
     def export(self, P):
         return dict(P)

@@ -1,6 +1,6 @@
-"""Decoder-training building blocks over the C ABI (reference seg_solver.py:351-465): the loss, and the flat-bucket
-gradient all-reduce + Adam step that replaces the reference's per-parameter KVStore('nccl') push/pull
-(seg_solver.py:55-56,421).  The decoder backward pass itself is not built in round 1.
+"""Decoder-training building blocks over the C ABI (reference seg_solver.py:351-465): the loss, the conv weight
+gradient, and the flat-bucket gradient all-reduce + Adam step that replaces the reference's per-parameter
+KVStore('nccl') push/pull (seg_solver.py:55-56,421).  ``decoder_training.DecoderTrainer`` composes them into the step.
 """
 from __future__ import annotations
 
@@ -16,9 +16,10 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def softmax_ce(logits, labels, want_grad=True, dtype=None):
+def softmax_ce(logits, labels, want_grad=True, dtype=None, grad_scale=1.0):
     """logits [N,K,H,W] fp32 cuda, labels [N,1,H,W] or [N,H,W] int32 (-1 = ignore).
-    Returns (loss [N], dlogits or None) with the reference's semantics (mean over all pixels, ignored ones weigh 0)."""
+    Returns (loss [N], grad_scale * dlogits or None) with the reference's semantics (mean over all pixels, ignored
+    ones weigh 0).  Training passes grad_scale = H*W (see gsx.h) and divides it out again in the optimizer step."""
     lib = L.lib(dtype)
     n, k, h, w = logits.shape
     logits = logits.contiguous()
@@ -26,7 +27,7 @@ def softmax_ce(logits, labels, want_grad=True, dtype=None):
     loss = torch.empty(n, dtype=torch.float32, device=logits.device)
     dl = torch.empty_like(logits) if want_grad else None
     scratch = torch.empty(n * 256, dtype=torch.float32, device=logits.device)
-    L.check(lib.gsx_softmax_ce(L.ptr(logits), L.ptr(labels), n, k, h, w, L.ptr(loss), L.ptr(dl), L.ptr(scratch),
+    L.check(lib.gsx_softmax_ce(L.ptr(logits), L.ptr(labels), n, k, h, w, L.ptr(loss), L.ptr(dl), float(grad_scale), L.ptr(scratch),
                                scratch.numel(), _stream()), 'gsx_softmax_ce', dtype)
     return loss, dl
 
@@ -71,22 +72,24 @@ class FlatAdam:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.g, op=dist.ReduceOp.SUM, group=group)
 
-    def step(self, global_batch, group=None):
+    def step(self, global_batch, group=None, grad_scale=1.0):
+        """``grad_scale``: the factor the loss gradient was multiplied by for the 16-bit backward pass (divided out
+        here, through Adam's rescale_grad)."""
         self.allreduce_grads(group)
         self.t += 1
         if self.device.type != 'cuda':
             raise RuntimeError('FlatAdam.step needs a CUDA device: there is no CPU fallback')
         lib = L.lib(self.dtype)
         L.check(lib.gsx_adam_step(L.ptr(self.w), L.ptr(self.g), L.ptr(self.m), L.ptr(self.v), self.count, self.t, self.lr,
-                                  self.beta1, self.beta2, self.eps, self.wd, 1.0 / float(global_batch), _stream()),
+                                  self.beta1, self.beta2, self.eps, self.wd, 1.0 / (float(global_batch) * float(grad_scale)), _stream()),
                 'gsx_adam_step', self.dtype)
 
 
 def dgrad_weights(weight):
     """Weights that turn the forward 3x3 / 1x1 conv kernel into its own data gradient:
     ``dX = conv(dY, dgrad_weights(W))`` for ``Y = conv(X, W)`` (stride 1, 'same' padding) -- channels swapped,
-    taps flipped.  The decoder's dgrad therefore runs on the existing tcgen05 shift-GEMM kernel; only the weight
-    gradient and the BatchNorm backward need new kernels (not built yet).  weight: [Cout,Cin,k,k] numpy."""
+    taps flipped.  The decoder's dgrad therefore runs on the existing tcgen05 shift-GEMM kernel; the weight gradient and
+    the BatchNorm backward have their own kernels (csrc/train.cu).  weight: [Cout,Cin,k,k] numpy."""
     w = np.asarray(weight, np.float32)
     return np.ascontiguousarray(np.transpose(w, (1, 0, 2, 3))[:, :, ::-1, ::-1])
 

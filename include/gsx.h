@@ -82,7 +82,7 @@ int gsx_synth_feature_shape(const gsx_synth* h, int level, int* c, int* hgt, int
  * parameter, else num_layers floats.  noise_dev: NULL -> Philox, else num_layers device pointers to
  * [n,1,h,w] fp32 (the planes AddNoise samples at networks_stylegan.py:300).  Outputs (each nullable):
  * img_f32_dev [n,3,H,W], img_u8_dev [n,H,W,3] (image_generator.py:76-84), feats_f32_dev[level] [n,C,h,w].
- * Blocked bf16 features stay in the workspace for gsx_dec_forward. */
+ * The blocked 16-bit features stay in the workspace for gsx_dec_forward. */
 int gsx_synth_forward(gsx_synth* h, int n, const float* z_dev, const float* psi_host,
                       const float* const* noise_dev, uint64_t seed, uint64_t first_sample, float* img_f32_dev,
                       uint8_t* img_u8_dev, float* const* feats_f32_dev, void* ws, size_t ws_bytes,
@@ -116,11 +116,13 @@ int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z_host, cons
                       size_t synth_ws_bytes, void* dec_ws, size_t dec_ws_bytes, void* stage_dev,
                       size_t stage_bytes, gsx_stream stream, gsx_stream copy_stream, int slot);
 
-/* ---- decoder-training building blocks (seg_solver.py:351-465).  Round 1: loss and optimizer step only; the
- *      decoder backward pass is not built yet.
+/* ---- decoder-training building blocks (seg_solver.py:351-465): loss, weight gradient, BatchNorm / upsample kernels,
+ *      optimizer step (the conv forward / data gradient go through gsx_op_conv).
  * gsx_softmax_ce: SoftmaxCELoss(axis=1) with sample_weight = (label > -1) (seg_solver.py:404-407).
  *   logits [n,classes,h,w] fp32, labels [n,h,w] int32 (-1 = ignore) -> loss_dev[n] (mean over all h*w pixels) and,
- *   if dlogits_dev != NULL, d(sum_n loss_n)/dlogits.  scratch_dev: n*256 floats.
+ *   if dlogits_dev != NULL, grad_scale * d(sum_n loss_n)/dlogits.  grad_scale = h*w keeps the gradient O(1) through
+ *   the 16-bit backward pass (1/(h*w) is an fp16 sub-normal at 1024^2); fold 1/grad_scale into gsx_adam_step's
+ *   rescale_grad.  scratch_dev: n*256 floats.
  * gsx_adam_step: MXNet Adam on one flat fp32 bucket after the single gradient all-reduce (seg_solver.py:56,421):
  *   lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t), g' = g*rescale_grad + wd*w. ---- */
 /* Weight / bias gradient of a stride-1 'same' k x k conv (k = 1 or 3), fp32 NCHW in (converted to the blocked 16-bit
@@ -141,7 +143,8 @@ int gsx_op_bn_lrelu_bwd(const float* dy_dev, const float* z_dev, const float* st
                         const float* beta_dev, const float* drop_dev, float* dz_dev, float* dparam_dev, int n, int c, int hw,
                         gsx_stream stream);
 int gsx_softmax_ce(const float* logits_dev, const int* labels_dev, int n, int num_classes, int h, int w,
-                   float* loss_dev, float* dlogits_dev, float* scratch_dev, size_t scratch_floats, gsx_stream stream);
+                   float* loss_dev, float* dlogits_dev, float grad_scale, float* scratch_dev, size_t scratch_floats,
+                   gsx_stream stream);
 int gsx_adam_step(float* w_dev, const float* g_dev, float* m_dev, float* v_dev, size_t count, int t, float lr, float beta1,
                   float beta2, float eps, float wd, float rescale_grad, gsx_stream stream);
 

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(gsx_lib, dtype):
     for s in syms:
         assert hasattr(lib, s), f'{s} declared in include/gsx.h but not exported'
     assert set(syms) == set(L.EXPORTS)
-    assert lib.gsx_abi_version() == 1
+    assert lib.gsx_abi_version() == 2
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -13,7 +13,7 @@ class _Adam:
         self.m = {k: torch.zeros(s, dtype=torch.float64) for k, s in shapes.items()}
         self.v = {k: torch.zeros(s, dtype=torch.float64) for k, s in shapes.items()}
 
-    def apply(self, grads, batch, group=None):
+    def apply(self, grads, batch, group=None, grad_scale=1.0):
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             grads = dict(grads)
@@ -25,7 +25,7 @@ class _Adam:
         lr_t = self.lr * np.sqrt(1 - 0.999 ** self.t) / (1 - 0.9 ** self.t)
         for k in self.names:
             w = self.P[k].double()
-            g = grads[k].double() / batch + self.wd * w
+            g = grads[k].double() / (batch * grad_scale) + self.wd * w
             self.m[k] = 0.9 * self.m[k] + 0.1 * g
             self.v[k] = 0.999 * self.v[k] + 0.001 * g * g
             self.P[k] = (w - lr_t * self.m[k] / (self.v[k].sqrt() + 1e-8)).float()
@@ -107,4 +107,4 @@ class TorchBackend:
         loss = (-torch.gather(lp, 1, mask.clamp(min=0)) * w).mean(dim=(1, 2, 3))
         onehot = torch.zeros_like(logits).scatter_(1, mask.clamp(min=0), 1.0)
         hw = logits.shape[2] * logits.shape[3]
-        return loss, w * (lp.exp() - onehot) / hw
+        return loss, w * (lp.exp() - onehot) / hw, 1.0
