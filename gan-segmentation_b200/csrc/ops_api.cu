@@ -12,7 +12,15 @@ extern std::atomic<uint64_t> g_launches;
 
 struct Tmp {
   std::vector<void*> ptrs;
-  ~Tmp() { for (void* p : ptrs) pool_put(p); }
+  cudaStream_t st = nullptr;
+  bool has_stream = false;
+  // A block goes back to the pool only when nothing enqueued by this call can still touch it -- also on the early
+  // error returns, where copies / conversion kernels may already be in flight (the success paths have synchronised,
+  // for them this is a no-op).
+  ~Tmp() {
+    if (has_stream) cudaStreamSynchronize(st);
+    for (void* p : ptrs) pool_put(p);
+  }
   template <class T> T* get(size_t n) {
     void* p = pool_get(std::max<size_t>(n, 1) * sizeof(T));
     if (!p) return nullptr;
@@ -34,6 +42,7 @@ extern "C" int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, in
   const bool argmax = (flags & EPI_ARGMAX) != 0;
   const int Ho = up ? 2 * h : h, Wo = up ? 2 * w : w;
   Tmp tmp;
+  tmp.st = st; tmp.has_stream = true;
   set_error("");
   ConvLayer L;
   PlanOverride po{};
@@ -149,6 +158,7 @@ extern "C" int gsx_op_pass1(int n, int c, int h, int w, const float* x_dev, int 
                             float* stats_dev, gsx_stream stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Tmp tmp;
+  tmp.st = st; tmp.has_stream = true;
   const int nin = in_broadcast ? 1 : n;
   act_t* xb = tmp.get<act_t>((size_t)nin * c * h * w);
   act_t* ob = tmp.get<act_t>((size_t)n * c * h * w);
@@ -170,6 +180,7 @@ extern "C" int gsx_op_apply(int n, int c, int h, int w, const float* x_dev, cons
                             float* img_f32_dev, uint8_t* img_u8_dev, gsx_stream stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Tmp tmp;
+  tmp.st = st; tmp.has_stream = true;
   act_t* xb = tmp.get<act_t>((size_t)n * c * h * w);
   act_t* ob = tmp.get<act_t>((size_t)n * c * h * w);
   if (!xb || !ob) { set_error("cudaMalloc failed"); return -2; }

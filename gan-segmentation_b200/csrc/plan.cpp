@@ -39,15 +39,19 @@ bool pdl_enabled(int kind) {
 }
 
 namespace {
-struct PoolBlock { void* p; size_t size; bool used; };
+struct PoolBlock { void* p; size_t size; bool used; int dev; };
 thread_local std::vector<PoolBlock> g_pool;
+int cur_dev() { int d = 0; cudaGetDevice(&d); return d; }
 }
+// Blocks belong to the device they were allocated on: one host thread may drive several GPUs
+// (ImageGenerator(gpu_ids=[0,1,..]) / torch.cuda.device guards), and a block of another device must never be handed out.
 void* pool_get(size_t bytes) {
   if (bytes == 0) bytes = 256;
+  const int dev = cur_dev();
   int best = -1;
   for (int i = 0; i < (int)g_pool.size(); ++i) {
     const PoolBlock& b = g_pool[i];
-    if (!b.used && b.size >= bytes && b.size <= 2 * bytes + (1 << 20) && (best < 0 || b.size < g_pool[best].size)) best = i;
+    if (!b.used && b.dev == dev && b.size >= bytes && b.size <= 2 * bytes + (1 << 20) && (best < 0 || b.size < g_pool[best].size)) best = i;
   }
   if (best >= 0) { g_pool[best].used = true; return g_pool[best].p; }
   void* p = nullptr;
@@ -56,7 +60,7 @@ void* pool_get(size_t bytes) {
     pool_release();                                   // out of memory: drop the cached blocks and retry once
     if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   }
-  g_pool.push_back({p, bytes, true});
+  g_pool.push_back({p, bytes, true, dev});
   return p;
 }
 void pool_put(void* p) {
@@ -66,10 +70,13 @@ void pool_put(void* p) {
   cudaFree(p);
 }
 void pool_release() {
+  const int dev = cur_dev();
   std::vector<PoolBlock> keep;
   for (auto& b : g_pool) {
-    if (b.used) keep.push_back(b);
-    else cudaFree(b.p);
+    if (b.used) { keep.push_back(b); continue; }
+    if (b.dev != dev) cudaSetDevice(b.dev);           // free under the owning device
+    cudaFree(b.p);
+    if (b.dev != dev) cudaSetDevice(dev);
   }
   g_pool.swap(keep);
 }

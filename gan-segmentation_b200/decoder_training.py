@@ -204,6 +204,7 @@ class CudaBackend:
             b16 = torch.zeros(16, device=self.device)
             b16[:cout] = b
             r = self.ops.conv(mode, xs[0], self._w(w), x1=x1, bias=b16, flags=L.EPI_ARGMAX, num_classes=cout, dtype=self.dtype)
+            self.last_mask = r['mask']                 # first-max argmax of the same logits (train metric, seg_solver.py:415-419)
             return r['logits']
         return self.ops.conv(mode, xs[0], self._w(w), x1=x1, bias=b, dtype=self.dtype)['out']
 

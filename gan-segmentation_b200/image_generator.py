@@ -42,7 +42,9 @@ class ImageGenerator:
         return generator_config(max_res_log2, base_scale[0], base_scale[1])
 
     def _split(self, n):
-        """split_and_load(even_split=False) (:95): contiguous, sizes differ by at most one."""
+        """Contiguous slices of the batch, one per context, sizes differing by at most one.  (The reference's
+        split_and_load(even_split=False) (:95) gives the whole remainder to the LAST slice instead; the results are
+        the same either way because latents and noise are keyed by the global sample index, not by the split.)"""
         k = len(self.ctx)
         base, rem = divmod(n, k)
         sizes = [base + (1 if i < rem else 0) for i in range(k)]

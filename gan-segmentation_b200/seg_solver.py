@@ -147,24 +147,35 @@ class SegSolver:
             print('number of training samples should be > 0')
             raise SystemExit(-1)
         bs = int(cfg['train_batch_size'])
-        iters_per_epoch = int(len(ds) / bs)
-        print('total train samples: {}'.format(len(ds)))
-        print('batch size: {}'.format(bs))
-        print('epoch size: {}'.format(iters_per_epoch))
-        world = 1
+        # One process per GPU: an iteration consumes bs samples PER RANK (rank r takes the r-th slice of bs*world
+        # consecutive entries of the shuffled order, the same order on every rank), gradients are summed over the ranks
+        # and rescaled by 1/(bs*world).  The reference splits one batch over its contexts (seg_solver.py:389-390), which
+        # cannot work with its own train_batch_size = 1 on more than one GPU.
+        rank, world = 0, 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
-            world = torch.distributed.get_world_size()
+            rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        iters_per_epoch = int(len(ds) / (bs * world))
+        if iters_per_epoch <= 0:
+            raise ValueError(f'{len(ds)} training samples are fewer than one global batch ({bs} x {world} ranks)')
+        if rank == 0:
+            print('total train samples: {}'.format(len(ds)))
+            print('batch size: {}'.format(bs))
+            print('epoch size: {}'.format(iters_per_epoch))
         with torch.cuda.device(self.ctx[0]):
-            trainer = DecoderTrainer(cfg, self.net.get_parameters(), CudaBackend(self.ctx[0]))
+            backend = CudaBackend(self.ctx[0])
+            trainer = DecoderTrainer(cfg, self.net.get_parameters(), backend)
             rng = np.random.RandomState(cfg['seed'])
-            gen = torch.Generator(device=self.ctx[0]).manual_seed(int(cfg['seed']))
+            gen = torch.Generator(device=self.ctx[0]).manual_seed(int(cfg['seed']) + 7919 * rank)   # dropout: per rank
             display = cfg['train_display_iters']
             done = 0
             for epoch in range(int(cfg['train_epochs'])):
                 tic = speed_tic = time.time()
                 order = rng.permutation(len(ds))                       # DataLoader(shuffle=True, last_batch='discard')
+                correct = total = 0                                    # mx.metric.Accuracy between two log lines (:173-175)
+                ep_correct = ep_total = 0
                 for nbatch in range(1, iters_per_epoch + 1):
-                    items = [ds[int(j)] for j in order[(nbatch - 1) * bs:nbatch * bs]]
+                    lo = ((nbatch - 1) * world + rank) * bs
+                    items = [ds[int(j)] for j in order[lo:lo + bs]]
                     mask = np.stack([it[1] for it in items]).astype(np.int32)
                     nfeat = len(items[0]) - 2
                     feats = [np.stack([np.asarray(it[2 + k], np.float32) for it in items]) for k in range(nfeat)]
@@ -173,22 +184,34 @@ class SegSolver:
                         drops = [(torch.rand((bs, cfg['features'][k]) + tuple(feats[k].shape[2:]), generator=gen, device=self.ctx[0]) > 0.5).float()
                                  for k in range(nfeat)]
                     loss = trainer.step(feats, mask, drops, global_batch=bs * world)
+                    pred = getattr(backend, 'last_mask', None)          # argmax of this step's logits (uint8, device)
+                    if pred is not None:
+                        hit = int((pred.cpu().numpy().astype(np.int32) == mask.reshape(pred.shape)).sum())
+                        correct += hit; total += mask.size; ep_correct += hit; ep_total += mask.size
                     done += 1
-                    if display is not None and nbatch % display == 0:
-                        speed = 1.0 * display * bs / (time.time() - speed_tic)
-                        logging.info('Epoch[%03d] Batch[%04d] Speed: % 9.2f samples/sec total-loss=%f', epoch, nbatch, speed,
-                                     float(loss.mean().item()))
+                    if display is not None and nbatch % display == 0 and rank == 0:
+                        speed = 1.0 * display * bs * world / (time.time() - speed_tic)
+                        logging.info('Epoch[%03d] Batch[%04d] Speed: % 9.2f samples/sec accuracy=%f total-loss=%f', epoch, nbatch,
+                                     speed, correct / max(total, 1), float(loss.mean().item()))
+                        correct = total = 0
                         speed_tic = time.time()
                     if max_iters is not None and done >= max_iters:
                         break
-                logging.info('Epoch[%d] Time cost=%.3f', epoch + 1, time.time() - tic)
-                if epoch_end_callback is not None:
+                if rank == 0:
+                    logging.info('Epoch[%d] Train-accuracy=%f', epoch + 1, ep_correct / max(ep_total, 1))
+                    logging.info('Epoch[%d] Learning rate=%.5f', epoch + 1, trainer.lr)
+                    logging.info('Epoch[%d] Time cost=%.3f', epoch + 1, time.time() - tic)
+                if epoch_end_callback is not None and rank == 0:
                     epoch_end_callback()
                 if max_iters is not None and done >= max_iters:
                     break
             self.set_parameters(trainer.state())
+            backend.lib.gsx_op_release_cache()             # the single-operator hooks keep their scratch memory: return it
         self.is_trained = True
-        self.save()
+        if rank == 0:                                     # every rank holds the same weights; one writer
+            self.save()
+        if world > 1:
+            torch.distributed.barrier()
         return []
 
     def evaluate(self, input_dir, output_dir=None):
