@@ -23,8 +23,9 @@ def _write_pair(dst_dir, index, img_rgb, mask):
     cv2.imwrite(join(dst_dir, f'mask_{index:06d}.png'), mask)                    # main.py:103 (class ids)
 
 
-def generate_dataset(pipeline, dst_dir, n_total, seed=0, psi=None, rank=0, world=1, workers=8, progress=None):
+def generate_dataset(pipeline, dst_dir, n_total, seed=0, psi=None, rank=0, world=1, workers=8, progress=None, write=True):
     """pipeline: networks.GeneratePipeline (batch = pipeline.n).  Writes this rank's shard of range(n_total).
+    ``write=False`` runs the same sweep (kernels + device-to-host copies) without encoding (measures the producer alone).
     Returns the number of samples written by this rank."""
     os.makedirs(dst_dir, exist_ok=True)
     lo, hi = shard_range(n_total, rank, world)
@@ -39,7 +40,7 @@ def generate_dataset(pipeline, dst_dir, n_total, seed=0, psi=None, rank=0, world
             pipeline.wait()
             imgs = pipeline.img_host[slot].numpy()
             masks = pipeline.mask_host[slot].numpy()
-            for k in range(n):
+            for k in range(n if write else 0):
                 # copy out of the pinned slot: it is reused two batches later
                 futures.append(pool.submit(_write_pair, dst_dir, first + k, imgs[k].copy(), masks[k].copy()))
 

@@ -1,5 +1,7 @@
 """Drop-in surface on the GPU: the loop of the reference's ``main.py generate`` (main.py:94-103) runs against
 the mirrored ImageGenerator / SegSolver classes, single- and (when 2 GPUs are visible) multi-context."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -135,3 +137,20 @@ def test_fit_trains_the_decoder(tmp_path):
     solver2 = SegSolver(6, str(data), str(ckpt), gpu_ids=[0], keep_weights=True, verbose=False)
     assert solver2.is_trained
     assert abs(dict(solver2.evaluate(str(data)))['total-loss'] - after['total-loss']) < 1e-5
+
+
+def test_cli_generate_action_writes_the_dataset(tmp_path):
+    """``python -m gan_segmentation_b200.main generate`` (reference main.py:75-104): GENERATE_NUM pairs of
+    img_XXXXXX.jpg / mask_XXXXXX.png under BASE_DIR/dataset/train_generated, read from the reference's config keys."""
+    import cv2
+    from gan_segmentation_b200 import main as M
+    cfg = tmp_path / 'config.yml'
+    cfg.write_text('BASE_DIR: "%s"\nGAN: "bedrooms"\nGAN_DIR: "none"\nGAN_GPU_IDS: [0]\nGAN_BATCH_SIZE_PER_GPU: 2\n'
+                   'SOLVER_GPU_IDS: [0]\nANNOTATION: "segmentation"\nGENERATE_NUM: 5\n' % tmp_path)
+    assert M.main(['generate', '--config', str(cfg), '--random-init', '--psi', '0.7']) == 0
+    out = tmp_path / 'dataset' / 'train_generated'
+    names = sorted(os.listdir(out))
+    assert names == [f'img_{i:06d}.jpg' for i in range(5)] + [f'mask_{i:06d}.png' for i in range(5)]
+    m = cv2.imread(str(out / 'mask_000004.png'), cv2.IMREAD_UNCHANGED)
+    assert m.shape == (256, 256) and set(np.unique(m)) <= {0, 1}
+    assert cv2.imread(str(out / 'img_000000.jpg')).shape == (256, 256, 3)

@@ -164,3 +164,22 @@ def test_batch_split_matches_split_and_load():
     g.ctx = [0, 1, 2]
     assert g._split(8) == [(0, 3), (3, 6), (6, 8)]
     assert g._split(2) == [(0, 1), (1, 2), (2, 2)]
+
+
+def test_cli_reads_the_reference_config_keys(tmp_path):
+    """main.py:15-43: same actions, same config.yml keys; the GUI action is declined, compute actions need a GPU."""
+    from gan_segmentation_b200 import main as M
+    cfg = tmp_path / 'config.yml'
+    cfg.write_text('BASE_DIR: "%s"\nGAN: "bedrooms"\nGAN_DIR: "stylegan-models"\nGAN_GPU_IDS: [0]\n'
+                   'GAN_BATCH_SIZE_PER_GPU: 8\nSOLVER_GPU_IDS: [0]\nANNOTATION: "segmentation"\nGENERATE_NUM: 10000\n' % tmp_path)
+    a = M.parse_args(['generate', '--config', str(cfg)])
+    assert a.action == 'generate' and M.parse_args([]).action == 'annotation'          # main.py:18-20 default
+    c = M.load_config_file(str(cfg))
+    assert c['GAN'] == 'bedrooms' and c['GENERATE_NUM'] == 10000 and c['GAN_GPU_IDS'] == [0]
+    assert M.MAX_RES_LOG2 == {'ffhq': 10, 'cars': 9, 'bedrooms': 8}
+    assert M.main(['annotation', '--config', str(cfg)]) == 2
+    import torch
+    if not torch.cuda.is_available():
+        import pytest
+        with pytest.raises(Exception):                                                 # no CPU fallback
+            M.main(['generate', '--config', str(cfg), '--random-init'])
