@@ -506,22 +506,17 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     if (!cuda_ok(cudaMemcpyAsync(w.psi, psi_host, h->nlayers * sizeof(float), cudaMemcpyHostToDevice, st), "copy psi")) return -2;
     psi = w.psi;
   }
-  // mapping MLP
-  const float* cur = w.z;
-  for (int i = 0; i < 8; ++i) {
-    DenseArgs d{};
-    d.x = cur; d.W = h->d_map_w[i]; d.b = h->d_map_b[i]; d.y = (i & 1) ? w.wb : w.wa;
-    d.N = N; d.K = Z; d.U = Z; d.lrelu = 1; d.pixelnorm = (i == 0);
-    { ProfScope ps("map.dense", 4.0 * Z * Z + 8.0 * N * Z, 2.0 * N * Z * Z, st); launch_dense(d, st); g_launches++; }
-    cur = d.y;
-  }
-  {   // all style layers at once; truncation folded into the operand load
-    DenseArgs d{};
-    d.x = cur; d.W = h->d_aff_w; d.b = h->d_aff_b; d.y = w.styles;
-    d.N = N; d.K = Z; d.U = h->S_total; d.lrelu = 0; d.pixelnorm = 0;
-    d.latent_avg = h->d_latent_avg; d.psi = psi; d.unit_layer = h->d_unit_layer;
-    ProfScope ps("styles", 4.0 * h->S_total * Z + 4.0 * N * (Z + h->S_total), 2.0 * N * Z * h->S_total, st);
-    launch_dense(d, st); g_launches++;
+  // mapping MLP + all style affines (truncation folded in): one cooperative launch
+  {
+    MapArgs m{};
+    m.z = w.z; m.ya = w.wa; m.yb = w.wb;
+    for (int i = 0; i < 8; ++i) { m.W[i] = h->d_map_w[i]; m.b[i] = h->d_map_b[i]; }
+    m.Waff = h->d_aff_w; m.baff = h->d_aff_b; m.latent_avg = h->d_latent_avg; m.psi = psi; m.unit_layer = h->d_unit_layer;
+    m.styles = w.styles; m.N = N; m.S = h->S_total;
+    ProfScope ps("map+styles", 4.0 * (8.0 * Z * Z + (double)h->S_total * Z) + 4.0 * N * (Z + h->S_total),
+                 2.0 * N * Z * (8.0 * Z + h->S_total), st);
+    if (!launch_mapping(m, st)) { cuda_ok(cudaGetLastError(), "mapping launch"); return -2; }
+    g_launches++;
   }
   // noise planes: explicit inputs, or all of them from the Philox generator in one launch
   std::vector<const float*> noise(h->nlayers);

@@ -254,6 +254,16 @@ struct DenseArgs {            // y[n][u] = act( sum_k x'[n][k] W[u][k] + b[u] ),
   const float* latent_avg; const float* psi; const int* unit_layer;
 };
 void launch_dense(const DenseArgs& a, cudaStream_t st);
+struct MapArgs {              // the whole mapping path (styles.cu: mapping_kernel); latent size 512
+  const float* z;             // [N][512] latents
+  const float* W[8]; const float* b[8];      // mapping layers, pre-scaled
+  float *ya, *yb;             // [N][512] ping-pong buffers (layer 7 leaves the disentangled latents in yb)
+  const float* Waff; const float* baff;      // [S][512], [S]: the AdaIN affines of all style layers
+  const float* latent_avg; const float* psi; const int* unit_layer;
+  float* styles;              // [N][S]
+  int N, S;
+};
+bool launch_mapping(const MapArgs& a, cudaStream_t st);
 
 // Launch with programmatic stream serialization (see ptx.cuh) when the current forward pass is small enough for it to
 // pay (plan.cpp); GSX_NO_PDL=1: never, GSX_PDL=1: always.

@@ -241,6 +241,23 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   return r;
 }
 
+// 32 values per lane x 32 lanes -> lane L returns value L summed over the warp: a halving butterfly, 31 shuffles in
+// all (a plain xor-reduction of every value would take 160); fixed order, so results are bit-reproducible.
+__device__ __forceinline__ float warp_transpose_reduce32(float (&vals)[32], int lane) {
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    const int half = 16 >> step;                      // values kept per lane after this step
+    const bool upper = (lane & half) != 0;            // lane bit deciding which half is kept
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = upper ? vals[half + i] : vals[i];
+      const float send = upper ? vals[i] : vals[half + i];
+      vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return vals[0];
+}
+
 // ---------------------------------------------------------------- misc
 // One lane of a converged warp; lets the compiler keep the tcgen05 / TMA issue sequence in uniform
 // registers without wrapping every instruction in a per-thread loop (which `lane == 0` does).

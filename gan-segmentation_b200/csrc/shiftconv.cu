@@ -79,18 +79,7 @@ __device__ __forceinline__ float warp_reduce_32x32(const float (&s1)[16], const 
   float vals[32];
 #pragma unroll
   for (int i = 0; i < 16; ++i) { vals[i] = s1[i]; vals[16 + i] = s2[i]; }
-#pragma unroll
-  for (int step = 0; step < 5; ++step) {
-    const int half = 16 >> step;                      // values kept per lane after this step
-    const bool upper = (lane & half) != 0;            // lane bit deciding which half is kept
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float keep = upper ? vals[half + i] : vals[i];
-      const float send = upper ? vals[i] : vals[half + i];
-      vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-    }
-  }
-  return vals[0];
+  return warp_transpose_reduce32(vals, lane);
 }
 
 // argmax over the classes of the output phases held in one 16-column chunk (CT columns per phase): first maximum
