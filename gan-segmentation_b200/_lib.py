@@ -61,6 +61,7 @@ _SIGS = {
     'gsx_last_error': (C.c_char_p, []),
     'gsx_abi_version': (_i, []),
     'gsx_launch_count': (_u64, []),
+    'gsx_set_option': (_i, [C.c_char_p, _i]),
     'gsx_synth_create': (_i, [C.POINTER(SynthCfg), C.POINTER(_vp)]),
     'gsx_synth_destroy': (None, [_vp]),
     'gsx_synth_set_param': (_i, [_vp, C.c_char_p, _fp, C.POINTER(C.c_int64), _i]),

@@ -95,9 +95,20 @@ struct Arena {              // carves a caller-owned workspace
   }
 };
 
+// Per-sample operands of a conv that has its input's AdaIN folded in (modulate.cu); carved from the caller's workspace.
+struct ModBufs { act_t* w = nullptr; float* bias_n = nullptr; float* bdelta = nullptr; };
+static ModBufs take_mod(Arena& a, const ConvLayer& L, int N) {
+  ModBufs m;
+  m.w = a.take<act_t>((size_t)N * L.wpack_elems);
+  m.bias_n = a.take<float>((size_t)N * L.g.bias_cols);
+  m.bdelta = a.take<float>((size_t)N * 9 * L.g.bias_cols);
+  return m;
+}
+static int g_opt_fold_apply = 1;           // gsx_set_option("fold_apply", 0/1), read when a handle is finalized
+
 // Runs one planned conv layer: builds the tensor maps for this batch / these buffers and launches.
 static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1, const ConvEpi& epi, cudaStream_t st,
-                     const char* label = "conv") {
+                     const char* label = "conv", const ModBufs* mod = nullptr) {
   // algorithmic work of this layer: 2 B x (input + output elements), upsample/concat folded,
   // +4 B x noise plane, uint8 mask; dense FLOPs of the reference formulation
   const double in_el = (double)N * (L.cin0 + L.cin1) * L.H * L.W, out_px = (double)N * epi.Ho * epi.Wo;
@@ -113,6 +124,12 @@ static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1
   p.e = epi;
   p.e.out_planar = L.out_planar;
   p.wpack = L.wpack_dev;
+  p.wpack_n_stride = 0;
+  if (L.g.per_sample) {
+    if (!mod) { set_error("run_conv: per-sample layer without modulated operands"); return false; }
+    p.wpack = mod->w; p.wpack_n_stride = L.wpack_elems;
+    p.e.bias = nullptr; p.e.bias_n = mod->bias_n; p.e.bdelta = mod->bdelta;
+  }
   p.taps = L.taps_dev;
   set_error("");
   make_input_tensormaps(p, L, N, x0, x1);
@@ -133,9 +150,14 @@ static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1
 
 static bool upload_conv(ConvLayer& L, const float* w) {
   std::vector<act_t> packed;
-  pack_conv_weights(L, w, packed);
+  std::vector<float> packed_f32;
+  pack_conv_weights(L, w, packed, L.g.per_sample ? &packed_f32 : nullptr);
   L.wpack_elems = packed.size();
   L.wpack_dev = dev_upload(packed);
+  if (L.g.per_sample) {
+    L.wf32_dev = dev_upload(packed_f32);
+    if (!L.wf32_dev) return false;
+  }
   std::vector<int4> taps(4 * kMaxSlots);
   build_tap_table(L.g, taps.data());
   L.taps_dev = dev_upload(taps);
@@ -154,6 +176,10 @@ struct SynthBlock {
   ConvLayer conv1, conv2;                 // conv1 unused at r == 2
   float *ns1 = nullptr, *b1 = nullptr, *ns2 = nullptr, *b2 = nullptr;
   bool fold = false;                      // conv1 = deconv + blur + noise/bias/lrelu/stats in one kernel (DECONV4B)
+  // AdaIN folded into the consumers (modulate.cu): mod2 = conv_2 reads the un-normalised first half t1 with per-sample
+  // weights (no apply1 pass); t2 = the block's output stays un-normalised in feat[] and every consumer (next block's
+  // conv_1, the decoder's cvt conv, ToRGB) folds AdaIN 2 in (no apply2 pass); mod1 = conv_1 consumes such a tensor.
+  bool mod1 = false, mod2 = false, t2 = false;
   float* wt = nullptr;                    // fold: scaled deconv weights [4][4][Cin][C] fp32 for the border correction
 };
 
@@ -190,6 +216,7 @@ struct SynthWs {
   std::vector<act_t*> feat;
   act_t *bufA, *bufB;
   float *e_rows, *e_cols;                 // border corrections of the folded deconv+blur layers
+  std::vector<ModBufs> mod1, mod2;        // per block: per-sample operands of conv_1 / conv_2 (AdaIN folded in)
   size_t total;
 };
 
@@ -228,6 +255,10 @@ static SynthWs synth_layout(const gsx_synth* h, int N, void* base) {
     if (b.fold) maxe = std::max(maxe, (size_t)N * 2 * std::max(b.H, b.W) * b.C);
   w.e_rows = a.take<float>(maxe);
   w.e_cols = a.take<float>(maxe);
+  for (const auto& b : h->blocks) {
+    w.mod1.push_back(b.mod1 ? take_mod(a, b.conv1, N) : ModBufs());
+    w.mod2.push_back(b.mod2 ? take_mod(a, b.conv2, N) : ModBufs());
+  }
   w.total = a.off;
   return w;
 }
@@ -252,6 +283,11 @@ static int synth_stats_tiles(const gsx_synth* h, int l) {
 extern "C" const char* gsx_last_error(void) { return last_error_cstr(); }
 extern "C" int gsx_abi_version(void) { return 2; }
 extern "C" uint64_t gsx_launch_count(void) { return g_launches.load(); }
+extern "C" int gsx_set_option(const char* name, int value) {
+  if (name && std::strcmp(name, "fold_apply") == 0) { g_opt_fold_apply = value != 0; return 0; }
+  set_error(std::string("unknown option: ") + (name ? name : "(null)"));
+  return -1;
+}
 
 extern "C" int gsx_synth_create(const gsx_synth_cfg* cfg, gsx_synth** out) {
   if (!cfg || !out) { set_error("null argument"); return -1; }
@@ -287,7 +323,8 @@ extern "C" void gsx_synth_destroy(gsx_synth* h) {
   for (auto& b : h->blocks) {
     cudaFree(b.conv1.wpack_dev); cudaFree(b.conv2.wpack_dev);
     cudaFree(b.conv1.taps_dev); cudaFree(b.conv2.taps_dev);
-    cudaFree(b.ns1); cudaFree(b.b1); cudaFree(b.ns2); cudaFree(b.b2);
+    cudaFree(b.conv1.wf32_dev); cudaFree(b.conv2.wf32_dev);
+    cudaFree(b.ns1); cudaFree(b.b1); cudaFree(b.ns2); cudaFree(b.b2); cudaFree(b.wt);
   }
   delete h;
 }
@@ -379,6 +416,7 @@ extern "C" int gsx_synth_finalize(gsx_synth* h) {
   for (auto& b : h->blocks) {
     cudaFree(b.conv1.wpack_dev); cudaFree(b.conv2.wpack_dev);
     cudaFree(b.conv1.taps_dev); cudaFree(b.conv2.taps_dev);
+    cudaFree(b.conv1.wf32_dev); cudaFree(b.conv2.wf32_dev);
     cudaFree(b.ns1); cudaFree(b.b1); cudaFree(b.ns2); cudaFree(b.b2); cudaFree(b.wt);
   }
   h->blocks.clear();
@@ -387,6 +425,14 @@ extern "C" int gsx_synth_finalize(gsx_synth* h) {
     b.r = r; b.C = h->nf(r); b.Cin = r > 2 ? h->nf(r - 1) : b.C;
     h->hw(r, b.H, b.W);
     const std::string p = "net" + std::to_string(r);
+    // AdaIN folded into the consumer convs for the channel-thin blocks (<= 64 channels, >= 64^2 pixels): per-sample
+    // modulated weights are then a few KB to 150 KB per sample; the wide blocks keep the separate apply pass (their
+    // weight sets are MBs per sample).  A block's output can only stay un-normalised if the next block's conv_1 supports
+    // per-sample weights (the stacked-phase plans do, the phase-grid plan of cout >= 64 layers does not).
+    auto thin = [&](int rr) { int hh, ww; h->hw(rr, hh, ww); return g_opt_fold_apply && h->nf(rr) <= 64 && hh * ww >= 64 * 64; };
+    b.mod2 = thin(r);
+    b.t2 = thin(r) && (r == L || h->nf(r + 1) < 64);
+    b.mod1 = r > 2 && !h->blocks.empty() && h->blocks.back().t2;
     if (r > 2) {
       const bool deconv = r >= 7;                                            // networks_stylegan.py:154
       const int k = deconv ? 4 : 3;
@@ -403,7 +449,7 @@ extern "C" int gsx_synth_finalize(gsx_synth* h) {
       const int fold_maxc = fm ? atoi(fm) : 16;
       if (deconv && b.C <= fold_maxc && b.C < 64) {
         set_error("");
-        plan_conv(b.conv1, DECONV4B, b.H / 2, b.W / 2, b.Cin, 0, b.C, 0, nullptr, /*aux: noise tile*/ 1);
+        plan_conv(b.conv1, DECONV4B, b.H / 2, b.W / 2, b.Cin, 0, b.C, 0, nullptr, /*aux: noise tile*/ 1, 0, b.mod1 ? 1 : 0);
         b.fold = !*gsx_last_error() && b.conv1.g.NB == 1 && b.conv1.g.up_cols;
       }
       if (b.fold) {
@@ -415,7 +461,7 @@ extern "C" int gsx_synth_finalize(gsx_synth* h) {
         if (!b.wt) return -2;
       } else {
         set_error("");
-        plan_conv(b.conv1, deconv ? DECONV4 : UPCONV3, b.H / 2, b.W / 2, b.Cin, 0, b.C, 0, nullptr);
+        plan_conv(b.conv1, deconv ? DECONV4 : UPCONV3, b.H / 2, b.W / 2, b.Cin, 0, b.C, 0, nullptr, 0, 0, b.mod1 ? 1 : 0);
       }
       if (*gsx_last_error()) return -1;
       if (!upload_conv(b.conv1, ws.data())) return -2;
@@ -431,7 +477,7 @@ extern "C" int gsx_synth_finalize(gsx_synth* h) {
       // (the in-place AdaIN pass does not care) and let conv_2 use the space-to-depth plan with dense boxes
       // (measured: conv_2 0.67 -> 0.58 ms, the producer's split stores cost 0.03 ms; GSX_PLANAR_G=0 turns it off)
       const bool planar_in = b.fold && !(tune_env("GSX_PLANAR_G") && atoi(tune_env("GSX_PLANAR_G")) == 0) && !tune_env("GSX_NO_S2D");
-      plan_conv(b.conv2, CONV3, b.H, b.W, b.C, 0, b.C, 0, nullptr, /*aux: noise tile*/ 1, planar_in ? 1 : 0);
+      plan_conv(b.conv2, CONV3, b.H, b.W, b.C, 0, b.C, 0, nullptr, /*aux: noise tile*/ 1, planar_in ? 1 : 0, b.mod2 ? 1 : 0);
       if (*gsx_last_error()) return -1;
       if (planar_in) b.conv1.out_planar = 1;
       if (!upload_conv(b.conv2, ws.data())) return -2;
@@ -554,61 +600,79 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     const double act_bytes = 2.0 * N * b.C * b.H * b.W, plane_bytes = 4.0 * N * b.H * b.W;
     float* st1 = w.partial[l1];
     float* st2 = w.partial[l2];
+    // AdaIN 2 of the previous block folded into this block's conv_1: feat[bi-1] holds the un-normalised tensor
+    const float* coef_in = b.mod1 ? w.coef[l1 - 1] : nullptr;
+    const ModBufs* m1 = b.mod1 ? &w.mod1[bi] : nullptr;
+    if (b.mod1) {
+      ProfScope ps(tag + "modulate1", 0, 0, st);
+      launch_modulate(b.conv1, coef_in, b.fold ? b.b1 : nullptr, N, m1->w, m1->bias_n, m1->bdelta, st); g_launches += 2;
+    }
     Pass1Args p1{};
     p1.out = w.bufB; p1.C = b.C; p1.N = N; p1.H = b.H; p1.W = b.W;
     p1.nscale = b.ns1; p1.bias = b.b1; p1.noise = noise[l1]; p1.stats = st1;
     if (b.fold) {
       { ProfScope ps(tag + "border", 0, 0, st);
-        launch_deconv_border(w.feat[bi - 1], b.wt, w.e_rows, w.e_cols, N, b.Cin, b.C, b.H / 2, b.W / 2, st); g_launches++; }
+        launch_deconv_border(w.feat[bi - 1], b.wt, w.e_rows, w.e_cols, N, b.Cin, b.C, b.H / 2, b.W / 2, st, coef_in); g_launches++; }
       ConvEpi e{};
       e.out = w.bufB; e.Ho = b.H; e.Wo = b.W; e.up = 1; e.Cout = b.C;
       e.flags = EPI_LRELU | EPI_STATS;
       e.bias = b.b1; e.nscale = b.ns1; e.noise = noise[l1];
       e.stats = st1; e.stats_T = w.stats_T[l1];
       e.e_rows = w.e_rows; e.e_cols = w.e_cols;
-      if (!run_conv(b.conv1, N, w.feat[bi - 1], nullptr, e, st, (tag + "deconv+blur").c_str())) return -2;
+      if (!run_conv(b.conv1, N, w.feat[bi - 1], nullptr, e, st, (tag + "deconv+blur").c_str(), m1)) return -2;
     } else if (b.r == 2) {
       p1.in = h->d_const; p1.in_broadcast = 1; p1.blur = 0;
     } else {
       ConvEpi e{};
       e.out = w.bufA; e.Ho = b.H; e.Wo = b.W; e.up = 1; e.flags = 0; e.Cout = b.C;
-      if (!run_conv(b.conv1, N, w.feat[bi - 1], nullptr, e, st, (tag + (b.r >= 7 ? "deconv" : "upconv")).c_str())) return -2;
+      if (!run_conv(b.conv1, N, w.feat[bi - 1], nullptr, e, st, (tag + (b.r >= 7 ? "deconv" : "upconv")).c_str(), m1)) return -2;
       p1.in = w.bufA; p1.in_broadcast = 0; p1.blur = 1;
     }
     if (!b.fold) { ProfScope ps(tag + "pass1", (b.r == 2 ? 1.0 : 2.0) * act_bytes + plane_bytes, 0, st); launch_pass1(p1, st); g_launches++; }
     { ProfScope ps(tag + "finalize", 0, 0, st);
       launch_finalize(st1, w.stats_T[l1], N, b.C, b.H * b.W, w.styles, h->S_total, h->style_off[l1], w.coef[l1], st);
       g_launches++; }
-    ApplyArgs a1{};
-    a1.in = w.bufB; a1.out = w.bufB; a1.C = b.C; a1.N = N; a1.H = b.H; a1.W = b.W;
-    a1.coef = w.coef[l1];
-    { ProfScope ps(tag + "apply1", 2.0 * act_bytes, 0, st); launch_apply(a1, st); g_launches++; }
+    const ModBufs* m2 = b.mod2 ? &w.mod2[bi] : nullptr;
+    if (b.mod2) {
+      // AdaIN 1 folded into conv_2: no pass over the tensor, only the per-sample weights / bias
+      ProfScope ps(tag + "modulate2", 0, 0, st);
+      launch_modulate(b.conv2, w.coef[l1], b.b2, N, m2->w, m2->bias_n, m2->bdelta, st); g_launches += 2;
+    } else {
+      ApplyArgs a1{};
+      a1.in = w.bufB; a1.out = w.bufB; a1.C = b.C; a1.N = N; a1.H = b.H; a1.W = b.W;
+      a1.coef = w.coef[l1];
+      ProfScope ps(tag + "apply1", 2.0 * act_bytes, 0, st); launch_apply(a1, st); g_launches++;
+    }
 
+    act_t* t2buf = b.t2 ? w.feat[bi] : w.bufA;          // folded AdaIN 2: the un-normalised tensor IS the block's output
     ConvEpi e2{};
-    e2.out = w.bufA; e2.Ho = b.H; e2.Wo = b.W; e2.up = 0; e2.Cout = b.C;
+    e2.out = t2buf; e2.Ho = b.H; e2.Wo = b.W; e2.up = 0; e2.Cout = b.C;
     e2.bias = b.b2; e2.nscale = b.ns2; e2.noise = noise[l2];
     const bool fused_stats = b.conv2.g.NB == 1;
     e2.flags = EPI_LRELU | (fused_stats ? EPI_STATS : 0);
     e2.stats = fused_stats ? st2 : nullptr;
     e2.stats_T = w.stats_T[l2];
-    if (!run_conv(b.conv2, N, w.bufB, nullptr, e2, st, (tag + "conv2").c_str())) return -2;
-    if (!fused_stats) { ProfScope ps(tag + "stats", act_bytes, 0, st); launch_stats(w.bufA, st2, b.C, N, b.H * b.W, st); g_launches++; }
+    if (!run_conv(b.conv2, N, w.bufB, nullptr, e2, st, (tag + "conv2").c_str(), m2)) return -2;
+    if (!fused_stats) { ProfScope ps(tag + "stats", act_bytes, 0, st); launch_stats(t2buf, st2, b.C, N, b.H * b.W, st); g_launches++; }
     { ProfScope ps(tag + "finalize", 0, 0, st);
       launch_finalize(st2, w.stats_T[l2], N, b.C, b.H * b.W, w.styles, h->S_total, h->style_off[l2], w.coef[l2], st);
       g_launches++; }
 
     ApplyArgs a2{};
-    a2.in = w.bufA; a2.out = w.feat[bi]; a2.C = b.C; a2.N = N; a2.H = b.H; a2.W = b.W;
+    a2.in = t2buf; a2.out = b.t2 ? nullptr : w.feat[bi]; a2.C = b.C; a2.N = N; a2.H = b.H; a2.W = b.W;
     a2.coef = w.coef[l2];
     a2.out_nchw_f32 = feats_f32_dev ? feats_f32_dev[bi] : nullptr;
-    if (b.r == h->L) {
+    const bool last = b.r == h->L;
+    if (last) {
       a2.wrgb = h->d_wrgb; a2.brgb = h->d_brgb; a2.img_f32 = img_f32_dev; a2.img_u8 = img_u8_dev; a2.nc = h->cfg.channels;
     }
-    {
-      double by = 2.0 * act_bytes;
-      if (b.r == h->L) by += (img_u8_dev ? 1.0 : 0.0) * N * b.H * b.W * h->cfg.channels + (img_f32_dev ? 4.0 : 0.0) * N * b.H * b.W * h->cfg.channels;
+    if (!b.t2 || last || a2.out_nchw_f32) {
+      // (with AdaIN 2 folded into the consumers this pass survives only as ToRGB on the last block -- a read of the
+      //  tensor and a 3-byte write -- and as the fp32 NCHW feature output of the drop-in mode)
+      double by = (b.t2 ? 1.0 : 2.0) * act_bytes;
+      if (last) by += (img_u8_dev ? 1.0 : 0.0) * N * b.H * b.W * h->cfg.channels + (img_f32_dev ? 4.0 : 0.0) * N * b.H * b.W * h->cfg.channels;
       if (a2.out_nchw_f32) by += 2.0 * act_bytes;
-      ProfScope ps(tag + (b.r == h->L ? "apply2+rgb" : "apply2"), by, b.r == h->L ? 2.0 * N * b.H * b.W * b.C * h->cfg.channels : 0, st);
+      ProfScope ps(tag + (last ? (b.t2 ? "rgb" : "apply2+rgb") : "apply2"), by, last ? 2.0 * N * b.H * b.W * b.C * h->cfg.channels : 0, st);
       launch_apply(a2, st); g_launches++;
     }
   }
@@ -637,6 +701,8 @@ extern "C" int gsx_synth_export_latents(gsx_synth* h, int n, float* out_dev, con
 struct DecLevel {
   int H, W, cin, f, fnext;
   ConvLayer cvt, conv_a, conv_b, shortcut, final_;
+  ConvLayer cvt_ps;                       // cvt with per-sample weights: the generator left this level's feature un-normalised
+  bool has_cvt_ps = false;                //   (AdaIN folded into the consumers, modulate.cu)
   bool has_shortcut = false;
   float *b_cvt = nullptr, *b_a = nullptr, *b_b = nullptr, *b_sc = nullptr, *b_final = nullptr;
 };
@@ -651,6 +717,7 @@ struct gsx_dec {
 
 struct DecWs {
   std::vector<act_t*> feat, c, a, sc, prev;     // prev[i] = input "prev" of level i (null at 0)
+  std::vector<ModBufs> mod;                     // per level: per-sample operands of cvt_ps
   size_t total;
 };
 
@@ -671,6 +738,8 @@ static DecWs dec_layout(const gsx_dec* d, int N, void* base, bool own_feats) {
       w.prev[i + 1] = ar.take<act_t>(plane * 4 * d->cfg.features[i + 1]);
     }
   }
+  for (int i = 0; i < nf; ++i)
+    w.mod.push_back((size_t)i < d->levels.size() && d->levels[i].has_cvt_ps ? take_mod(ar, d->levels[i].cvt_ps, N) : ModBufs());
   w.total = ar.off;
   return w;
 }
@@ -695,6 +764,7 @@ static void free_level(DecLevel& l) {
   cudaFree(l.shortcut.wpack_dev); cudaFree(l.final_.wpack_dev);
   cudaFree(l.cvt.taps_dev); cudaFree(l.conv_a.taps_dev); cudaFree(l.conv_b.taps_dev);
   cudaFree(l.shortcut.taps_dev); cudaFree(l.final_.taps_dev);
+  cudaFree(l.cvt_ps.wpack_dev); cudaFree(l.cvt_ps.taps_dev); cudaFree(l.cvt_ps.wf32_dev);
   cudaFree(l.b_cvt); cudaFree(l.b_a); cudaFree(l.b_b); cudaFree(l.b_sc); cudaFree(l.b_final);
 }
 
@@ -762,6 +832,18 @@ extern "C" int gsx_dec_finalize(gsx_dec* d) {
     l.cvt.out_planar = (i == nf - 1 && planar_final) ? 1 : 0;
     if (!upload_conv(l.cvt, w.data())) return -2;
     l.b_cvt = dev_upload(b);
+    if (g_opt_fold_apply && l.cin <= 64 && l.H * l.W >= 64 * 64) {
+      // the generator may hand this level over un-normalised (its AdaIN 2 folded into the consumers): same conv with
+      // per-sample weights built by launch_modulate at forward time
+      set_error("");
+      plan_conv(l.cvt_ps, CONV3, l.H, l.W, l.cin, 0, l.f, 0, nullptr, 0, 0, /*per_sample*/ 1);
+      if (!*gsx_last_error()) {
+        l.cvt_ps.out_planar = l.cvt.out_planar;
+        if (!upload_conv(l.cvt_ps, w.data())) return -2;
+        l.has_cvt_ps = true;
+      }
+      set_error("");
+    }
     const int c0 = i > 0 ? l.f : l.f, c1 = i > 0 ? l.f : 0;          // concat(prev, cvt) (networks_seg.py:108-109)
     const int cin_main = c0 + c1;
     if (i < nf - 1) {
@@ -828,6 +910,7 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
   if (w.total > ws_bytes) { set_error("decoder workspace too small"); return -1; }
   pdl_set_for_work((double)N * d->levels[nf - 1].H * d->levels[nf - 1].W);
   std::vector<const act_t*> feat(nf);
+  std::vector<const float*> feat_coef(nf, nullptr);      // per level: AdaIN coefficients still to be applied (un-normalised feature)
   if (own) {
     for (int i = 0; i < nf; ++i) {
       const DecLevel& l = d->levels[i];
@@ -844,6 +927,10 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
       const SynthBlock& b = synth->blocks[i];
       if (b.C != l.cin || b.H != l.H || b.W != l.W) { set_error("generator/decoder feature shape mismatch"); return -1; }
       feat[i] = sw.feat[i];
+      if (b.t2) {
+        if (!l.has_cvt_ps) { set_error("the generator folds AdaIN at a level the decoder has no per-sample conv for"); return -1; }
+        feat_coef[i] = sw.coef[2 * i + 1];
+      }
     }
   }
   for (int i = 0; i < nf; ++i) {
@@ -851,7 +938,12 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
     {
       ConvEpi e{};
       e.out = w.c[i]; e.Ho = l.H; e.Wo = l.W; e.flags = EPI_LRELU; e.Cout = l.f; e.bias = l.b_cvt;
-      if (!run_conv(l.cvt, N, feat[i], nullptr, e, st, ("d" + std::to_string(i) + ".cvt").c_str())) return -2;
+      if (feat_coef[i]) {
+        const ModBufs& m = w.mod[i];
+        { ProfScope ps("d" + std::to_string(i) + ".modulate", 0, 0, st);
+          launch_modulate(l.cvt_ps, feat_coef[i], l.b_cvt, N, m.w, m.bias_n, m.bdelta, st); g_launches += 2; }
+        if (!run_conv(l.cvt_ps, N, feat[i], nullptr, e, st, ("d" + std::to_string(i) + ".cvt").c_str(), &m)) return -2;
+      } else if (!run_conv(l.cvt, N, feat[i], nullptr, e, st, ("d" + std::to_string(i) + ".cvt").c_str())) return -2;
     }
     const act_t* x0 = i > 0 ? w.prev[i] : w.c[i];
     const act_t* x1 = i > 0 ? w.c[i] : nullptr;

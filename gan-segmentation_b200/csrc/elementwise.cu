@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kApThreads) apply_kernel(const ApplyArgs a) {
       unpack8(r[it], f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], ca[i], cc[i]);
-      *reinterpret_cast<uint4*>(out + (size_t)pix * 8) = pack8(f);
+      if (a.out) *reinterpret_cast<uint4*>(out + (size_t)pix * 8) = pack8(f);
       if (a.out_nchw_f32) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) a.out_nchw_f32[((size_t)n * a.C + cb * 8 + i) * HW + pix] = f[i];
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256) apply_rgb_kernel(const ApplyArgs a) {
         for (int k = 0; k < 4; ++k)
           if (k < a.nc) rgb[k] = fmaf(s_w[k * a.C + cb * 8 + i], f[i], rgb[k]);
       }
-      *reinterpret_cast<uint4*>(a.out + off) = pack8(f);
+      if (a.out) *reinterpret_cast<uint4*>(a.out + off) = pack8(f);     // (null: AdaIN folded into the consumers, only the image leaves)
       if (a.out_nchw_f32) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) a.out_nchw_f32[((size_t)n * a.C + cb * 8 + i) * HW + pix] = f[i];
@@ -362,8 +362,77 @@ __global__ void __launch_bounds__(256) apply_rgb_kernel(const ApplyArgs a) {
   }
 }
 
+// ToRGB alone (AdaIN 2 of the last block folded into its consumers: the normalised feature is never written).  The
+// modulation is linear, so it moves into the 1x1 weights: rgb_k = sum_c (Wrgb[k][c] a_c) t_c + (sum_c Wrgb[k][c] b_c + brgb_k).
+// One thread = PIX pixels, all CB x PIX 16-byte loads issued before the first use; 3 bytes out per pixel.
+template <int CB, int PIX>
+__global__ void __launch_bounds__(256) rgb_kernel(const ApplyArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float s_w[4][CB * 8];
+  __shared__ float s_b[4];
+  const int n = blockIdx.y;
+  const int HW = a.H * a.W;
+  if (threadIdx.x < 4 * CB * 8) {
+    const int k = threadIdx.x / (CB * 8), c = threadIdx.x - k * (CB * 8);
+    s_w[k][c] = k < a.nc ? a.wrgb[k * a.C + c] * a.coef[((size_t)n * a.C + c) * 2] : 0.f;
+  }
+  if (threadIdx.x < 4) {
+    float acc = threadIdx.x < a.nc ? a.brgb[threadIdx.x] : 0.f;
+    if (threadIdx.x < a.nc)
+      for (int c = 0; c < a.C; ++c) acc = fmaf(a.wrgb[threadIdx.x * a.C + c], a.coef[((size_t)n * a.C + c) * 2 + 1], acc);
+    s_b[threadIdx.x] = acc;
+  }
+  __syncthreads();
+  const int base = blockIdx.x * (256 * PIX) + threadIdx.x;
+  uint4 r[PIX][CB];
+#pragma unroll
+  for (int i = 0; i < PIX; ++i) {
+    const int pix = base + i * 256;
+#pragma unroll
+    for (int cb = 0; cb < CB; ++cb)
+      if (pix < HW) r[i][cb] = ldg_nc_u4(a.in + (((size_t)cb * a.N + n) * HW + pix) * 8);
+  }
+#pragma unroll
+  for (int i = 0; i < PIX; ++i) {
+    const int pix = base + i * 256;
+    if (pix >= HW) continue;
+    float rgb[4] = {s_b[0], s_b[1], s_b[2], s_b[3]};
+#pragma unroll
+    for (int cb = 0; cb < CB; ++cb) {
+      float f[8];
+      unpack8(r[i][cb], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rgb[k] = fmaf(s_w[k][cb * 8 + j], f[j], rgb[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < a.nc) {
+        if (a.img_f32) a.img_f32[((size_t)n * a.nc + k) * HW + pix] = rgb[k];
+        if (a.img_u8) {
+          // image_generator.py:76-84: (x - (-1)) / 2 -> clip [0,1] -> *255 -> truncate to uint8
+          float u = (rgb[k] + 1.f) / 2.f;
+          u = fminf(fmaxf(u, 0.f), 1.f);
+          a.img_u8[((size_t)n * HW + pix) * a.nc + k] = (unsigned char)(255.f * u);
+        }
+      }
+    }
+  }
+}
+
 void launch_apply(const ApplyArgs& a, cudaStream_t st) {
   const int HW = a.H * a.W;
+  if (a.wrgb && !a.out && !a.out_nchw_f32 && (a.C == 16 || a.C == 32 || a.C == 64)) {
+    const int pixn = a.C == 16 ? 8 : (a.C == 32 ? 4 : 2);
+    dim3 grid((HW + 256 * pixn - 1) / (256 * pixn), a.N);
+    if (a.C == 16) launch_pdl(rgb_kernel<2, 8>, grid, dim3(256), 0, st, a);
+    else if (a.C == 32) launch_pdl(rgb_kernel<4, 4>, grid, dim3(256), 0, st, a);
+    else launch_pdl(rgb_kernel<8, 2>, grid, dim3(256), 0, st, a);
+    return;
+  }
   if (a.wrgb) {
     dim3 grid(min((HW + 255) / 256, 4096), a.N);
     const size_t smem = (size_t)(2 * a.C + a.nc * a.C) * sizeof(float);
@@ -528,7 +597,8 @@ static constexpr int kBorderThreads = 128;
 
 __global__ void __launch_bounds__(kBorderThreads) deconv_border_kernel(const act_t* __restrict__ x, const float* __restrict__ wt,
                                                                        float* __restrict__ e_rows, float* __restrict__ e_cols,
-                                                                       int N, int Cin, int Cout, int H, int W) {
+                                                                       int N, int Cin, int Cout, int H, int W,
+                                                                       const float* __restrict__ coef) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float ring[];                      // [kBorderSeg + 2][Cout]
@@ -569,8 +639,13 @@ __global__ void __launch_bounds__(kBorderThreads) deconv_border_kernel(const act
 #else
               const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[k]));
 #endif
-              acc = fmaf(f.x, __ldg(wk + (size_t)(cb * 8 + 2 * k) * Cout), acc);
-              acc = fmaf(f.y, __ldg(wk + (size_t)(cb * 8 + 2 * k + 1) * Cout), acc);
+              float x0 = f.x, x1 = f.y;
+              if (coef) {          // the stored tensor is the un-normalised t: x = a*t + b (AdaIN folded into the consumers)
+                const float4 ab = __ldg(reinterpret_cast<const float4*>(coef + ((size_t)n * Cin + cb * 8 + 2 * k) * 2));
+                x0 = fmaf(x0, ab.x, ab.y); x1 = fmaf(x1, ab.z, ab.w);
+              }
+              acc = fmaf(x0, __ldg(wk + (size_t)(cb * 8 + 2 * k) * Cout), acc);
+              acc = fmaf(x1, __ldg(wk + (size_t)(cb * 8 + 2 * k + 1) * Cout), acc);
             }
           }
         }
@@ -590,11 +665,11 @@ __global__ void __launch_bounds__(kBorderThreads) deconv_border_kernel(const act
 }
 
 void launch_deconv_border(const act_t* x, const float* wt, float* e_rows, float* e_cols, int N, int Cin, int Cout, int H,
-                          int W, cudaStream_t st) {
+                          int W, cudaStream_t st, const float* coef) {
   const int len = 2 * (H > W ? H : W);
   dim3 grid((len + kBorderSeg - 1) / kBorderSeg, 4, N);
   launch_pdl(deconv_border_kernel, grid, dim3(kBorderThreads), (kBorderSeg + 2) * Cout * sizeof(float), st, x, wt, e_rows, e_cols, N, Cin,
-                                                                                             Cout, H, W);
+             Cout, H, W, coef);
 }
 
 }  // namespace gsx

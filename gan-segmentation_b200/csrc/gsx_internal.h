@@ -112,6 +112,10 @@ struct ConvGeom {
   int dbg;                     // tuning only (env GSX_DBG): 1 skip epilogue work, 2 skip MMAs, 4 skip activation loads,
                                //   8 issuers do not wait for operands (with 4: pure MMA issue rate)
   int chan_off, chan_n;        // smem table of the per-channel epilogue operands: [2][chan_n] floats (bias, noise scale)
+  int per_sample;              // 1: weights and bias differ per sample (the producer's AdaIN is folded into this conv, see
+                               //    modulate.cu): the B operand is streamed per tile from wpack + n * wpack_n_stride, the bias
+                               //    comes from e.bias_n per accumulator column (one private smem copy per epilogue warp)
+  int bias_w_off, bias_cols;   // per-warp bias copies: smem offset, floats per copy (= n_ntiles * N_tile)
   int a_off;                   // byte offset of the A stages in dynamic smem (after header + stats slots + channel table + aux)
   int tmem_cols;               // allocated TMEM columns (power of two) = acc_bufs * n_groups*n_mtiles*N_tile rounded up
   int acc_bufs;                // 2: accumulators double buffered (MMA of tile i+1 overlaps epilogue of tile i)
@@ -140,6 +144,10 @@ struct ConvEpi {
   int out_planar;              // 1: store the output phase-planar (its only consumer is a space-to-depth conv)
   const float* e_rows;         // DECONV4B border corrections: [N][2 (top,bottom)][Wo][Cout] and
   const float* e_cols;         //   [N][2 (left,right)][Ho][Cout] fp32, subtracted before noise / bias; or null
+  const float* bias_n;         // per_sample: [N][bias_cols] bias per accumulator column (layer bias + the folded AdaIN shift
+                               //   through all taps), replaces `bias`
+  const float* bdelta;         // per_sample: [N][9][bias_cols] added to the accumulators of rows on the image border (class =
+                               //   3*rowclass + colclass, 0 first / 1 interior / 2 last): minus the taps that fall outside
   unsigned char* mask;         // [N][Ho][Wo]
   float* logits;               // [N][num_classes][Ho][Wo] or null
   int num_classes;
@@ -152,6 +160,7 @@ struct ConvParams {
   ConvGeom g;
   ConvEpi e;
   const act_t* wpack;
+  size_t wpack_n_stride;       // per_sample: elements between the packed weight sets of consecutive samples (else 0)
   // per (phase, slot) tap table in device memory: {A shift in bytes, accumulator group, first-of-group, 0}.
   // (Indexing the by-value parameter arrays dynamically would make the compiler copy the whole parameter
   //  block to local memory and turn every field access of the MMA issue loop into a local load.)
@@ -167,6 +176,7 @@ struct ConvLayer {
   ConvGeom g{};                       // geometry with N-independent fields filled
   act_t* wpack_dev = nullptr;
   size_t wpack_elems = 0;
+  float* wf32_dev = nullptr;          // per-sample layers: the packed weight stream in fp32 (modulate.cu scales it per sample)
   int4* taps_dev = nullptr;           // 4 * kMaxSlots entries
 };
 void build_tap_table(const ConvGeom& g, int4* out /* 4*kMaxSlots */);
@@ -180,12 +190,14 @@ struct PlanOverride {
 
 // plan.cpp
 void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cout, int argmax_classes,
-               const PlanOverride* ov, int aux_kind = 0, int in_planar = 0);
+               const PlanOverride* ov, int aux_kind = 0, int in_planar = 0, int per_sample = 0);
 void make_noise_tensormap(CUtensorMap* tm, const void* base, int N, int H, int W, int boxW, int boxH, int boxN);
 void finish_geom_for_batch(ConvGeom& g, int N);
 // weights: CONV3/UPCONV3 (Cout,Cin,3,3); DECONV4 (Cin,Cout,4,4); CONV1 (Cout,Cin,1,1); fp32, already
 // scaled (wscale / BN folded).  Returns packed act_t host buffer in the order the kernel streams it.
-void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& out);
+void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& out, std::vector<float>* out_f32 = nullptr);
+// tap offset (dy, dx) in {-1,0,1} of every slot of a CONV3 / s2d / stacked-phase up-conv plan (input-grid units)
+void slot_offsets(const ConvLayer& L, int* dy, int* dx);
 void make_act_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, int W, int boxW, int boxH, int boxN,
                         int boxCB);
 // s2d mode: phase plane (py, px) of a blocked activation tensor, boxes in 2x2-block coordinates
@@ -197,13 +209,18 @@ void make_planar_tensormap(CUtensorMap* tm, const void* base, int C, int N, int 
 // fills p.tm[] (or p.tm_pl[][] in s2d mode) for the layer's input tensors
 void make_input_tensormaps(ConvParams& p, const ConvLayer& L, int N, const void* x0, const void* x1);
 
-// launchers (shiftconv.cu / elementwise.cu / styles.cu)
+// launchers (shiftconv.cu / elementwise.cu / styles.cu / modulate.cu)
 void launch_shiftconv(const ConvParams& p, cudaStream_t st);
+// Per-sample operands of a conv whose input's AdaIN (coef [N][Cin][2] = a, b) is folded into it: modulated 16-bit weight
+// streams wout [N][L.wpack_elems], interior bias bias_n [N][bias_cols] (layer bias `bias` [cout] included, may be null) and
+// border-class corrections bdelta [N][9][bias_cols].  Two launches.
+void launch_modulate(const ConvLayer& L, const float* coef, const float* bias, int N, act_t* wout, float* bias_n, float* bdelta,
+                     cudaStream_t st);
 
 // Border correction of the folded deconv + blur (DECONV4B).  x: blocked low-res input [Cin/8][N][H][W][8];
 // wt: the (scaled) transposed-conv weights rearranged to [4][4][Cin][Cout] fp32.
 void launch_deconv_border(const act_t* x, const float* wt, float* e_rows, float* e_cols, int N, int Cin, int Cout, int H,
-                          int W, cudaStream_t st);
+                          int W, cudaStream_t st, const float* coef = nullptr /* [N][Cin][2]: x is a*t + b of the stored t */);
 
 struct Pass1Args {            // blur? + noise + bias + lrelu + stats  (generator, first half of a block)
   const act_t* in; act_t* out;  // blocked; in may have sample stride 0 (constant tensor)
@@ -217,7 +234,7 @@ void launch_pass1(const Pass1Args& a, cudaStream_t st);
 int pass1_tiles(int H, int W);
 
 struct ApplyArgs {            // InstanceNorm + AdaIN: out = (t-mean)*rstd*(scale+1)+shift
-  const act_t* in; act_t* out;  // blocked
+  const act_t* in; act_t* out;  // blocked; out may be null (only the optional outputs below are written)
   int C, N, H, W;
   const float* coef;          // [N][C][2]: out = in * coef[..][0] + coef[..][1]  (from launch_finalize)
   // optional ToRGB fused on the un-rounded values (last layer): rgb = Wrgb[3][C] x + brgb

@@ -93,7 +93,7 @@ static int pow2_cols(int c) {
 }
 
 void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cout, int argmax_classes,
-               const PlanOverride* ov, int aux_kind, int in_planar) {
+               const PlanOverride* ov, int aux_kind, int in_planar, int per_sample) {
   L.mode = mode; L.H = H; L.W = W; L.cin0 = cin0; L.cin1 = cin1; L.cout = cout;
   ConvGeom& g = L.g;
   std::memset(&g, 0, sizeof(g));
@@ -154,7 +154,9 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   const int stats_bytes = (2 * 4 * epi_groups * 2 * cout_tile * 4 + 1023) / 1024 * 1024;
   // per-channel epilogue operands of every output channel (bias, noise scale), staged once per CTA
   const int chan_n = std::max(16, ceil_div(argmax_classes > 0 ? argmax_classes : cout, cout_tile) * cout_tile);
-  const int chan_bytes = (2 * chan_n * 4 + 1023) / 1024 * 1024;
+  // per-sample bias: one private copy per epilogue warp (no cross-warp synchronisation when the sample changes)
+  const int bias_cols = per_sample ? ceil_div(cout, cout_tile) * N_tile : 0;
+  const int chan_bytes = (2 * chan_n * 4 + 4 * epi_groups * bias_cols * 4 + 1023) / 1024 * 1024;
   const int hdr_bytes = kHeader + stats_bytes + chan_bytes;
 
   int TW = (W <= 126) ? W : ((W % 64 == 0) ? 64 : 126);
@@ -253,6 +255,8 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   g.epi_groups = epi_groups;
   g.ctas_per_sm = 1;
   g.chan_off = kHeader + stats_bytes; g.chan_n = chan_n;
+  g.per_sample = per_sample; g.bias_cols = bias_cols; g.bias_w_off = g.chan_off + 2 * chan_n * 4;
+  if (per_sample && (NB != 1 || phase_grid || g.n_ntiles != 1 || argmax_classes > 0)) { set_error("plan_conv: per-sample weights need NB = 1, one N tile, no phase grid"); return; }
   g.aux_kind = aux_kind; g.aux_off = hdr_bytes; g.aux_bytes = (int)aux_bytes;
   g.aux_bw = s2d ? TW : TW / 2; g.aux_bh = s2d ? TH : TH / 2 + 1;
   g.aux_up = aux_up; g.aux_shift = s2d ? 0 : 1;
@@ -314,13 +318,23 @@ static void up3_taps(int p, int a, int* k, int* nk) {
   else        { if (a == 0) { k[0] = 0; k[1] = 1; *nk = 2; } else { k[0] = 2; *nk = 1; } }
 }
 
-void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& out) {
+void slot_offsets(const ConvLayer& L, int* dy, int* dx) {
+  static const int kT[4] = {-1, 0, 0, 1};
+  for (int s = 0; s < L.g.n_slots; ++s) {
+    if (L.g.s2d) { dy[s] = kT[s / 4]; dx[s] = kT[s % 4]; }
+    else if (L.mode == CONV1) { dy[s] = 0; dx[s] = 0; }
+    else { dy[s] = s / 3 - 1; dx[s] = s % 3 - 1; }
+  }
+}
+
+void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& out, std::vector<float>* out_f32) {
   const ConvGeom& g = L.g;
   const int cin = L.cin0 + L.cin1, cout = L.cout;
   const int nz = g.phase_grid ? 4 : 1;
   const int k16pc = g.CBK / 2;
   const size_t tile = (size_t)g.N_tile * 16;
   out.assign((size_t)nz * g.n_ntiles * g.n_k * g.n_slots * k16pc * tile, to_act(0.f));
+  if (out_f32) out_f32->assign(out.size(), 0.f);
   const bool up = (L.mode == UPCONV3 || L.mode == DECONV4 || L.mode == DECONV4B);
 
   auto wval = [&](int z, int slot, int co, int ci) -> float {   // co: row of the MMA weight tile
@@ -391,8 +405,10 @@ void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& o
               if (!g.up_cols && co >= cout) continue;
               for (int k = 0; k < 16; ++k) {
                 const int ci = (kc * g.CBK + 2 * j) * 8 + k;
-                out[base + (size_t)(k >> 3) * (g.N_tile * 8) + (size_t)nr * 8 + (k & 7)] =
-                    to_act(wval(z, slot, co, ci));
+                const float wv = wval(z, slot, co, ci);
+                const size_t idx = base + (size_t)(k >> 3) * (g.N_tile * 8) + (size_t)nr * 8 + (k & 7);
+                out[idx] = to_act(wv);
+                if (out_f32) (*out_f32)[idx] = wv;
               }
             }
 }

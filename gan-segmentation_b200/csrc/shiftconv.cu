@@ -181,6 +181,11 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
   const int total_tiles = g.tiles_x * g.tiles_y * g.tiles_n * g.n_ntiles * (g.phase_grid ? 4 : 1);
   const int nbuf = g.acc_bufs;
   const int cols_per_buf = g.n_mtiles * g.N_tile;
+  // Work items of this CTA: round-robin over the grid, or -- per-sample layers -- one contiguous range, so that a CTA
+  // crosses a sample boundary (= reloads its resident weight set and bias) at most a few times per launch.
+  const int t_first = g.per_sample ? (int)((long long)blockIdx.x * total_tiles / gridDim.x) : (int)blockIdx.x;
+  const int t_last = g.per_sample ? (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x) : total_tiles;
+  const int t_step = g.per_sample ? 1 : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.stages; ++s) {
@@ -231,14 +236,15 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     // ================================ TMA producer =================================
     if (elect_one()) {
       const size_t b_stage_elems = (size_t)(g.b_stage_bytes / 2);
-      if (g.b_resident) {                                      // all k-chunks of the (single) weight set
+      if (g.b_resident && !g.per_sample) {                     // all k-chunks of the (single) weight set
         mbar_expect_tx(&hdr->bres_full, (uint32_t)(g.n_k * g.b_stage_bytes));
         bulk_load(b_base, p.wpack, (uint32_t)(g.n_k * g.b_stage_bytes), &hdr->bres_full);
       }
       const uint32_t stage_bytes = (uint32_t)(g.a_stage_bytes + (g.b_resident ? 0 : g.b_stage_bytes));
       pdl_wait();                                   // activations / aux tiles come from earlier kernels of the stream
       int it = 0, tlp = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tlp) {
+      int w_sample = -1;                            // sample whose weight set is resident (per-sample layers)
+      for (int t = t_first; t < t_last; t += t_step, ++tlp) {
         const TileCoord tc = decode_tile(g, t);
         if (g.aux_kind) {
           // per-tile epilogue operand (noise plane tile / residual tile), double buffered on its own barriers
@@ -250,7 +256,15 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
           else tma_load_4d(dst, &p.tm_aux, &hdr->aux_full[ab], (tc.x0 >> g.aux_shift) * 2, tc.y0 >> g.aux_shift, tc.n0,
                            tc.ntile * (g.cout_tile >> 3));
         }
-        const act_t* wsrc = p.wpack + ((size_t)(tc.phase * g.n_ntiles + tc.ntile) * g.n_k) * b_stage_elems;
+        if (g.b_resident && g.per_sample && tc.n0 != w_sample) {
+          // the resident weight set belongs to a sample: at a sample boundary wait until the MMAs that read the old
+          // set have finished (the "empty" commit of the last chunk issued covers all earlier ones), then reload
+          if (it > 0) mbar_wait_relaxed(&hdr->empty[(it - 1) % g.stages], (uint32_t)(((it - 1) / g.stages) & 1));
+          w_sample = tc.n0;
+          mbar_expect_tx(&hdr->bres_full, (uint32_t)(g.n_k * g.b_stage_bytes));
+          bulk_load(b_base, p.wpack + (size_t)tc.n0 * p.wpack_n_stride, (uint32_t)(g.n_k * g.b_stage_bytes), &hdr->bres_full);
+        }
+        const act_t* wsrc = p.wpack + (size_t)tc.n0 * p.wpack_n_stride + ((size_t)(tc.phase * g.n_ntiles + tc.ntile) * g.n_k) * b_stage_elems;
         for (int kc = 0; kc < g.n_k; ++kc, ++it) {
           const int s = it % g.stages;
           const int round = it / g.stages;
@@ -301,7 +315,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     keep_in_reg(mt_desc); keep_in_reg(idesc); keep_in_reg(a_hi); keep_in_reg(b_hi); keep_in_reg(n_k); keep_in_reg(stages);
     keep_in_reg(n_mtiles); keep_in_reg(a_stride); keep_in_reg(b_stride); keep_in_reg(n_tile);
     const uint32_t a_smem = smem_u32(a_base), b_smem = smem_u32(b_base);
-    if (g.b_resident) mbar_wait(&hdr->bres_full, 0);
+    uint32_t bres_par = 0;
+    if (g.b_resident && !g.per_sample) mbar_wait(&hdr->bres_full, 0);
     // Everything between the last MMA of a chunk and the first of the next is time the tensor pipe may run dry
     // (measured: ~1 us per work item with integer divisions and the tile decode in this path), so the stage /
     // buffer bookkeeping is incremental and only the phase (schedule selector, phase_grid layers) is decoded.
@@ -316,9 +331,16 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     uint32_t aa[16], bb[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { aa[i] = 0; bb[i] = 0; }
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+    int w_next = t_first;                           // first tile of the next sample (per-sample resident weights)
+    const int tiles_per_sample = g.tiles_x * g.tiles_y;
+    for (int t = t_first; t < t_last; t += t_step, ++tl) {
       int phase = 0;
       if (phased) { int rem; phase = fast_div(t, sp_nt, rem); }
+      if (b_res && g.per_sample && t >= w_next) {     // first tile of a sample: its weight set has to be resident
+        mbar_wait(&hdr->bres_full, bres_par);
+        bres_par ^= 1u;
+        w_next = (t / tiles_per_sample + 1) * tiles_per_sample;
+      }
       if (tl >= nbuf) mbar_wait(&hdr->tmem_empty[buf], empty_par);
       tc_fence_after();
       const uint32_t acc_base = tmem_base + (uint32_t)(buf * cols_per_buf);
@@ -396,11 +418,15 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
       chan_s[g.chan_n + i] = (GEN && e.nscale && i < e.Cout) ? __ldg(e.nscale + i) : 0.f;
     }
     named_bar_sync(1, kEpiThreads);
-    const ulonglong2* const bias_s2 = reinterpret_cast<const ulonglong2*>(chan_s);
     const ulonglong2* const ns_s2 = reinterpret_cast<const ulonglong2*>(chan_s + g.chan_n);
+    // per-sample layers (the producer's AdaIN folded into this conv): bias per accumulator column of the tile's sample,
+    // in a private copy per warp -> refreshed by the warp itself whenever its tile belongs to another sample
+    const bool per_sample = g.per_sample != 0;
+    float* const bias_w = reinterpret_cast<float*>(smem + g.bias_w_off) + (size_t)ew * g.bias_cols;
+    int bias_sample = -1;
 
     int tl = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+    for (int t = t_first; t < t_last; t += t_step, ++tl) {
       const TileCoord tc = decode_tile(g, t);
       const int buf = tl % nbuf;
       float* my_slot = stats_slots + ((size_t)(tl & 1) * kEpiWarps + ew) * slot_floats;
@@ -412,6 +438,16 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
         for (int i = lane; i < slot_floats; i += 32) my_slot[i] = 0.f;
         __syncwarp();
       }
+      if (per_sample && tc.n0 != bias_sample) {
+        bias_sample = tc.n0;
+        __syncwarp();
+        for (int i = lane; i < g.bias_cols; i += 32) bias_w[i] = __ldg(e.bias_n + (size_t)tc.n0 * g.bias_cols + i);
+        __syncwarp();
+      }
+      // image-border class of this tile's rows (per-sample layers: the folded AdaIN shift must not flow in through taps
+      // that fall outside the image; interior tiles skip the whole test)
+      const bool tile_edge = per_sample && e.bdelta != nullptr &&
+                             (tc.y0 == 0 || tc.y0 + g.TH >= g.H || tc.x0 == 0 || tc.x0 + g.TW >= g.W);
       const int ab = tl & 1;
       const uint8_t* aux = smem + g.aux_off + (size_t)ab * g.aux_bytes;
       if (g.aux_kind) mbar_wait_relaxed<32>(&hdr->aux_full[ab], (uint32_t)((tl >> 1) & 1));
@@ -513,6 +549,17 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
                 nz0 = pk2(t2.x, t2.x); nz1 = pk2(t2.y, t2.y);
               }
               tmem_ld_wait();
+              if (tile_edge) {
+                const int cls = (lc.y == 0 ? 0 : (lc.y == g.H - 1 ? 2 : 1)) * 3 + (lc.x == 0 ? 0 : (lc.x == g.W - 1 ? 2 : 1));
+                if (lc.valid && cls != 4) {
+                  const float* dp = e.bdelta + ((size_t)lc.n * 9 + cls) * g.bias_cols + ((2 * py) * cpp + c16) * 16;
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    va[i] = __float_as_uint(__uint_as_float(va[i]) + __ldg(dp + i));
+                    vb[i] = __float_as_uint(__uint_as_float(vb[i]) + __ldg(dp + cpp * 16 + i));
+                  }
+                }
+              }
               if (tile_border) {
                 // 1-pixel output border of the folded deconv+blur: subtract what the blur would have read from
                 // outside the cropped deconv output (only tiles on the image border get here)
@@ -550,8 +597,12 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
                           e.addsrc + ((((size_t)(c0 >> 3) + h) * g.N + lc.n) * (plane_out >> 2) + (size_t)lc.y * (e.Wo >> 1) + lc.x) * 8));
                   }
                   const uint32_t r4[4] = {rv.x, rv.y, rv.z, rv.w};
-                  const ulonglong2 bq0 = bias_s2[(c0 >> 2) + 2 * h], bq1 = bias_s2[(c0 >> 2) + 2 * h + 1];
+                  // bias: per channel (shared table), or per column of the two phases (per-sample layers)
+                  const ulonglong2* bpa = reinterpret_cast<const ulonglong2*>(per_sample ? bias_w + ((2 * py) * cpp + c16) * 16 : chan_s + c0) + 2 * h;
+                  const ulonglong2* bpb = reinterpret_cast<const ulonglong2*>(per_sample ? bias_w + ((2 * py + 1) * cpp + c16) * 16 : chan_s + c0) + 2 * h;
+                  const ulonglong2 bq0 = bpa[0], bq1 = bpa[1], bq2 = bpb[0], bq3 = bpb[1];
                   const f32x2 bias4[4] = {bq0.x, bq0.y, bq1.x, bq1.y};
+                  const f32x2 bias4b[4] = {bq2.x, bq2.y, bq3.x, bq3.y};
                   f32x2 ns4[4] = {0ull, 0ull, 0ull, 0ull};
                   if (GEN) {
                     const ulonglong2 nq0 = ns_s2[(c0 >> 2) + 2 * h], nq1 = ns_s2[(c0 >> 2) + 2 * h + 1];
@@ -562,7 +613,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
                   for (int k = 0; k < 4; ++k) {
                     const int j = h * 4 + k, i0 = 2 * j;
                     f32x2 a = add2(pk2u(va[i0], va[i0 + 1]), bias4[k]);
-                    f32x2 b = add2(pk2u(vb[i0], vb[i0 + 1]), bias4[k]);
+                    f32x2 b = add2(pk2u(vb[i0], vb[i0 + 1]), bias4b[k]);
                     if (GEN) { a = fma2(ns4[k], nz0, a); b = fma2(ns4[k], nz1, b); }
                     const f32x2 am = mul2(a, slope2), bm = mul2(b, slope2);
                     float a0, a1, b0, b1, m0, m1, m2, m3;
@@ -647,13 +698,21 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
               }
             }
             tmem_ld_wait();
+            if (tile_edge) {
+              const int cls = (lc.y == 0 ? 0 : (lc.y == g.H - 1 ? 2 : 1)) * 3 + (lc.x == 0 ? 0 : (lc.x == g.W - 1 ? 2 : 1));
+              if (lc.valid && cls != 4) {
+                const float* dp = e.bdelta + ((size_t)lc.n * 9 + cls) * g.bias_cols + cc * 16;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldg(dp + i));
+              }
+            }
             if (lc.valid) {
               const uint32_t w8[8] = {add0.x, add0.y, add0.z, add0.w, add1.x, add1.y, add1.z, add1.w};
               uint32_t o[8];
               f32x2 bias8[8], ns8[8];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const ulonglong2 bq = bias_s2[(c0 >> 2) + q];
+                const ulonglong2 bq = reinterpret_cast<const ulonglong2*>(per_sample ? bias_w + cc * 16 : chan_s + c0)[q];
                 bias8[2 * q] = bq.x; bias8[2 * q + 1] = bq.y;
                 ns8[2 * q] = 0ull; ns8[2 * q + 1] = 0ull;
                 if (GEN) { const ulonglong2 nq = ns_s2[(c0 >> 2) + q]; ns8[2 * q] = nq.x; ns8[2 * q + 1] = nq.y; }

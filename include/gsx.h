@@ -58,6 +58,11 @@ const char* gsx_last_error(void);
 int gsx_abi_version(void);
 /* Number of kernels this library has launched in the calling process (all handles); bench.py reports it. */
 uint64_t gsx_launch_count(void);
+/* Process-wide build-time options, read when a handle is finalized (gsx_*_finalize).
+ *   "fold_apply" (default 1): fold the AdaIN normalise+modulate step of the channel-thin generator blocks into the convs
+ *                 that consume it (per-sample modulated weights) instead of a separate pass over the tensor; 0 keeps the
+ *                 reference's operator order (networks_stylegan.py:56-73) everywhere -- for A/B tests. */
+int gsx_set_option(const char* name, int value);
 
 /* ---- generator: replaces Generator(config) / load_parameters / __call__
  *      (networks_stylegan.py:76-197, image_generator.py:20-22, :99) ---- */
