@@ -173,6 +173,7 @@ def main():
     ap.add_argument('--dtype', default=os.environ.get('GSX_DTYPE', 'fp16'), choices=['fp16', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--layers-out', default='', help='write the per-layer roofline table (TSV) here')
+    ap.add_argument('--opt', action='append', default=[], help='library option name=value (gsx_set_option), for A/B runs')
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -198,6 +199,9 @@ def main():
         dist.init_process_group('nccl', device_id=device)
     steps, warm = max(1, args.steps), max(3, args.warmup)
     B = wl['batch']
+    for o in args.opt:
+        k, v = o.split('=')
+        L.check(L.lib(args.dtype).gsx_set_option(k.encode(), int(v)), f'gsx_set_option({o})', args.dtype)
     gc, dc, gp, dp, G, D = build_models(wl, args.dtype, device)
     pipe = GeneratePipeline(G, D, B)
     lib = G._lib

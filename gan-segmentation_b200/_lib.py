@@ -81,6 +81,7 @@ _SIGS = {
     'gsx_generate_host': (_i, [_vp, _vp, _i, _fp, _fp, _u64, _u64, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _i]),
     'gsx_synth_device_counter': (_i, [_vp, _i, C.c_uint64]),
     'gsx_op_conv_wgrad': (_i, [_i, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _vp]),
+    'gsx_op_conv_wgrad_tc': (_i, [_i, _i, _i, _i, _i, _i, _fp, _fp, _fp, _vp]),
     'gsx_op_release_cache': (None, []),
     'gsx_op_upsample2': (_i, [_fp, _fp, _i, _i, _i, _i, _vp]),
     'gsx_op_sumpool2': (_i, [_fp, _fp, _i, _i, _i, _i, _vp]),

@@ -105,6 +105,7 @@ static ModBufs take_mod(Arena& a, const ConvLayer& L, int N) {
   return m;
 }
 static int g_opt_fold_apply = 1;           // gsx_set_option("fold_apply", 0/1), read when a handle is finalized
+static int g_opt_fold_deconv_maxc = 16;    // gsx_set_option("fold_deconv_maxc", C): deconv+blur folded into one kernel up to C channels
 
 // Runs one planned conv layer: builds the tensor maps for this batch / these buffers and launches.
 static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1, const ConvEpi& epi, cudaStream_t st,
@@ -285,6 +286,7 @@ extern "C" int gsx_abi_version(void) { return 2; }
 extern "C" uint64_t gsx_launch_count(void) { return g_launches.load(); }
 extern "C" int gsx_set_option(const char* name, int value) {
   if (name && std::strcmp(name, "fold_apply") == 0) { g_opt_fold_apply = value != 0; return 0; }
+  if (name && std::strcmp(name, "fold_deconv_maxc") == 0) { g_opt_fold_deconv_maxc = value; return 0; }
   set_error(std::string("unknown option: ") + (name ? name : "(null)"));
   return -1;
 }
@@ -445,8 +447,7 @@ extern "C" int gsx_synth_finalize(gsx_synth* h) {
       // epilogue into the conv -- removes the separate blur/noise/bias/lrelu/stats pass over the largest tensors
       // (measured r01: 16-channel 1024^2 layer 1.01 -> 0.81 ms; at 32 channels the heavier epilogue cancels the gain,
       //  GSX_FOLD_MAXC raises the limit for experiments)
-      const char* fm = tune_env("GSX_FOLD_MAXC");
-      const int fold_maxc = fm ? atoi(fm) : 16;
+      const int fold_maxc = g_opt_fold_deconv_maxc;
       if (deconv && b.C <= fold_maxc && b.C < 64) {
         set_error("");
         plan_conv(b.conv1, DECONV4B, b.H / 2, b.W / 2, b.Cin, 0, b.C, 0, nullptr, /*aux: noise tile*/ 1, 0, b.mod1 ? 1 : 0);

@@ -311,6 +311,11 @@ void* pool_get(size_t bytes);
 void pool_put(void* p);
 void pool_release();
 
+// wgrad.cu: tensor-core weight gradient (see there).  scratch: wgrad_scratch_floats(...) floats.
+size_t wgrad_scratch_floats(int K, int Cin, int Cout, int sms);
+bool launch_wgrad(int K, int N, int H, int W, int Cin, int Cout, int cout_real, const act_t* x, const act_t* dy, float* dw,
+                  int cin_off, int cin_total, float scale, float* scratch, cudaStream_t st);
+
 void set_error(const std::string& msg);
 bool cuda_ok(cudaError_t e, const char* what);
 

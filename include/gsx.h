@@ -61,7 +61,9 @@ uint64_t gsx_launch_count(void);
 /* Process-wide build-time options, read when a handle is finalized (gsx_*_finalize).
  *   "fold_apply" (default 1): fold the AdaIN normalise+modulate step of the channel-thin generator blocks into the convs
  *                 that consume it (per-sample modulated weights) instead of a separate pass over the tensor; 0 keeps the
- *                 reference's operator order (networks_stylegan.py:56-73) everywhere -- for A/B tests. */
+ *                 reference's operator order (networks_stylegan.py:56-73) everywhere -- for A/B tests.
+ *   "fold_deconv_maxc" (default 16): the transposed conv + blur + noise/bias/lrelu/statistics of a block run as ONE kernel
+ *                 when the block has at most this many channels (0: never). */
 int gsx_set_option(const char* name, int value);
 
 /* ---- generator: replaces Generator(config) / load_parameters / __call__
@@ -135,6 +137,10 @@ int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z_host, cons
  * first, CUDA-core version of the decoder's weight gradient (seg_solver.py:411-412 err.backward()). */
 int gsx_op_conv_wgrad(int k, int n, int h, int w, int cin, int cout, const float* x_dev, const float* dy_dev,
                       float* dw_dev, float* db_dev, gsx_stream stream);
+/* The same weight gradient on tcgen05 tensor cores (csrc/wgrad.cu): a split-K GEMM over the pixels with the blocked
+ * activation layout read as MN-major operands, one partial per CTA, fixed-order reduction.  cin % 8 == 0, cout <= 56. */
+int gsx_op_conv_wgrad_tc(int k, int n, int h, int w, int cin, int cout, const float* x_dev, const float* dy_dev,
+                         float* dw_dev, gsx_stream stream);
 /* Train-mode BatchNorm (batch statistics, eps 1e-5) + LeakyReLU(0.2) (+ Dropout(0.5) mask) forward / backward and the
  * nearest-x2 upsample / its adjoint, fp32 NCHW (networks_seg.py:14-29, 70-78, 87).  stats_dev [3][C] = mean, biased
  * variance, rstd; dparam_dev [2][C] = dbeta, dgamma.  Deterministic (fixed-order double partial sums). */

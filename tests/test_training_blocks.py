@@ -249,3 +249,26 @@ def test_training_step_at_ffhq_size_matches_the_oracle(gsx_lib):
         ref_moved = p_ref[k] - np.asarray(params[k], np.float32)
         big = np.abs(g_ref[k]) > 0.05 * np.abs(g_ref[k]).max()
         assert np.mean(np.sign(moved[big]) == np.sign(ref_moved[big])) > 0.999, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('k,n,h,w,cin,cout', [(3, 2, 37, 53, 16, 16), (3, 1, 64, 200, 64, 32), (1, 2, 32, 32, 64, 32),
+                                               (3, 2, 16, 16, 256, 32), (3, 1, 130, 300, 32, 2), (3, 3, 8, 8, 512, 32),
+                                               (3, 1, 4, 4, 32, 32), (3, 1, 256, 256, 16, 16)])
+def test_tensor_core_wgrad_matches_autograd(gsx_lib, k, n, h, w, cin, cout):
+    """csrc/wgrad.cu (tcgen05, pixels as the GEMM K dimension, MN-major operands straight from the blocked layout) against
+    autograd on the same 16-bit-rounded operands; ragged tiles, 1x1, many-channel and 2-class (final conv) shapes."""
+    import ctypes as C
+    from gan_segmentation_b200 import _lib as L
+    lib = L.lib()
+    g = torch.Generator().manual_seed(k * 1000 + h)
+    x = torch.randn((n, cin, h, w), generator=g).half().float().cuda().requires_grad_(False)
+    dy = torch.randn((n, cout, h, w), generator=g).half().float().cuda()
+    wt = torch.zeros((cout, cin, k, k), device='cuda', requires_grad=True)
+    F.conv2d(x, wt, None, 1, k // 2).backward(dy)
+    dw = torch.empty((cout, cin, k, k), device='cuda')
+    rc = lib.gsx_op_conv_wgrad_tc(k, n, h, w, cin, cout, L.ptr(x), L.ptr(dy), L.ptr(dw), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    L.check(rc, 'gsx_op_conv_wgrad_tc')
+    ref = wt.grad
+    err = float((dw - ref).abs().max() / ref.abs().max())
+    assert err < 2e-3, err
