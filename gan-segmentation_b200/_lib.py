@@ -89,6 +89,13 @@ _SIGS = {
     'gsx_op_bn_lrelu_bwd': (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
     'gsx_softmax_ce': (_i, [_fp, _vp, _i, _i, _i, _i, _fp, _fp, C.c_float, _fp, _sz, _vp]),
     'gsx_adam_step': (_i, [_fp, _fp, _fp, _fp, _sz, _i, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
+    'gsx_train_create': (_i, [C.POINTER(DecCfg), _i, _i, C.POINTER(_vp)]),
+    'gsx_train_destroy': (None, [_vp]),
+    'gsx_train_param_count': (_i, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
+    'gsx_train_param_info': (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), C.POINTER(_sz)]),
+    'gsx_train_workspace_bytes': (_i, [_vp, C.POINTER(_sz)]),
+    'gsx_train_dropout_mask': (_i, [_vp, _i, _u64, _fp, _vp]),
+    'gsx_train_step': (_i, [_vp, _fp, _fp, C.POINTER(_vp), _vp, _vp, _vp, _u64, _fp, _vp, C.POINTER(C.c_float), _vp, _sz, _vp]),
     'gsx_profile_enable': (_i, [_i]),
     'gsx_profile_dump': (_i, [C.c_char_p, _sz]),
     'gsx_op_conv': (_i, [_i] * 7 + [_fp, _fp, _fp, _fp, _fp, _fp, _i, _fp, _fp, _fp, _vp, _fp, _i,

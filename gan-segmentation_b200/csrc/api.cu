@@ -149,6 +149,11 @@ static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1
   return cuda_ok(cudaGetLastError(), "shiftconv launch");
 }
 
+bool run_conv_layer(const ConvLayer& L, int N, const act_t* x0, const act_t* x1, const ConvEpi& epi, cudaStream_t st,
+                    const char* label) {
+  return run_conv(L, N, x0, x1, epi, st, label, nullptr);
+}
+
 static bool upload_conv(ConvLayer& L, const float* w) {
   std::vector<act_t> packed;
   std::vector<float> packed_f32;

@@ -196,6 +196,8 @@ void finish_geom_for_batch(ConvGeom& g, int N);
 // weights: CONV3/UPCONV3 (Cout,Cin,3,3); DECONV4 (Cin,Cout,4,4); CONV1 (Cout,Cin,1,1); fp32, already
 // scaled (wscale / BN folded).  Returns packed act_t host buffer in the order the kernel streams it.
 void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& out, std::vector<float>* out_f32 = nullptr);
+// gather form of the packing (4 source indices into the reference weight tensor per packed element, -1 = none)
+bool pack_conv_sources(const ConvLayer& L, std::vector<int>& src);
 // tap offset (dy, dx) in {-1,0,1} of every slot of a CONV3 / s2d / stacked-phase up-conv plan (input-grid units)
 void slot_offsets(const ConvLayer& L, int* dy, int* dx);
 void make_act_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, int W, int boxW, int boxH, int boxN,
@@ -208,6 +210,10 @@ void make_planar_tensormap(CUtensorMap* tm, const void* base, int C, int N, int 
                            int boxN, int boxCB);
 // fills p.tm[] (or p.tm_pl[][] in s2d mode) for the layer's input tensors
 void make_input_tensormaps(ConvParams& p, const ConvLayer& L, int N, const void* x0, const void* x1);
+
+// api.cu: builds the tensor maps of one planned conv for this batch / these buffers and launches it
+bool run_conv_layer(const ConvLayer& L, int N, const act_t* x0, const act_t* x1, const ConvEpi& epi, cudaStream_t st,
+                    const char* label);
 
 // launchers (shiftconv.cu / elementwise.cu / styles.cu / modulate.cu)
 void launch_shiftconv(const ConvParams& p, cudaStream_t st);

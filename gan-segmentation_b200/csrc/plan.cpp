@@ -413,6 +413,60 @@ void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& o
             }
 }
 
+// The same packing as pack_conv_weights, as a gather table: every packed element is the sum of up to 4 entries of the
+// reference weight tensor (Cout,Cin,k,k) (one for plain / 1x1 / space-to-depth convs, up to four merged taps for the
+// nearest-x2 + 3x3 phases); -1 = no term.  Training re-packs the 16-bit operands from the fp32 master weights on the
+// device every step (train_step.cu: pack_kernel).  CONV3 / CONV1 / UPCONV3 only.
+bool pack_conv_sources(const ConvLayer& L, std::vector<int>& src) {
+  const ConvGeom& g = L.g;
+  if (L.mode != CONV3 && L.mode != CONV1 && L.mode != UPCONV3) return false;
+  const int cin = L.cin0 + L.cin1, cout = L.cout;
+  const int nz = g.phase_grid ? 4 : 1;
+  const int k16pc = g.CBK / 2;
+  const size_t tile = (size_t)g.N_tile * 16;
+  src.assign((size_t)nz * g.n_ntiles * g.n_k * g.n_slots * k16pc * tile * 4, -1);
+  auto terms = [&](int z, int slot, int co, int ci, int* out) -> void {
+    out[0] = out[1] = out[2] = out[3] = -1;
+    if (g.s2d) {
+      static const int kT[4] = {-1, 0, 0, 1}, kP[4] = {1, 0, 1, 0};
+      const int q = co / g.cout_tile, c = co % g.cout_tile;
+      if (c >= cout) return;
+      const int ky = 2 * kT[slot / 4] + kP[slot / 4] - (q >> 1), kx = 2 * kT[slot % 4] + kP[slot % 4] - (q & 1);
+      if (ky < -1 || ky > 1 || kx < -1 || kx > 1) return;
+      out[0] = ((c * cin + ci) * 3 + ky + 1) * 3 + kx + 1;
+      return;
+    }
+    if (L.mode == CONV3) { if (co < cout) out[0] = (co * cin + ci) * 9 + slot; return; }
+    if (L.mode == CONV1) { if (co < cout) out[0] = co * cin + ci; return; }
+    int ph, a, b;
+    if (g.phase_grid) { ph = z; a = slot >> 1; b = slot & 1; }
+    else {
+      ph = co / g.cout_tile; co = co % g.cout_tile;
+      a = slot / 3 - (ph >> 1); b = slot % 3 - (ph & 1);
+      if (a < 0 || a > 1 || b < 0 || b > 1) return;
+    }
+    if (co >= cout) return;
+    int ky[2], kx[2], nky, nkx, n = 0;
+    up3_taps(ph >> 1, a, ky, &nky); up3_taps(ph & 1, b, kx, &nkx);
+    for (int i = 0; i < nky; ++i)
+      for (int j = 0; j < nkx; ++j) out[n++] = ((co * cin + ci) * 3 + ky[i]) * 3 + kx[j];
+  };
+  size_t base = 0;
+  for (int z = 0; z < nz; ++z)
+    for (int nt = 0; nt < g.n_ntiles; ++nt)
+      for (int kc = 0; kc < g.n_k; ++kc)
+        for (int slot = 0; slot < g.n_slots; ++slot)
+          for (int j = 0; j < k16pc; ++j, base += tile)
+            for (int nr = 0; nr < g.N_tile; ++nr) {
+              const int co = g.up_cols ? nr : nt * g.N_tile + nr;
+              for (int k = 0; k < 16; ++k) {
+                const int ci = (kc * g.CBK + 2 * j) * 8 + k;
+                terms(z, slot, co, ci, &src[(base + (size_t)(k >> 3) * (g.N_tile * 8) + (size_t)nr * 8 + (k & 7)) * 4]);
+              }
+            }
+  return true;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -292,3 +292,140 @@ class _FlatAdamAdapter:
 
     def export(self, P):
         return dict(P)
+
+
+class ResidentTrainer:
+    """The decoder training step of the product: ONE C-ABI call per iteration (``gsx_train_step``, csrc/train_step.cu) --
+    blocked 16-bit activations resident in a workspace, tcgen05 convolutions / data gradients / weight gradients, fused
+    BatchNorm+LeakyReLU+Dropout kernels, no host synchronisation and no library kernels -- followed by the single all-reduce
+    of the flat gradient bucket (``torch.distributed``: plumbing) and the fused Adam kernel (``gsx_adam_step``).
+
+    ``step(feats, mask, dropout_seed)`` = one iteration of the reference fit loop on one rank (seg_solver.py:386-421)."""
+
+    def __init__(self, cfg, params, n, device='cuda', base_hw=(4, 4), base_lr=None, wd=None, dtype=None,
+                 beta1=0.9, beta2=0.999, eps=1e-8):
+        import ctypes as C
+        from . import _lib as L
+        self.L, self.C = L, C
+        self.cfg = cfg
+        self.n = int(n)
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.lib = L.lib(dtype)
+        self.lr = cfg['base_lr'] if base_lr is None else base_lr
+        self.wd = (cfg.get('wd', 0.0) or 0.0) if wd is None else wd
+        self.beta1, self.beta2, self.eps = beta1, beta2, eps
+        self.t = 0
+        nf = len(cfg['in_channels'])
+        c = L.DecCfg()
+        c.num_levels = nf
+        for i, v in enumerate(cfg['in_channels']):
+            c.in_channels[i] = v
+        for i, v in enumerate(cfg['features']):
+            c.features[i] = v
+        c.use_bn = int(bool(cfg['use_bn']))
+        c.base_y, c.base_x = base_hw
+        self.num_levels, self.num_classes = nf, cfg['features'][-1]
+        self.out_hw = (base_hw[0] << (nf - 1), base_hw[1] << (nf - 1))
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.gsx_train_create(C.byref(c), self.n, int(bool(cfg.get('use_dropout', False))), C.byref(h)),
+                    'gsx_train_create', dtype)
+        self._h = h
+        nl, nt = C.c_size_t(), C.c_size_t()
+        count = self.lib.gsx_train_param_count(h, C.byref(nl), C.byref(nt))
+        self.n_learn, self.n_total = nl.value, nt.value
+        self.layout = {}
+        for i in range(count):
+            name, off, cnt = C.c_char_p(), C.c_size_t(), C.c_size_t()
+            L.check(self.lib.gsx_train_param_info(h, i, C.byref(name), C.byref(off), C.byref(cnt)), 'gsx_train_param_info', dtype)
+            self.layout[name.value.decode()] = (off.value, cnt.value)
+        self.p = torch.zeros(self.n_total, dtype=torch.float32, device=self.device)
+        self.g = torch.zeros(self.n_learn, dtype=torch.float32, device=self.device)
+        self.m = torch.zeros_like(self.g)
+        self.v = torch.zeros_like(self.g)
+        self.shapes = {k: tuple(np.asarray(v).shape) for k, v in params.items()}
+        self.load(params)
+        sz = C.c_size_t()
+        L.check(self.lib.gsx_train_workspace_bytes(h, C.byref(sz)), 'gsx_train_workspace_bytes', dtype)
+        self.ws = torch.empty(sz.value, dtype=torch.uint8, device=self.device)
+        self.loss = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self.pred = torch.zeros((self.n,) + self.out_hw, dtype=torch.uint8, device=self.device)
+        self.grad_scale = 1.0
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None):
+                self.lib.gsx_train_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def view(self, buf, name):
+        off, cnt = self.layout[name]
+        return buf[off:off + cnt]
+
+    def load(self, params):
+        missing = [k for k in self.layout if k not in params]
+        if missing:
+            raise KeyError(f'missing decoder parameters: {missing[:4]}')
+        host = np.zeros(self.n_total, np.float32)
+        for k, (off, cnt) in self.layout.items():
+            a = np.asarray(params[k], np.float32).reshape(-1)
+            if a.size != cnt:
+                raise ValueError(f'parameter {k} has {a.size} elements, expected {cnt}')
+            host[off:off + cnt] = a
+        self.p.copy_(torch.from_numpy(host))
+
+    def state(self):
+        """name -> numpy float32 in the reference's shapes (what checkpoint_last.params holds)."""
+        host = self.p.detach().cpu().numpy()
+        return {k: host[off:off + cnt].reshape(self.shapes.get(k, (cnt,))).copy() for k, (off, cnt) in self.layout.items()}
+
+    def grads(self):
+        """Learnable-parameter gradients of the last step (true scale), name -> numpy."""
+        host = self.g.detach().cpu().numpy() / self.grad_scale
+        return {k: host[off:off + cnt].reshape(self.shapes.get(k, (cnt,))).copy()
+                for k, (off, cnt) in self.layout.items() if off < self.n_learn}
+
+    def dropout_mask(self, level, seed):
+        f = self.cfg['features'][level]
+        h, w = self.out_hw[0] >> (self.num_levels - 1 - level), self.out_hw[1] >> (self.num_levels - 1 - level)
+        out = torch.empty((self.n, f, h, w), dtype=torch.float32, device=self.device)
+        self.L.check(self.lib.gsx_train_dropout_mask(self._h, level, int(seed), self.L.ptr(out), self._stream()), 'dropout_mask', self.dtype)
+        return out
+
+    def _stream(self):
+        return self.C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def forward_backward(self, feats, mask, dropout_seed=0):
+        """Enqueues forward + backward; returns the per-sample loss (device tensor).  Gradients (scaled) land in ``self.g``."""
+        L, C = self.L, self.C
+        with torch.cuda.device(self.device):
+            keep = [torch.as_tensor(f, dtype=torch.float32).to(self.device).contiguous() for f in feats]
+            if len(keep) != self.num_levels or keep[0].shape[0] != self.n:
+                raise ValueError('expected %d feature maps of batch %d' % (self.num_levels, self.n))
+            ptrs = (C.c_void_p * self.num_levels)(*[t.data_ptr() for t in keep])
+            lab = torch.as_tensor(np.asarray(mask) if not torch.is_tensor(mask) else mask).to(self.device)
+            lab = lab.reshape((self.n,) + self.out_hw).to(torch.int32).contiguous()
+            gs = C.c_float(1.0)
+            rc = self.lib.gsx_train_step(self._h, L.ptr(self.p), L.ptr(self.g), ptrs, None, None, L.ptr(lab), int(dropout_seed),
+                                         L.ptr(self.loss), L.ptr(self.pred), C.byref(gs), L.ptr(self.ws), self.ws.numel(), self._stream())
+            L.check(rc, 'gsx_train_step', self.dtype)
+            self.grad_scale = float(gs.value)
+            self._keep = (keep, lab)
+        return self.loss
+
+    def step(self, feats, mask, dropout_seed=0, global_batch=None, group=None):
+        loss = self.forward_backward(feats, mask, dropout_seed)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.g, op=dist.ReduceOp.SUM, group=group)          # the step's only collective
+        self.t += 1
+        L = self.L
+        with torch.cuda.device(self.device):
+            L.check(self.lib.gsx_adam_step(L.ptr(self.p), L.ptr(self.g), L.ptr(self.m), L.ptr(self.v), self.n_learn, self.t, self.lr,
+                                           self.beta1, self.beta2, self.eps, self.wd,
+                                           1.0 / (float(global_batch or self.n) * self.grad_scale), self._stream()),
+                    'gsx_adam_step', self.dtype)
+        return loss

@@ -159,6 +159,31 @@ int gsx_softmax_ce(const float* logits_dev, const int* labels_dev, int n, int nu
 int gsx_adam_step(float* w_dev, const float* g_dev, float* m_dev, float* v_dev, size_t count, int t, float lr, float beta1,
                   float beta2, float eps, float wd, float rescale_grad, gsx_stream stream);
 
+/* ---- one decoder-training iteration behind one call (seg_solver.py:386-421; csrc/train_step.cu).
+ * gsx_train_create: decoder config (use_bn must be 1), the per-rank batch n, Dropout(0.5) after the cvt blocks on/off
+ *   (cfg['use_dropout'], networks_seg.py:77-78).  All parameters live in ONE flat fp32 device array: the learnable ones
+ *   first (conv weight/bias, BatchNorm gamma/beta, in the order of gsx_train_param_info), then the BatchNorm moving
+ *   statistics; gsx_train_param_count returns the number of entries and the two sizes, gsx_train_param_info the reference
+ *   (structural) name, offset and element count of entry `index` -- what SegSolver.save/load map to checkpoint_last.params.
+ * gsx_train_step: train-mode forward (batch statistics; moving statistics updated in params_dev), SoftmaxCE with weight
+ *   (label > -1), backward.  feats_f32_dev[level] [n,C,h,w] fp32 (the reference's features; the generator is frozen, :393),
+ *   labels_dev [n,H,W] int32 (-1 = ignore).  Writes loss_dev[n], optionally the argmax of the logits (train metric), and
+ *   *grad_scale_out * d(sum_n loss_n)/d(param) into grads_dev[learnable count]: the loss gradient is scaled by H*W for the
+ *   16-bit backward pass; the caller all-reduces grads_dev (the step's only collective) and calls gsx_adam_step with
+ *   rescale_grad = 1 / (global_batch * grad_scale).  Dropout masks are Philox bits of (dropout_seed, level, sample, element),
+ *   recomputed in the backward pass; gsx_train_dropout_mask exports one ({0,1} floats [n,C,h,w]) for parity tests.
+ *   Only enqueues work on `stream`; the workspace (gsx_train_workspace_bytes) is caller-owned. ---- */
+typedef struct gsx_train gsx_train;
+int gsx_train_create(const gsx_dec_cfg* cfg, int n, int use_dropout, gsx_train** out);
+void gsx_train_destroy(gsx_train* h);
+int gsx_train_param_count(const gsx_train* h, size_t* learnable, size_t* total);
+int gsx_train_param_info(const gsx_train* h, int index, const char** name, size_t* offset, size_t* count);
+int gsx_train_workspace_bytes(const gsx_train* h, size_t* bytes);
+int gsx_train_dropout_mask(const gsx_train* h, int level, uint64_t seed, float* out_dev, gsx_stream stream);
+int gsx_train_step(gsx_train* h, const float* params_dev, float* grads_dev, const float* const* feats_f32_dev,
+                   const gsx_synth* synth, const void* synth_ws, const int* labels_dev, uint64_t dropout_seed, float* loss_dev,
+                   uint8_t* pred_mask_dev, float* grad_scale_out, void* ws, size_t ws_bytes, gsx_stream stream);
+
 /* ---- per-launch timing of the forward passes (bench.py's per-layer roofline table): enable, run a
  *      forward, dump "label\tms\talgorithmic_bytes\talgorithmic_flops\n" lines.  Off by default. ---- */
 int gsx_profile_enable(int on);

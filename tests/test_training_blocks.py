@@ -272,3 +272,74 @@ def test_tensor_core_wgrad_matches_autograd(gsx_lib, k, n, h, w, cin, cout):
     ref = wt.grad
     err = float((dw - ref).abs().max() / ref.abs().max())
     assert err < 2e-3, err
+
+
+def _resident_case(res, n, use_dropout, seed=3):
+    from gan_segmentation_b200.config import decoder_config
+    from gan_segmentation_b200.random_init import init_decoder_params
+    cfg = dict(decoder_config(res), use_dropout=use_dropout, base_lr=1e-3)
+    params = init_decoder_params(cfg, seed=2)
+    rs = np.random.RandomState(seed)
+    feats = [rs.randn(n, c, 4 << i, 4 << i).astype(np.float32) for i, c in enumerate(cfg['in_channels'])]
+    hw = 4 << (res - 2)
+    mask = rs.randint(-1, 2, (n, 1, hw, hw)).astype(np.int64)
+    return cfg, params, feats, mask
+
+
+def _grad_errors(grads, g_ref):
+    gmax = max(float(np.abs(g).max()) for g in g_ref.values())
+    rows = []
+    for k, b in g_ref.items():
+        a = grads[k].astype(np.float64)
+        floor = 1e-3 * gmax
+        l2 = float(np.linalg.norm(a - b)) / max(float(np.linalg.norm(b)), floor * np.sqrt(b.size))
+        rows.append((l2, k))
+    return sorted(rows, reverse=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('res,n,use_dropout', [(5, 2, False), (6, 1, True), (7, 3, True)])
+def test_resident_train_step_matches_the_oracle(gsx_lib, res, n, use_dropout):
+    """gsx_train_step (one C-ABI call: forward, loss, backward on resident blocked 16-bit tensors) against
+    oracle/train_oracle.py with the same dropout masks (exported Philox bits): loss, every gradient tensor, the moving
+    statistics, and the parameters after the Adam step."""
+    from oracle import train_oracle as T
+    from gan_segmentation_b200.decoder_training import ResidentTrainer
+    cfg, params, feats, mask = _resident_case(res, n, use_dropout)
+    tr = ResidentTrainer(cfg, params, n)
+    seed = 1234
+    drops = [tr.dropout_mask(i, seed).cpu() for i in range(res - 1)] if use_dropout else None
+    if use_dropout:
+        assert 0.4 < float(drops[-1].mean()) < 0.6 and set(np.unique(drops[0].numpy())) <= {0.0, 1.0}
+    p_ref, st, loss_ref, g_ref = T.train_step(params, cfg, feats, mask, dropout_masks=drops)
+    loss = tr.step(feats, mask, dropout_seed=seed)
+    torch.cuda.synchronize()
+    assert np.allclose(loss.cpu().numpy(), loss_ref, rtol=2e-2, atol=1e-3), (loss, loss_ref)
+    rows = _grad_errors(tr.grads(), g_ref)
+    print('largest relative gradient errors:', [(k, round(e, 4)) for e, k in rows[:6]])
+    for e, k in rows:
+        assert e <= 4e-2, (k, e)
+    new = tr.state()
+    for k in p_ref:
+        if k.endswith(('running_mean', 'running_var')):
+            assert np.allclose(new[k], p_ref[k], rtol=2e-2, atol=2e-3), k
+    # the first Adam step moves a weight by ~lr * sign(g): compare the signs where the gradient is not tiny
+    for k in ('main_block_%d.0.weight' % (res - 2), 'cvt_block_1.0.weight', 'main_block_1.1.base_layers.3.weight'):
+        big = np.abs(g_ref[k]) > 0.1 * np.abs(g_ref[k]).max()
+        a = np.sign(new[k] - np.asarray(params[k], np.float32))[big]
+        b = np.sign(p_ref[k] - np.asarray(params[k], np.float32))[big]
+        assert np.mean(a == b) > 0.995, k
+
+
+@pytest.mark.gpu
+def test_resident_training_reduces_the_loss_and_is_reproducible(gsx_lib):
+    from gan_segmentation_b200.decoder_training import ResidentTrainer
+    cfg, params, feats, mask = _resident_case(6, 2, True)
+    runs = []
+    for _ in range(2):
+        tr = ResidentTrainer(cfg, params, 2, base_lr=2e-3)
+        losses = [float(tr.step(feats, mask, dropout_seed=7 + i).mean()) for i in range(10)]
+        runs.append((losses, tr.state()))
+    assert runs[0][0][-1] < 0.85 * runs[0][0][0], runs[0][0]
+    assert runs[0][0] == runs[1][0]                                         # no atomics anywhere: bit-reproducible
+    assert all(np.array_equal(runs[0][1][k], runs[1][1][k]) for k in runs[0][1])
