@@ -30,6 +30,10 @@ WORKLOADS = {
                         name='StyleGAN-cars 512x384 generator + decoder forward, batch 64/GPU (BASELINE configs[2])'),
     'bedrooms256': dict(gan='bedrooms', max_res_log2=8, base=(4, 4), batch=1, psi=1.0,
                         name='StyleGAN-bedrooms 256^2 generator + decoder forward, batch 1 (BASELINE configs[0])'),
+    # BASELINE configs[3]: decoder training, generator frozen; handled by run_train (metric: training samples/sec)
+    'ffhq_train': dict(gan='ffhq', max_res_log2=10, base=(4, 4), batch=1, psi=0.7, train=True,
+                       name='FFHQ hair decoder training on 20 synthetic annotated samples, generator frozen, batch 1/GPU, '
+                            'one decoder-gradient all-reduce per step (BASELINE configs[3])'),
 }
 
 
@@ -129,6 +133,107 @@ def cpu_oracle_rate(wl, n_samples, warm=1):
                        f'(PyTorch CPU fp32, {cores} threads); the MXNet reference is not installable offline'), times
 
 
+def run_train(args, wl, rank, world, local):
+    """BASELINE configs[3]: decoder training on 20 synthetic annotated samples (features from the frozen generator at
+    seeds 0..19, masks = disk 1 / ring 0 / rest -1), per-GPU batch B, one all-reduce of the flat gradient bucket per step.
+    value = samples/s over all ranks, device-timed; the all-reduce is timed separately with its own events."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from gan_segmentation_b200 import _lib as L
+    from gan_segmentation_b200.decoder_training import ResidentTrainer
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    B = wl['batch']
+    steps, warm = max(1, args.steps), max(4, args.warmup)
+    gc, dc, gp, dp, G, D = build_models(wl, args.dtype, device)
+    n_samples = 20
+    # the 20 annotated samples: features of the frozen generator kept on the device as fp32 NCHW (what the reference's
+    # feat_*.pickle files hold, 127 MiB each), synthetic 3-valued masks
+    feats, masks = [], []
+    H, W = G.out_hw
+    yy, xx = np.mgrid[0:H, 0:W]
+    for i in range(n_samples):
+        out = G.forward(n=1, seed=11, first_sample=i, psi=wl['psi'], return_image=False, return_features=True)
+        feats.append([f.clone() for f in out['features']])
+        rr = np.hypot(yy - H * (0.4 + 0.01 * i), xx - W * 0.5)
+        masks.append(torch.from_numpy(np.where(rr < 0.25 * H, 1, np.where(rr < 0.4 * H, 0, -1)).astype(np.int32)).to(device))
+    del G
+    cfg = dict(dc, use_dropout=True, base_lr=1e-4)
+    tr = ResidentTrainer(cfg, dp, B, device=device, base_hw=wl['base'], dtype=args.dtype)
+    stream = torch.cuda.current_stream()
+    order = np.random.RandomState(1).permutation(n_samples)
+
+    def batch(i):
+        idx = [int(order[((i * world + rank) * B + k) % n_samples]) for k in range(B)]
+        f = [torch.cat([feats[j][l] for j in idx], 0) if B > 1 else feats[idx[0]][l] for l in range(len(feats[0]))]
+        m = torch.stack([masks[j] for j in idx], 0)
+        return f, m
+
+    ar_ms = []
+
+    def step(i, timed=False):
+        f, m = batch(i)
+        tr.forward_backward(f, m, dropout_seed=(i * world + rank))
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            dist.all_reduce(tr.g, op=dist.ReduceOp.SUM)
+            e1.record(stream)
+            if timed:
+                ar_ms.append((e0, e1))
+        tr.t += 1
+        L.check(tr.lib.gsx_adam_step(L.ptr(tr.p), L.ptr(tr.g), L.ptr(tr.m), L.ptr(tr.v), tr.n_learn, tr.t, tr.lr, tr.beta1, tr.beta2,
+                                     tr.eps, tr.wd, 1.0 / (B * world * tr.grad_scale), C.c_void_p(stream.cuda_stream)), 'adam', args.dtype)
+
+    for i in range(warm):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = float(tr.loss.mean())
+    e0.record(stream)
+    for i in range(steps):
+        step(warm + i, timed=True)
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = L.launch_count() - n0
+    if rank == 0:
+        ar = [a.elapsed_time(b) for a, b in ar_ms]
+        nbytes = tr.n_learn * 4
+        line = dict(metric='decoder training samples/sec', value=steps * B * world / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=steps,
+                    warmup=warm, ms_per_step=ms / steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype=args.dtype,
+                    data='synthetic',
+                    config=dict(workload=wl['name'], batch_per_gpu=B, global_batch=B * world, samples=n_samples,
+                                features='resident in HBM as fp32 NCHW (the reference reloads a 127 MiB pickle per sample)',
+                                optimizer='Adam 1e-4, rescale 1/global batch', dropout='Philox, in-kernel',
+                                parallelism=f'data parallel over {world} GPU(s): one all-reduce of the flat {nbytes / 2**20:.1f} MiB gradient bucket per step',
+                                graph='gsx_train_step replayed from a CUDA graph'),
+                    clocks=clocks, gpu_launches=int(launches) * world if not tr.use_graph else None,
+                    gpu_launches_note='the step is replayed from a CUDA graph (~380 kernels of this library per step); only the Adam kernel is launched directly',
+                    allreduce=dict(bytes=nbytes, ms_median=statistics.median(ar) if ar else 0.0, ms_max=max(ar) if ar else 0.0),
+                    loss=dict(first=l0, last=float(tr.loss.mean())),
+                    e2e=dict(value=steps * B * world / (ms * 1e-3), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0,
+                             note='training consumes device-resident annotated samples; there is no per-step host transfer on this path'))
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return
@@ -183,6 +288,9 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
         run_reference(args, wl, rank, world)
+        return
+    if wl.get('train'):
+        run_train(args, wl, rank, world, local)
         return
 
     import numpy as np

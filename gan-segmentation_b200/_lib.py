@@ -95,6 +95,7 @@ _SIGS = {
     'gsx_train_param_info': (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), C.POINTER(_sz)]),
     'gsx_train_workspace_bytes': (_i, [_vp, C.POINTER(_sz)]),
     'gsx_train_dropout_mask': (_i, [_vp, _i, _u64, _fp, _vp]),
+    'gsx_train_set_seed_buffer': (_i, [_vp, _vp]),
     'gsx_train_step': (_i, [_vp, _fp, _fp, C.POINTER(_vp), _vp, _vp, _vp, _u64, _fp, _vp, C.POINTER(C.c_float), _vp, _sz, _vp]),
     'gsx_profile_enable': (_i, [_i]),
     'gsx_profile_dump': (_i, [C.c_char_p, _sz]),

@@ -219,8 +219,8 @@ __global__ void __launch_bounds__(256) stats_kernel(const act_t* in, float* stat
 
 int stats_tiles(int HW) { return min(16, (HW + 255) / 256); }
 
-void launch_stats(const act_t* in, float* stats_partial, int C, int N, int HW, cudaStream_t st) {
-  dim3 grid(stats_tiles(HW), (C / 8) * N);
+void launch_stats(const act_t* in, float* stats_partial, int C, int N, int HW, cudaStream_t st, int tiles) {
+  dim3 grid(tiles > 0 ? tiles : stats_tiles(HW), (C / 8) * N);
   launch_pdl(stats_kernel, grid, dim3(256), 0, st, in, stats_partial, C, N, HW);
 }
 

@@ -249,7 +249,7 @@ struct ApplyArgs {            // InstanceNorm + AdaIN: out = (t-mean)*rstd*(scal
 };
 void launch_apply(const ApplyArgs& a, cudaStream_t st);
 
-void launch_stats(const act_t* in, float* stats_partial, int C, int N, int HW, cudaStream_t st);
+void launch_stats(const act_t* in, float* stats_partial, int C, int N, int HW, cudaStream_t st, int tiles = 0 /* 0: stats_tiles(HW) */);
 int stats_tiles(int HW);
 // Sums the per-tile partials in a fixed order and turns them into the AdaIN coefficients
 //   a = rstd * (scale + 1),  b = shift - mean * a      (networks_stylegan.py:254-262, eps 1e-5)

@@ -113,6 +113,7 @@ struct BnFwdArgs {
   const act_t* z; act_t* y; const float4* bnp;
   int C, N, H, W;
   int drop_site; unsigned long long seed;      // drop_site < 0: no dropout
+  const unsigned long long* seed_dev;          // non-null: the seed is read from device memory (CUDA-graph replays)
   const act_t* addsrc;                         // blocked [C/8][N][H/2][W/2][8], nearest-upsampled and added, or null
 };
 // y = Dropout(LeakyReLU(BN(z))) (+ up2(addsrc)): one pass over the blocked tensor
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(256) bn_fwd_kernel(const BnFwdArgs a) {
     float f[8];
     t_unpack8(__ldg(reinterpret_cast<const uint4*>(z + (size_t)p * 8)), f);
     uint32_t keep = 0xFFu;
-    if (a.drop_site >= 0) keep = drop_bits(a.seed, a.drop_site, n, cb, p);
+    if (a.drop_site >= 0) keep = drop_bits(a.seed_dev ? *a.seed_dev : a.seed, a.drop_site, n, cb, p);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float pre = fmaf(f[i], ca[i], cc[i]);
@@ -153,6 +154,7 @@ struct BnBwdArgs {
   int C, N, HW, T;
   int drop_site; unsigned long long seed;
   float m;
+  const unsigned long long* seed_dev;
 };
 // g = dy * dropout' * lrelu'(pre);  partial sums of g (-> dbeta) and g * xhat (-> dgamma) per (sample, block)
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
     t_unpack8(__ldg(reinterpret_cast<const uint4*>(z + (size_t)p * 8)), f);
     t_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (size_t)p * 8)), d);
     uint32_t keep = 0xFFu;
-    if (a.drop_site >= 0) keep = drop_bits(a.seed, a.drop_site, n, cb, p);
+    if (a.drop_site >= 0) keep = drop_bits(a.seed_dev ? *a.seed_dev : a.seed, a.drop_site, n, cb, p);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float pre = fmaf(f[i], ca[i], cc[i]);
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
     t_unpack8(__ldg(reinterpret_cast<const uint4*>(z + (size_t)p * 8)), f);
     t_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (size_t)p * 8)), d);
     uint32_t keep = 0xFFu;
-    if (a.drop_site >= 0) keep = drop_bits(a.seed, a.drop_site, n, cb, p);
+    if (a.drop_site >= 0) keep = drop_bits(a.seed_dev ? *a.seed_dev : a.seed, a.drop_site, n, cb, p);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float pre = fmaf(f[i], ca[i], cc[i]);
@@ -334,6 +336,8 @@ __global__ void dropout_mask_kernel(float* out, int N, int C, int HW, int site, 
 }
 
 static int ew_grid(int HW) { return std::max(1, std::min((HW + 255) / 256, 2048)); }
+// tiles of a two-level per-channel reduction: ~4 blocks per SM over all planes, at least 1024 pixels per block
+static int t_tiles(int HW, int planes) { return std::max(1, std::min(std::min((HW + 1023) / 1024, 64), (592 + planes - 1) / planes)); }
 
 }  // namespace gsx
 
@@ -376,6 +380,7 @@ struct gsx_train {
   int4* pack_idx = nullptr;
   size_t pack_count = 0;
   float* bn_mem = nullptr;
+  const unsigned long long* seed_dev = nullptr;     // gsx_train_set_seed_buffer
   int sms = 148;
 };
 
@@ -619,6 +624,11 @@ extern "C" int gsx_train_param_info(const gsx_train* h, int index, const char** 
   *name = h->order[index].c_str(); *offset = e.first; *count = e.second;
   return 0;
 }
+extern "C" int gsx_train_set_seed_buffer(gsx_train* h, const uint64_t* seed_dev) {
+  if (!h) { set_error("null handle"); return -1; }
+  h->seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
+  return 0;
+}
 extern "C" int gsx_train_workspace_bytes(const gsx_train* h, size_t* bytes) {
   if (!h || !bytes) { set_error("bad argument"); return -1; }
   *bytes = train_layout(h, nullptr, true).total;
@@ -646,22 +656,23 @@ bool t_conv_dgrad(const TConv& c, int N, const act_t* dy, act_t* dx, cudaStream_
   return run_conv_layer(c.dgrad, N, dy, nullptr, e, st, label);
 }
 void t_bn_stats(const gsx_train* h, const TBn& b, const act_t* z, int HW, const float* p, float* r, float* stats, cudaStream_t st) {
-  launch_stats(z, stats, b.C, h->n, HW, st);
-  const int T = stats_tiles(HW);
+  // enough blocks to fill the GPU at batch 1: (C/8)*N planes x T tiles
+  const int T = t_tiles(HW, (b.C / 8) * h->n);
+  launch_stats(z, stats, b.C, h->n, HW, st, T);
   bn_finalize_kernel<<<(b.C + 63) / 64, 64, 0, st>>>(stats, h->n * T, b.C, (double)h->n * HW, p + b.gamma_off, p + b.beta_off,
                                                      r + b.rmean_off, r + b.rvar_off, b.bnp);
   g_launches += 2;
 }
 void t_bn_fwd(const gsx_train* h, const TBn& b, const act_t* z, act_t* y, int H, int W, int site, uint64_t seed, const act_t* addsrc, cudaStream_t st) {
-  BnFwdArgs a{z, y, b.bnp, b.C, h->n, H, W, site, seed, addsrc};
+  BnFwdArgs a{z, y, b.bnp, b.C, h->n, H, W, site, seed, h->seed_dev, addsrc};
   bn_fwd_kernel<<<dim3(ew_grid(H * W), (b.C / 8) * h->n), 256, 0, st>>>(a);
   g_launches++;
 }
 // dz (may alias dy) from dy, and dgamma / dbeta into the gradient bucket
 void t_bn_bwd(const gsx_train* h, const TBn& b, const act_t* z, const act_t* dy, act_t* dz, int HW, int site, uint64_t seed, float* g,
               float* stats, cudaStream_t st) {
-  const int T = std::max(1, std::min((HW + 255) / 256, 64));
-  BnBwdArgs a{z, dy, dz, b.bnp, b.dparam, stats, b.C, h->n, HW, T, site, seed, (float)h->n * (float)HW};
+  const int T = t_tiles(HW, (b.C / 8) * h->n);
+  BnBwdArgs a{z, dy, dz, b.bnp, b.dparam, stats, b.C, h->n, HW, T, site, seed, (float)h->n * (float)HW, h->seed_dev};
   bn_bwd_reduce_kernel<<<dim3(T, (b.C / 8) * h->n), 256, 0, st>>>(a);
   bn_bwd_finalize_kernel<<<(b.C + 63) / 64, 64, 0, st>>>(stats, h->n * T, b.C, g + b.gamma_off, g + b.beta_off, b.dparam);
   bn_bwd_apply_kernel<<<dim3(ew_grid(HW), (b.C / 8) * h->n), 256, 0, st>>>(a);
@@ -675,8 +686,9 @@ bool t_wgrad(const gsx_train* h, const TConv& c, const act_t* x0, const act_t* x
   return true;
 }
 void t_bias_grad(const gsx_train* h, const act_t* dy, int Cpad, int Creal, int HW, float* out, float* stats, cudaStream_t st) {
-  launch_stats(dy, stats, Cpad, h->n, HW, st);
-  chan_sum_finalize_kernel<<<1, 64, 0, st>>>(stats, h->n * stats_tiles(HW), Cpad, Creal, out);
+  const int T = t_tiles(HW, (Cpad / 8) * h->n);
+  launch_stats(dy, stats, Cpad, h->n, HW, st, T);
+  chan_sum_finalize_kernel<<<1, 64, 0, st>>>(stats, h->n * T, Cpad, Creal, out);
   g_launches += 2;
 }
 

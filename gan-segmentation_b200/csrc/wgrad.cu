@@ -34,6 +34,7 @@ struct WgradGeom {
   int x_bytes, y_bytes, stage_bytes;  // per stage
   int x_cb_stride, y_cb_stride;       // bytes between channel blocks in smem
   int q_steps;                        // K steps of 16 pixels per tile = TH * BW / 16
+  int rows;                           // valid accumulator rows per CTA = min(Cin, 128): only these reach the partials
 };
 
 struct WgradParams {
@@ -161,9 +162,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       mbar_wait_relaxed(&hdr->done, 0);
       tc_fence_after();
     }
-    float* out = p.partial + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * taps) * 128 * g.Cout;
+    float* out = p.partial + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * taps) * g.rows * g.Cout;
     const int row = quarter * 32 + lane;
-    for (int tp = 0; tp < taps; ++tp)
+    const bool live = row < g.rows && quarter * 32 < g.rows;
+    for (int tp = 0; tp < taps && quarter * 32 < g.rows; ++tp)
       for (int c = 0; c < g.Cout; c += 16) {
         uint32_t v[16];
         if (t1 > t0) {
@@ -173,10 +175,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = 0u;
         }
-        float4* o = reinterpret_cast<float4*>(out + ((size_t)tp * 128 + row) * g.Cout + c);
+        float4* o = reinterpret_cast<float4*>(out + ((size_t)tp * g.rows + row) * g.Cout + c);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          if (live) o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
       }
   }
   tc_fence_before();
@@ -186,14 +188,14 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
 
 // dW[co][ci][ky][kx] (+ optional accumulate) = scale * sum over CTAs of partial[mt][cta][tap][ci % 128][co]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int ctas, int m_tiles, int taps,
-                                    int Cin, int Cout, int cout_real, int cin_off, int cin_total, float scale) {
+                                    int Cin, int Cout, int cout_real, int cin_off, int cin_total, float scale, int rows) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = taps * Cin * cout_real;
   if (e >= total) return;
   const int tp = e % taps, ci = (e / taps) % Cin, co = e / (taps * Cin);
   const int mt = ci / 128, r = ci - mt * 128;
   float s = 0.f;
-  for (int c = 0; c < ctas; ++c) s += partial[(((size_t)(mt * ctas + c) * taps + tp) * 128 + r) * Cout + co];   // fixed order
+  for (int c = 0; c < ctas; ++c) s += partial[(((size_t)(mt * ctas + c) * taps + tp) * rows + r) * Cout + co];   // fixed order
   dw[((size_t)co * cin_total + cin_off + ci) * taps + tp] = s * scale;
 }
 
@@ -230,6 +232,7 @@ bool plan_wgrad(WgradGeom& g, int K, int N, int H, int W, int Cin, int Cout) {
   g.tiles_y = (H + g.TH - 1) / g.TH;
   g.n_tiles = g.tiles_x * g.tiles_y * N;
   g.q_steps = g.TH * BW / 16;
+  g.rows = std::min(Cin, 128);
   return true;
 }
 
@@ -251,7 +254,8 @@ bool launch_wgrad(int K, int N, int H, int W, int Cin, int Cout, int cout_real, 
   make_act_tensormap(&p.tm_x, x, Cin, N, H, W, g.BW, g.TH + K - 1, 1, g.cbx);
   make_act_tensormap(&p.tm_y, dy, Cout, N, H, W, g.BW, g.TH, 1, g.cbo);
   if (*gsx_last_error()) return false;
-  const int ctas = std::max(1, std::min(g.n_tiles, g_wg_sms / g.m_tiles));
+  // at least ~4 pixel tiles per CTA: every CTA costs a TMEM drain and a partial of taps x rows x Cout floats
+  const int ctas = std::max(1, std::min((g.n_tiles + 3) / 4, g_wg_sms / g.m_tiles));
   p.partial = scratch;
   static bool configured[64] = {false};
   int dev = 0; cudaGetDevice(&dev); dev = dev < 0 ? 0 : (dev > 63 ? 63 : dev);
@@ -259,7 +263,7 @@ bool launch_wgrad(int K, int N, int H, int W, int Cin, int Cout, int cout_real, 
   const size_t smem = 1024 + (size_t)kWgStages * g.stage_bytes;
   wgrad_kernel<<<dim3(ctas, g.m_tiles), 192, smem, st>>>(p);
   const int total = K * K * Cin * cout_real;
-  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(scratch, dw, ctas, g.m_tiles, K * K, Cin, Cout, cout_real, cin_off, cin_total, scale);
+  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(scratch, dw, ctas, g.m_tiles, K * K, Cin, Cout, cout_real, cin_off, cin_total, scale, g.rows);
   g_launches += 2;
   return cuda_ok(cudaGetLastError(), "wgrad launch");
 }

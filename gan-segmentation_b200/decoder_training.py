@@ -303,7 +303,7 @@ class ResidentTrainer:
     ``step(feats, mask, dropout_seed)`` = one iteration of the reference fit loop on one rank (seg_solver.py:386-421)."""
 
     def __init__(self, cfg, params, n, device='cuda', base_hw=(4, 4), base_lr=None, wd=None, dtype=None,
-                 beta1=0.9, beta2=0.999, eps=1e-8):
+                 beta1=0.9, beta2=0.999, eps=1e-8, use_graph=True):
         import ctypes as C
         from . import _lib as L
         self.L, self.C = L, C
@@ -352,6 +352,13 @@ class ResidentTrainer:
         self.loss = torch.zeros(self.n, dtype=torch.float32, device=self.device)
         self.pred = torch.zeros((self.n,) + self.out_hw, dtype=torch.uint8, device=self.device)
         self.grad_scale = 1.0
+        # The ~380 launches of a step are launch-bound at batch 1: after two eager steps the call is captured once in a
+        # CUDA graph and replayed (static input buffers; the dropout seed is read from device memory).
+        self.use_graph = bool(use_graph)
+        self._graph = None
+        self._calls = 0
+        self._static = None
+        self._seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
 
     def __del__(self):
         try:
@@ -398,22 +405,44 @@ class ResidentTrainer:
     def _stream(self):
         return self.C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _enqueue(self, feats, lab, dropout_seed):
+        L, C = self.L, self.C
+        ptrs = (C.c_void_p * self.num_levels)(*[t.data_ptr() for t in feats])
+        gs = C.c_float(1.0)
+        rc = self.lib.gsx_train_step(self._h, L.ptr(self.p), L.ptr(self.g), ptrs, None, None, L.ptr(lab), int(dropout_seed),
+                                     L.ptr(self.loss), L.ptr(self.pred), C.byref(gs), L.ptr(self.ws), self.ws.numel(), self._stream())
+        L.check(rc, 'gsx_train_step', self.dtype)
+        self.grad_scale = float(gs.value)
+
     def forward_backward(self, feats, mask, dropout_seed=0):
         """Enqueues forward + backward; returns the per-sample loss (device tensor).  Gradients (scaled) land in ``self.g``."""
-        L, C = self.L, self.C
+        L = self.L
         with torch.cuda.device(self.device):
             keep = [torch.as_tensor(f, dtype=torch.float32).to(self.device).contiguous() for f in feats]
             if len(keep) != self.num_levels or keep[0].shape[0] != self.n:
                 raise ValueError('expected %d feature maps of batch %d' % (self.num_levels, self.n))
-            ptrs = (C.c_void_p * self.num_levels)(*[t.data_ptr() for t in keep])
             lab = torch.as_tensor(np.asarray(mask) if not torch.is_tensor(mask) else mask).to(self.device)
             lab = lab.reshape((self.n,) + self.out_hw).to(torch.int32).contiguous()
-            gs = C.c_float(1.0)
-            rc = self.lib.gsx_train_step(self._h, L.ptr(self.p), L.ptr(self.g), ptrs, None, None, L.ptr(lab), int(dropout_seed),
-                                         L.ptr(self.loss), L.ptr(self.pred), C.byref(gs), L.ptr(self.ws), self.ws.numel(), self._stream())
-            L.check(rc, 'gsx_train_step', self.dtype)
-            self.grad_scale = float(gs.value)
-            self._keep = (keep, lab)
+            self._calls += 1
+            if not self.use_graph or self._calls <= 2:
+                L.check(self.lib.gsx_train_set_seed_buffer(self._h, None), 'set_seed_buffer', self.dtype)
+                self._enqueue(keep, lab, dropout_seed)
+                self._keep = (keep, lab)
+                return self.loss
+            if self._static is None:
+                self._static = ([torch.empty_like(t) for t in keep], torch.empty_like(lab))
+            for d, t in zip(self._static[0], keep):
+                d.copy_(t)
+            self._static[1].copy_(lab)
+            self._seed_dev.fill_(int(dropout_seed) & 0x7FFFFFFFFFFFFFFF)
+            if self._graph is None:
+                L.check(self.lib.gsx_train_set_seed_buffer(self._h, L.ptr(self._seed_dev)), 'set_seed_buffer', self.dtype)
+                torch.cuda.synchronize(self.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._enqueue(self._static[0], self._static[1], 0)
+                self._graph = graph
+            self._graph.replay()
         return self.loss
 
     def step(self, feats, mask, dropout_seed=0, global_batch=None, group=None):

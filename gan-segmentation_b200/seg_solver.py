@@ -133,11 +133,11 @@ class SegSolver:
         ``mask > -1``, backward, one all-reduce of the flat gradient bucket when ``torch.distributed`` is initialised
         (one process per GPU; the reference's in-process KVStore('nccl') sum), Adam(base_lr) with
         ``rescale_grad = 1/global batch``; ``epoch_end_callback()`` after every epoch; saves ``checkpoint_last.params``
-        and returns ``[]`` like the reference.  Runs on this repo's CUDA kernels through ``decoder_training.CudaBackend``
-        (first, functional version: single-operator hooks, not yet fast).  ``max_iters`` bounds the run (tests)."""
+        and returns ``[]`` like the reference.  Every iteration is one ``gsx_train_step`` call (``decoder_training.ResidentTrainer``: resident blocked
+        16-bit tensors, tcgen05 convs / data / weight gradients, CUDA-graph replay) + the gradient all-reduce + ``gsx_adam_step``.  ``max_iters`` bounds the run (tests)."""
         import logging
         import time
-        from .decoder_training import CudaBackend, DecoderTrainer
+        from .decoder_training import ResidentTrainer
         from .seg_datasets import CollectionDataset
         cfg = self.cfg
         if not self.keep_weights:
@@ -162,10 +162,8 @@ class SegSolver:
             print('batch size: {}'.format(bs))
             print('epoch size: {}'.format(iters_per_epoch))
         with torch.cuda.device(self.ctx[0]):
-            backend = CudaBackend(self.ctx[0])
-            trainer = DecoderTrainer(cfg, self.net.get_parameters(), backend)
+            trainer = ResidentTrainer(cfg, self.net.get_parameters(), bs, device=self.ctx[0], base_hw=self.base_hw)
             rng = np.random.RandomState(cfg['seed'])
-            gen = torch.Generator(device=self.ctx[0]).manual_seed(int(cfg['seed']) + 7919 * rank)   # dropout: per rank
             display = cfg['train_display_iters']
             done = 0
             for epoch in range(int(cfg['train_epochs'])):
@@ -179,12 +177,10 @@ class SegSolver:
                     mask = np.stack([it[1] for it in items]).astype(np.int32)
                     nfeat = len(items[0]) - 2
                     feats = [np.stack([np.asarray(it[2 + k], np.float32) for it in items]) for k in range(nfeat)]
-                    drops = None
-                    if cfg.get('use_dropout', False):
-                        drops = [(torch.rand((bs, cfg['features'][k]) + tuple(feats[k].shape[2:]), generator=gen, device=self.ctx[0]) > 0.5).float()
-                                 for k in range(nfeat)]
-                    loss = trainer.step(feats, mask, drops, global_batch=bs * world)
-                    pred = getattr(backend, 'last_mask', None)          # argmax of this step's logits (uint8, device)
+                    # Dropout masks: Philox bits of (seed, level, sample, element) inside the kernels; one seed per (step, rank)
+                    drop_seed = (int(cfg['seed']) << 40) + (done * world + rank)
+                    loss = trainer.step(feats, mask, dropout_seed=drop_seed, global_batch=bs * world)
+                    pred = trainer.pred                                 # argmax of this step's logits (uint8, device)
                     if pred is not None:
                         hit = int((pred.cpu().numpy().astype(np.int32) == mask.reshape(pred.shape)).sum())
                         correct += hit; total += mask.size; ep_correct += hit; ep_total += mask.size
@@ -206,7 +202,6 @@ class SegSolver:
                 if max_iters is not None and done >= max_iters:
                     break
             self.set_parameters(trainer.state())
-            backend.lib.gsx_op_release_cache()             # the single-operator hooks keep their scratch memory: return it
         self.is_trained = True
         if rank == 0:                                     # every rank holds the same weights; one writer
             self.save()

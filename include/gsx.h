@@ -180,6 +180,9 @@ int gsx_train_param_count(const gsx_train* h, size_t* learnable, size_t* total);
 int gsx_train_param_info(const gsx_train* h, int index, const char** name, size_t* offset, size_t* count);
 int gsx_train_workspace_bytes(const gsx_train* h, size_t* bytes);
 int gsx_train_dropout_mask(const gsx_train* h, int level, uint64_t seed, float* out_dev, gsx_stream stream);
+/* CUDA-graph replays of a captured step: with a seed buffer set (one uint64 in device memory; NULL switches it off) the
+ * kernels read the dropout seed from there instead of the dropout_seed argument baked into the captured launches. */
+int gsx_train_set_seed_buffer(gsx_train* h, const uint64_t* seed_dev);
 int gsx_train_step(gsx_train* h, const float* params_dev, float* grads_dev, const float* const* feats_f32_dev,
                    const gsx_synth* synth, const void* synth_ws, const int* labels_dev, uint64_t dropout_seed, float* loss_dev,
                    uint8_t* pred_mask_dev, float* grad_scale_out, void* ws, size_t ws_bytes, gsx_stream stream);

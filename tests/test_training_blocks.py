@@ -343,3 +343,76 @@ def test_resident_training_reduces_the_loss_and_is_reproducible(gsx_lib):
     assert runs[0][0][-1] < 0.85 * runs[0][0][0], runs[0][0]
     assert runs[0][0] == runs[1][0]                                         # no atomics anywhere: bit-reproducible
     assert all(np.array_equal(runs[0][1][k], runs[1][1][k]) for k in runs[0][1])
+
+
+@pytest.mark.gpu
+def test_resident_train_step_at_ffhq_size(gsx_lib):
+    """BASELINE config 4's own size for the product's training step: max_res_log2 = 10 (1024^2 logits), batch 1, against the
+    fp32 autograd oracle; same bounds as the hook-based step above (relative L2 error of every gradient tensor)."""
+    from oracle import train_oracle as T
+    from gan_segmentation_b200.config import decoder_config
+    from gan_segmentation_b200.decoder_training import ResidentTrainer
+    from gan_segmentation_b200.random_init import init_decoder_params
+    cfg = dict(decoder_config(10), use_dropout=False, base_lr=1e-4)
+    params = init_decoder_params(cfg, seed=2)
+    rs = np.random.RandomState(5)
+    feats = [rs.randn(1, c, 4 << i, 4 << i).astype(np.float32) for i, c in enumerate(cfg['in_channels'])]
+    yy, xx = np.mgrid[0:1024, 0:1024]
+    rr = np.hypot(yy - 500, xx - 540)
+    mask = np.where(rr < 260, 1, np.where(rr < 420, 0, -1)).astype(np.int64)[None, None]
+    p_ref, st, loss_ref, g_ref = T.train_step(params, cfg, feats, mask)
+    tr = ResidentTrainer(cfg, params, 1)
+    loss = tr.step(feats, mask)
+    torch.cuda.synchronize()
+    assert tr.grad_scale == 1024 * 1024
+    assert abs(float(loss[0]) - float(loss_ref[0])) < 2e-2 * abs(float(loss_ref[0]))
+    rows = _grad_errors(tr.grads(), g_ref)
+    print('largest relative gradient errors:', [(k, round(e, 4)) for e, k in rows[:6]])
+    for e, k in rows:
+        assert e <= 4e-2, (k, e)
+    pred = tr.pred.cpu().numpy()
+    assert pred.shape == (1, 1024, 1024) and set(np.unique(pred)) <= {0, 1}
+
+
+def _nccl_worker(rank, world, port, q):
+    import os
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    from gan_segmentation_b200.decoder_training import ResidentTrainer
+    cfg, params, feats, mask = _resident_case(6, 2, False)
+    tr = ResidentTrainer(cfg, params, 1, device=f'cuda:{rank}', base_lr=1e-3)
+    tr.step([f[rank:rank + 1] for f in feats], mask[rank:rank + 1], global_batch=world)
+    torch.cuda.synchronize()
+    st = tr.state()
+    q.put((rank, {k: st[k] for k in ('cvt_block_0.0.weight', 'main_block_4.0.bias', 'main_block_1.1.base_layers.1.gamma')}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_data_parallel_resident_step_two_gpus_nccl(gsx_lib):
+    """Two ranks, one sample each, ONE NCCL all-reduce of the flat gradient bucket, identical Adam step on both ranks: the
+    weights agree bit for bit across the ranks and match the single-rank batch-2 step (same summed gradient, 1/2 rescale;
+    BatchNorm statistics stay per rank, use_sync_bn = False in the reference, so only near-equality there)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, 29731, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    for k in got[0]:
+        assert np.array_equal(got[0][k], got[1][k]), k
+    from gan_segmentation_b200.decoder_training import ResidentTrainer
+    cfg, params, feats, mask = _resident_case(6, 2, False)
+    one = ResidentTrainer(cfg, params, 2, base_lr=1e-3)
+    one.step(feats, mask)
+    st = one.state()
+    for k in got[0]:
+        assert np.abs(got[0][k] - st[k]).max() < 2.5e-3, k            # first Adam step: |dw| = lr, sign flips where g ~ 0
