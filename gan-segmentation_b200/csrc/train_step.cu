@@ -714,6 +714,8 @@ extern "C" int gsx_train_step(gsx_train* h, const float* params_dev, float* grad
   // 16-bit operand streams of every conv (forward + data gradient) from the fp32 master weights
   pack_kernel<<<std::max(1, std::min((int)((h->pack_count + 255) / 256), 1184)), 256, 0, st>>>(P, h->pack_idx, h->wpack_all, h->pack_count);
   g_launches++;
+  // gradient bucket: every entry is written exactly once below, except the biases in front of a BatchNorm (exactly zero)
+  if (!cuda_ok(cudaMemsetAsync(G, 0, h->n_learn * sizeof(float), st), "zero grads")) return -2;
 
   // ---------------------------------------------------------------- forward (train mode)
   for (int i = 0; i < nf; ++i) {
@@ -776,7 +778,7 @@ extern "C" int gsx_train_step(gsx_train* h, const float* params_dev, float* grad
       t_bn_bwd(h, l.bn_b, w.z_b[i], d_prev_out, w.g1, 4 * HW, -1, 0, G, w.stats, st);                 // dz_b
       if (!launch_wgrad(3, N, 2 * l.H, 2 * l.W, l.fnext, l.conv_b.cout_pad, l.fnext, w.y_a[i], w.g1, G + l.conv_b.w_off, 0, l.fnext, 1.f,
                         w.wg_scratch, st)) return -2;
-      zero_kernel<<<1, 64, 0, st>>>(G + l.conv_b.b_off, l.fnext);      // bias in front of a BatchNorm: sum(dz) == 0 exactly
+      // (bias in front of a BatchNorm: sum(dz) == 0 exactly -- the bucket was zeroed at the start of the step)
       if (!t_conv_dgrad(l.conv_b, N, w.g1, w.g2, st, "t.conv_b.dgrad")) return -2;                     // dy_a
       // first conv (nearest-x2 + 3x3)
       t_bn_bwd(h, l.bn_a, w.z_a[i], w.g2, w.g1, 4 * HW, -1, 0, G, w.stats, st);                       // dz_a
@@ -787,7 +789,6 @@ extern "C" int gsx_train_step(gsx_train* h, const float* params_dev, float* grad
         if (!launch_wgrad(3, N, 2 * l.H, 2 * l.W, cm, l.conv_a.cout_pad, l.fnext, w.upx, w.g1, G + l.conv_a.w_off, 0, cm, 1.f, w.wg_scratch, st))
           return -2;
       }
-      zero_kernel<<<1, 64, 0, st>>>(G + l.conv_a.b_off, l.fnext);
       if (!t_conv_dgrad(l.conv_a, N, w.g1, w.g_up, st, "t.conv_a.dgrad")) return -2;                   // gradient at 2H x 2W
       // shortcut branch
       sumpool2_blocked_kernel<<<dim3(ew_grid(HW), (l.fnext / 8) * N), 256, 0, st>>>(d_prev_out, nullptr, w.g_sc, 0, l.H, l.W);
@@ -806,8 +807,6 @@ extern "C" int gsx_train_step(gsx_train* h, const float* params_dev, float* grad
     const act_t* d_c = dxin + (size_t)N * HW * l.c0 * (i > 0 ? 1 : 0);
     t_bn_bwd(h, l.bn_cvt, w.z_cvt[i], d_c, w.dzc, HW, drop ? i : -1, dropout_seed, G, w.stats, st);
     if (!launch_wgrad(3, N, l.H, l.W, l.cin, l.cvt.cout_pad, l.f, w.feat[i], w.dzc, G + l.cvt.w_off, 0, l.cin, 1.f, w.wg_scratch, st)) return -2;
-    zero_kernel<<<1, 64, 0, st>>>(G + l.cvt.b_off, l.f);
-    g_launches++;
     d_prev_out = dxin;                      // its first c0 channel blocks = gradient w.r.t. prev_i (level i-1's output)
   }
   return cuda_ok(cudaGetLastError(), "train step") ? 0 : -2;

@@ -136,16 +136,34 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       tc_fence_after();
+      // The issuing thread must be close to straight-line code (shiftconv.cu): descriptor low words per tap are built
+      // once per tile, the K loop only adds 16 positions (16 x 16 B = 16 descriptor units) per step.
+      const uint32_t xa = smem_u32(xs), ya = smem_u32(ys);
+      const uint32_t lbo = (128u >> 4) << 16;
+      uint32_t a_lo[9];
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) {
+        const int ky = tp / g.K, kx = tp - ky * g.K;
+        const int shift = tp < taps ? ky * g.BW + (kx - P) : 0;     // X position of dY position q: q + ky*BW + kx - P
+        a_lo[tp] = (((xa + (uint32_t)(shift * 16)) >> 4) & 0x3FFF) | lbo;
+      }
+      const uint32_t b_lo0 = ((ya >> 4) & 0x3FFF) | lbo;
+      const uint32_t a_hi = (uint32_t)(wg_desc(0, (uint32_t)g.x_cb_stride) >> 32), b_hi = (uint32_t)(wg_desc(0, (uint32_t)g.y_cb_stride) >> 32);
+      const uint32_t ncol = (uint32_t)g.Cout;
       if (elect_one()) {
-        const uint32_t xa = smem_u32(xs), ya = smem_u32(ys);
-        for (int q = 0; q < g.q_steps; ++q) {
-          const uint64_t bdesc = wg_desc(ya + (uint32_t)q * 256u, (uint32_t)g.y_cb_stride);
-          for (int tp = 0; tp < taps; ++tp) {
-            const int ky = tp / g.K, kx = tp - ky * g.K;
-            // X position of dY position q: (row + ky - P + P) * BW + xl + kx - P  (the X box starts P rows above)
-            const int shift = ky * g.BW + (kx - P);
-            const uint64_t adesc = wg_desc(xa + (uint32_t)(q * 16 + shift) * 16u, (uint32_t)g.x_cb_stride);
-            umma_f16kind(tmem_base + (uint32_t)(tp * g.Cout), adesc, bdesc, idesc, (first && q == 0) ? 0u : 1u);
+        uint32_t acc = first ? 0u : 1u;
+        if (taps == 9) {
+          for (int q = 0; q < g.q_steps; ++q) {
+            const uint32_t ko = (uint32_t)q * 16u;
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp) umma_f16kind_lohi(tmem_base + (uint32_t)tp * ncol, a_lo[tp] + ko, a_hi, b_lo0 + ko, b_hi, idesc, acc);
+            acc = 1u;
+          }
+        } else {
+          for (int q = 0; q < g.q_steps; ++q) {
+            const uint32_t ko = (uint32_t)q * 16u;
+            umma_f16kind_lohi(tmem_base, a_lo[0] + ko, a_hi, b_lo0 + ko, b_hi, idesc, acc);
+            acc = 1u;
           }
         }
         umma_commit(&hdr->empty[s]);

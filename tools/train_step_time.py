@@ -12,7 +12,7 @@ from gan_segmentation_b200.random_init import init_decoder_params
 args = [a for a in sys.argv[1:] if not a.startswith('--')]
 res = int(args[0]) if len(args) > 0 else 10
 n = int(args[1]) if len(args) > 1 else 1
-steps = int(args[2]) if len(args) > 2 else 10
+steps = max(1, int(args[2])) if len(args) > 2 else 10
 cfg = dict(decoder_config(res), use_dropout=True)
 params = init_decoder_params(cfg, seed=2)
 g = torch.Generator(device='cuda').manual_seed(0)
@@ -23,7 +23,7 @@ if '--hooks' in sys.argv:
     tr = DecoderTrainer(cfg, params, CudaBackend())
     step = lambda k: tr.step(feats, mask, drops)
 else:
-    tr = ResidentTrainer(cfg, params, n)
+    tr = ResidentTrainer(cfg, params, n, use_graph='--nograph' not in sys.argv)
     step = lambda k: tr.step(feats, mask, dropout_seed=k)
 losses = []
 for k in range(steps + 4):
