@@ -104,7 +104,7 @@ def build_models(wl, dtype, device):
     return gc, dc, gp, dp, G, D
 
 
-def cpu_oracle_rate(wl, n_samples, warm=1):
+def cpu_oracle_rate(wl, n_samples, warm=1, variants=False):
     """The oracle (PyTorch-CPU restatement of the reference; MXNet itself is not installable offline) on the
     host cores: image+mask samples/s at batch 1 (main.py:97-99 decodes one sample at a time)."""
     import numpy as np
@@ -128,9 +128,30 @@ def cpu_oracle_rate(wl, n_samples, warm=1):
         t = time.perf_counter() - t0
         if i >= warm:
             times.append(t)
-    return dict(value=1.0 / statistics.median(times), unit=UNIT, cores=cores, kind='port',
-                sample=f'{n_samples} latents at batch 1 after {warm} warm-up (median), oracle/generate_oracle.py '
-                       f'(PyTorch CPU fp32, {cores} threads); the MXNet reference is not installable offline'), times
+    out = dict(value=1.0 / statistics.median(times), unit=UNIT, cores=cores, kind='port',
+               sample=f'{n_samples} latents at batch 1 after {warm} warm-up (median), oracle/generate_oracle.py '
+                      f'(PyTorch CPU fp32, {cores} threads); the MXNet reference is not installable offline')
+    if variants:
+        # the reference's default generator batch (8, config.yml.example:5), compute only, and "as the reference
+        # drives it": generator at batch 8, every feature map through host numpy (image_generator.py:103-114), then the
+        # decoder one sample at a time (main.py:97-99).  One timed pass each (bounded sample).
+        import torch as _t
+        z = rs.randn(8, 512).astype(np.float32)
+        noise = [rs.randn(*s).astype(np.float32) for s in noise_shapes(gc, 8)]
+        t0 = time.perf_counter()
+        O.generate(gp, gc, dp, dc, z, noise, psi=wl['psi'])
+        out['batch8_value'] = 8.0 / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        with _t.no_grad():
+            img, feats = O.generator_forward(gp, gc, z, noise, wl['psi'])
+            img_u8 = O.transform_gan_back(img.numpy())
+            host = [f.numpy().copy() for f in feats]                        # .asnumpy() of the 9 feature maps
+            for k in range(8):
+                per = [_t.from_numpy(np.ascontiguousarray(h[k:k + 1])) for h in host]
+                O.argmax_mask(O.decoder_forward(dp, dc, per).numpy())
+        out['reference_driver_value'] = 8.0 / (time.perf_counter() - t0)
+        out['variants'] = 'batch8_value: batch 8 compute only; reference_driver_value: generator at batch 8, features via host numpy, decoder per sample (main.py:94-99); one pass each'
+    return out, times
 
 
 def run_train(args, wl, rank, world, local):
@@ -234,8 +255,53 @@ def run_train(args, wl, rank, world, local):
         dist.destroy_process_group()
 
 
+def make_config(wl, B, world):
+    """The workload description shared by both arms (the driver compares the two lines' config)."""
+    return dict(workload=wl['name'], batch_per_gpu=B, global_batch=B * world, psi=wl['psi'],
+                noise='on-device Philox4x32-10 keyed by (seed, global sample index, layer)',
+                weights='random init of the named architecture (seed 0 / 2), pretrained .params unavailable offline',
+                parallelism=f'latent-index sharding over {world} GPU(s), no collective',
+                l2='per-step working set (several GiB of activations) exceeds the 126 MB L2: inputs larger than L2')
+
+
+def run_reference_train(args, wl):
+    """CPU arm of the training workload: oracle/train_oracle.py (fp32 autograd restatement of seg_solver.py:386-421) on the
+    host cores, batch 1, random features of the generator's shapes."""
+    import numpy as np
+    import torch
+    from gan_segmentation_b200.config import decoder_config
+    from gan_segmentation_b200.random_init import init_decoder_params
+    from oracle import train_oracle as T
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dc = dict(decoder_config(wl['max_res_log2']), use_dropout=False, base_lr=1e-4)
+    dp = init_decoder_params(dc, seed=2)
+    rs = np.random.RandomState(0)
+    by, bx = wl['base']
+    feats = [rs.randn(1, c, by << i, bx << i).astype(np.float32) for i, c in enumerate(dc['in_channels'])]
+    H, W = by << (len(feats) - 1), bx << (len(feats) - 1)
+    mask = rs.randint(-1, 2, (1, 1, H, W)).astype(np.int64)
+    steps = max(1, min(args.steps, 3))
+    times, state = [], None
+    for i in range(1 + steps):
+        t0 = time.perf_counter()
+        dp, state, loss, _ = T.train_step(dp, dc, feats, mask, state)
+        if i >= 1:
+            times.append(time.perf_counter() - t0)
+    v = 1.0 / statistics.median(times)
+    base = dict(value=v, unit=UNIT, cores=cores, kind='port',
+                sample=f'{steps} training steps at batch 1 after 1 warm-up (median), oracle/train_oracle.py (PyTorch CPU fp32 autograd, {cores} threads)')
+    emit(dict(metric='decoder training samples/sec', value=v, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=1,
+              ms_per_step=1e3 * statistics.mean(times), higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+              data='synthetic', impl='reference', config=dict(workload=wl['name']), cpu_baseline=base, gpu_launches=0,
+              e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0)))
+
+
 def run_reference(args, wl, rank, world):
     if rank != 0:
+        return
+    if wl.get('train'):
+        run_reference_train(args, wl)
         return
     steps, warm = max(1, args.steps), max(0, args.warmup)
     steps = min(steps, 8)                                  # bounded: ~2 s per 1024^2 sample on 8 cores
@@ -243,7 +309,7 @@ def run_reference(args, wl, rank, world):
     ms = 1e3 * statistics.mean(times)
     line = dict(metric=METRIC, value=base['value'], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=min(warm, 1),
                 ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                impl='reference', config=dict(workload=wl['name'], step='1 latent (bounded sample of the batch)'),
+                impl='reference', config=make_config(wl, wl['batch'], max(1, args.gpus)),
                 cpu_baseline=dict(base), gpu_launches=0,
                 e2e=dict(value=base['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
@@ -381,12 +447,12 @@ def main():
     lib.gsx_profile_enable(0)
     rows = []
     for ln in buf.value.decode().strip().split('\n'):
-        lab, ms, by, fl = ln.split('\t')
-        rows.append(dict(label=lab, ms=float(ms), bytes=float(by), flops=float(fl)))
+        lab, ms, by, fl, fx, kern = (ln.split('\t') + ['', ''])[:6]
+        rows.append(dict(label=lab, ms=float(ms), bytes=float(by), flops=float(fl), flops_exec=float(fx or 0), kernel=kern))
     agg = {}
     for r in rows:
-        a = agg.setdefault(r['label'], dict(label=r['label'], ms=0.0, bytes=0.0, flops=0.0, launches=0))
-        a['ms'] += r['ms']; a['bytes'] += r['bytes']; a['flops'] += r['flops']; a['launches'] += 1
+        a = agg.setdefault(r['label'], dict(label=r['label'], ms=0.0, bytes=0.0, flops=0.0, flops_exec=0.0, launches=0, kernel=r['kernel']))
+        a['ms'] += r['ms']; a['bytes'] += r['bytes']; a['flops'] += r['flops']; a['flops_exec'] += r['flops_exec']; a['launches'] += 1
     ridge = pk['tensor'] * 1e12 / (pk['hbm'] * 1e9)
     table = []
     for a in agg.values():
@@ -396,25 +462,32 @@ def main():
         bound = 'tensor' if ai > ridge else 'hbm'
         ach = a['flops'] / (a['ms'] * 1e-3) / 1e12 if bound == 'tensor' else a['bytes'] / (a['ms'] * 1e-3) / 1e9
         peak = pk['tensor'] if bound == 'tensor' else pk['hbm']
-        table.append(dict(a, bound=bound, achieved=ach, peak=peak, frac=ach / peak,
+        # tensor-class layers: also the fraction on the flops the tensor cores actually execute (phase-decomposed up-convs
+        # execute 2.25x fewer than the dense-equivalent count)
+        frac_exec = a['flops_exec'] / (a['ms'] * 1e-3) / 1e12 / pk['tensor'] if a['flops_exec'] else 0.0
+        table.append(dict(a, bound=bound, achieved=ach, peak=peak, frac=ach / peak, frac_exec=frac_exec,
                           unit='TFLOP/s' if bound == 'tensor' else 'GB/s'))
     table.sort(key=lambda t: -t['ms'])
     step_ms_profiled = sum(t['ms'] for t in table)
     if args.layers_out:
         with open(args.layers_out, 'w') as f:
-            f.write('label\tlaunches\tms\tshare\tbound\talg_GB\talg_GFLOP\tachieved\tunit\tfrac_of_%s_peak\n' % pk['src'])
+            f.write('label\tkernel\tlaunches\tms\tshare\tbound\talg_GB\talg_GFLOP\texec_GFLOP\tachieved\tunit\tfrac_of_%s_peak\ttensor_frac_on_executed_flops\n' % pk['src'])
             for t in table:
-                f.write(f"{t['label']}\t{t['launches']}\t{t['ms']:.4f}\t{t['ms'] / step_ms_profiled:.4f}\t{t['bound']}\t"
-                        f"{t['bytes'] / 1e9:.4f}\t{t['flops'] / 1e9:.2f}\t{t['achieved']:.1f}\t{t['unit']}\t{t['frac']:.3f}\n")
+                f.write(f"{t['label']}\t{t['kernel'] or '-'}\t{t['launches']}\t{t['ms']:.4f}\t{t['ms'] / step_ms_profiled:.4f}\t{t['bound']}\t"
+                        f"{t['bytes'] / 1e9:.4f}\t{t['flops'] / 1e9:.2f}\t{t['flops_exec'] / 1e9:.2f}\t{t['achieved']:.1f}\t{t['unit']}\t{t['frac']:.3f}\t"
+                        f"{t['frac_exec']:.3f}\n")
     top = table[0]
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.workload, {}).get(top['label'])
-    roofline = dict(kernel=f"shiftconv_kernel [{top['label']}]" if '.conv' in top['label'] or 'cvt' in top['label'] or
-                    'final' in top['label'] or 'shortcut' in top['label'] else top['label'],
+    kshare = sum(t['ms'] for t in table if t['kernel'] == top['kernel']) / step_ms_profiled if top['kernel'] else None
+    roofline = dict(kernel=f"{top['kernel']} [{top['label']}]" if top['kernel'] else top['label'],
                     bound=top['bound'], achieved=top['achieved'], peak=top['peak'], unit=top['unit'], frac=top['frac'],
                     traffic=traffic, peak_source=pk['src'], share_of_step=top['ms'] / step_ms_profiled,
+                    kernel_share_of_step=kshare,
+                    note='achieved = algorithmic bytes (or dense-equivalent flops) of the dominant LAUNCH / its CUDA-event time; '
+                         'share_of_step is that launch, kernel_share_of_step all launches of the same __global__ function',
                     whole_step=dict(hbm_frac=sum(t['bytes'] for t in table if t['bound'] == 'hbm') / 1e9 /
                                     (sum(t['ms'] for t in table if t['bound'] == 'hbm') * 1e-3 + 1e-12) / pk['hbm'],
                                     tensor_frac=sum(t['flops'] for t in table if t['bound'] == 'tensor') / 1e12 /
@@ -422,16 +495,12 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        cpu, _ = cpu_oracle_rate(wl, 5 if wl['max_res_log2'] >= 10 else 10)
+        cpu, _ = cpu_oracle_rate(wl, 4 if wl['max_res_log2'] >= 10 else 10, variants=True)
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=steps, warmup=warm,
                 ms_per_step=ms_total / steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype=args.dtype, data='synthetic',
-                config=dict(workload=wl['name'], batch_per_gpu=B, global_batch=B * world, psi=wl['psi'],
-                            noise='on-device Philox4x32-10 keyed by (seed, global sample index, layer)',
-                            weights='random init of the named architecture (seed 0 / 2), pretrained .params unavailable offline',
-                            parallelism=f'latent-index sharding over {world} GPU(s), no collective',
-                            l2='per-step working set (~%.1f GiB) exceeds the 126 MB L2' % ((pipe.gws.numel() + pipe.dws.numel()) / 2 ** 30)),
+                config=make_config(wl, B, world), workspace_gib=(pipe.gws.numel() + pipe.dws.numel()) / 2 ** 30,
                 clocks=clocks, gpu_launches=launches * world,
                 e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=ms_e2e / steps, h2d_bytes_per_step=pipe.h2d_bytes * world,
                          d2h_bytes_per_step=pipe.d2h_bytes * world,

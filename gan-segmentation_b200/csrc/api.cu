@@ -70,14 +70,18 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Optional per-launch timing (bench.py's per-layer roofline table): CUDA events around every launch
 // of a forward pass, on the caller's stream.  Off on the hot path.
-struct ProfRec { std::string label; double bytes, flops; cudaEvent_t e0, e1; };
+struct ProfRec { std::string label; double bytes, flops, flops_exec; std::string kernel; cudaEvent_t e0, e1; };
 static std::vector<ProfRec> g_prof;
 static bool g_prof_on = false;
 struct ProfScope {
   cudaStream_t st; bool on;
-  ProfScope(const std::string& label, double bytes, double flops, cudaStream_t s) : st(s), on(g_prof_on) {
+  // flops: dense count of the reference formulation; flops_exec: what the tensor cores are actually asked to do (phase /
+  // space-to-depth decompositions, zero weight blocks of stacked phases included; tile halo rows excluded); kernel: the
+  // __global__ function behind the label
+  ProfScope(const std::string& label, double bytes, double flops, cudaStream_t s, double flops_exec = 0, const char* kernel = "")
+      : st(s), on(g_prof_on) {
     if (!on) return;
-    ProfRec r{label, bytes, flops, nullptr, nullptr};
+    ProfRec r{label, bytes, flops, flops_exec, kernel, nullptr, nullptr};
     cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
     cudaEventRecord(r.e0, st);
     g_prof.push_back(r);
@@ -118,7 +122,11 @@ static bool run_conv(const ConvLayer& L, int N, const act_t* x0, const act_t* x1
   if (epi.addsrc) bytes += 2.0 * out_px / 4 * L.cout;
   const double taps = L.mode == CONV1 ? 1 : ((L.mode == DECONV4 || L.mode == DECONV4B) ? 4 : 9);    // per OUTPUT pixel
   const double flops = 2.0 * out_px * taps * (L.cin0 + L.cin1) * L.cout;
-  ProfScope ps(label, bytes, flops, st);
+  // executed: every GEMM row (input-resolution pixel, or 2x2 block in the space-to-depth plan; x4 phase work items) times
+  // slots x Cin x all N columns
+  const double rows = (double)N * L.g.H * L.g.W * (L.g.phase_grid ? 4 : 1);
+  const double flops_exec = 2.0 * rows * L.g.n_slots * (L.cin0 + L.cin1) * L.g.N_tile * L.g.n_ntiles;
+  ProfScope ps(label, bytes, flops, st, flops_exec, "shiftconv_kernel");
   ConvParams p;
   p.g = L.g;
   finish_geom_for_batch(p.g, N);
@@ -1046,7 +1054,8 @@ extern "C" int gsx_profile_dump(char* buf, size_t cap) {
   for (auto& r : g_prof) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.e0, r.e1);
-    const int n = snprintf(buf + off, cap - off, "%s\t%.6f\t%.0f\t%.0f\n", r.label.c_str(), ms, r.bytes, r.flops);
+    const int n = snprintf(buf + off, cap - off, "%s\t%.6f\t%.0f\t%.0f\t%.0f\t%s\n", r.label.c_str(), ms, r.bytes, r.flops, r.flops_exec,
+                           r.kernel.c_str());
     if (n < 0 || (size_t)n >= cap - off) break;
     off += (size_t)n;
     cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);

@@ -188,7 +188,8 @@ int gsx_train_step(gsx_train* h, const float* params_dev, float* grads_dev, cons
                    uint8_t* pred_mask_dev, float* grad_scale_out, void* ws, size_t ws_bytes, gsx_stream stream);
 
 /* ---- per-launch timing of the forward passes (bench.py's per-layer roofline table): enable, run a
- *      forward, dump "label\tms\talgorithmic_bytes\talgorithmic_flops\n" lines.  Off by default. ---- */
+ *      forward, dump "label\tms\talgorithmic_bytes\talgorithmic_flops\texecuted_flops\tkernel\n" lines (executed = what the
+ *      tensor cores are asked to do after the phase / space-to-depth decompositions).  Off by default. ---- */
 int gsx_profile_enable(int on);
 int gsx_profile_dump(char* buf, size_t cap);
 
