@@ -73,6 +73,7 @@ extern "C" int gsx_op_conv(int mode, int n, int h, int w, int cin0, int cin1, in
   p.g = L.g;
   finish_geom_for_batch(p.g, n);
   p.wpack = wp;
+  p.wpack_n_stride = 0;
   p.taps = taps_d;
   ConvEpi e{};
   e.out = ob; e.Ho = Ho; e.Wo = Wo; e.up = up ? 1 : 0; e.flags = flags; e.Cout = cout;
