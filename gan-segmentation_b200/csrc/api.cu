@@ -213,6 +213,8 @@ struct gsx_synth {
   int last_n = 0;
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};   // gsx_generate_host pipelining
   unsigned long long* d_counter = nullptr;   // running global sample index in HBM (gsx_synth_device_counter; CUDA-graph replays)
+  cudaStream_t side = nullptr;               // the Philox noise fill runs here, concurrently with the mapping network
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   int nf(int r) const {
     const int f = (int)(cfg.fmap_base / std::pow(2.0, (r - 1) * (double)cfg.fmap_decay));
@@ -332,6 +334,9 @@ extern "C" void gsx_synth_destroy(gsx_synth* h) {
   if (!h) return;
   for (int i = 0; i < 2; ++i) { if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); }
   cudaFree(h->d_counter);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (int i = 0; i < 8; ++i) { cudaFree(h->d_map_w[i]); cudaFree(h->d_map_b[i]); }
   cudaFree(h->d_aff_w); cudaFree(h->d_aff_b); cudaFree(h->d_unit_layer); cudaFree(h->d_latent_avg);
   cudaFree(h->d_psi); cudaFree(h->d_wrgb); cudaFree(h->d_brgb); cudaFree(h->d_const);
@@ -566,18 +571,7 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     if (!cuda_ok(cudaMemcpyAsync(w.psi, psi_host, h->nlayers * sizeof(float), cudaMemcpyHostToDevice, st), "copy psi")) return -2;
     psi = w.psi;
   }
-  // mapping MLP + all style affines (truncation folded in): one cooperative launch
-  {
-    MapArgs m{};
-    m.z = w.z; m.ya = w.wa; m.yb = w.wb;
-    for (int i = 0; i < 8; ++i) { m.W[i] = h->d_map_w[i]; m.b[i] = h->d_map_b[i]; }
-    m.Waff = h->d_aff_w; m.baff = h->d_aff_b; m.latent_avg = h->d_latent_avg; m.psi = psi; m.unit_layer = h->d_unit_layer;
-    m.styles = w.styles; m.N = N; m.S = h->S_total;
-    ProfScope ps("map+styles", 4.0 * (8.0 * Z * Z + (double)h->S_total * Z) + 4.0 * N * (Z + h->S_total),
-                 2.0 * N * Z * (8.0 * Z + h->S_total), st);
-    if (!launch_mapping(m, st)) { cuda_ok(cudaGetLastError(), "mapping launch"); return -2; }
-    g_launches++;
-  }
+  bool forked = false;
   // noise planes: explicit inputs, or all of them from the Philox generator in one launch
   std::vector<const float*> noise(h->nlayers);
   {
@@ -594,8 +588,26 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     if (any && all && h->nlayers <= 24) {
       size_t tot = 0;
       for (int l = 0; l < h->nlayers; ++l) tot += pl.elems[l];
+      // The noise planes depend on nothing but (seed, sample index): generate them on a side stream while the mapping
+      // network (latency-bound, 128 CTAs) runs -- fork / join by events, so the caller's stream order (and a CUDA-graph
+      // capture of it) still covers everything.  Per-launch profiling keeps the single stream.
+      cudaStream_t ns = st;
+      if (!g_prof_on) {
+        if (!h->side) {
+          cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+          cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+          cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+        }
+        if (h->side && h->ev_fork && h->ev_join) {
+          cudaEventRecord(h->ev_fork, st);
+          cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+          ns = h->side;
+          forked = true;
+        }
+      }
       ProfScope ps("noise", 4.0 * N * tot, 0, st);
-      launch_fill_noise_all(pl, h->nlayers, N, seed, first_sample, st, h->d_counter); g_launches++;
+      launch_fill_noise_all(pl, h->nlayers, N, seed, first_sample, ns, h->d_counter); g_launches++;
+      if (forked) cudaEventRecord(h->ev_join, h->side);
     } else if (any) {
       for (int l = 0; l < h->nlayers; ++l) {
         if (noise[l] != w.noise[l]) continue;
@@ -604,6 +616,19 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
       }
     }
   }
+  // mapping MLP + all style affines (truncation folded in): one cooperative launch
+  {
+    MapArgs m{};
+    m.z = w.z; m.ya = w.wa; m.yb = w.wb;
+    for (int i = 0; i < 8; ++i) { m.W[i] = h->d_map_w[i]; m.b[i] = h->d_map_b[i]; }
+    m.Waff = h->d_aff_w; m.baff = h->d_aff_b; m.latent_avg = h->d_latent_avg; m.psi = psi; m.unit_layer = h->d_unit_layer;
+    m.styles = w.styles; m.N = N; m.S = h->S_total;
+    ProfScope ps("map+styles", 4.0 * (8.0 * Z * Z + (double)h->S_total * Z) + 4.0 * N * (Z + h->S_total),
+                 2.0 * N * Z * (8.0 * Z + h->S_total), st);
+    if (!launch_mapping(m, st)) { cuda_ok(cudaGetLastError(), "mapping launch"); return -2; }
+    g_launches++;
+  }
+  if (forked) cudaStreamWaitEvent(st, h->ev_join, 0);
   h->last_n = N;
   if (h->d_counter) { launch_advance_counter(h->d_counter, (unsigned long long)N, st); g_launches++; }   // after its readers
 
@@ -619,7 +644,7 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     const ModBufs* m1 = b.mod1 ? &w.mod1[bi] : nullptr;
     if (b.mod1) {
       ProfScope ps(tag + "modulate1", 0, 0, st);
-      launch_modulate(b.conv1, coef_in, b.fold ? b.b1 : nullptr, N, m1->w, m1->bias_n, m1->bdelta, st); g_launches += 2;
+      launch_modulate(b.conv1, coef_in, b.fold ? b.b1 : nullptr, N, m1->w, m1->bias_n, m1->bdelta, st); g_launches++;
     }
     Pass1Args p1{};
     p1.out = w.bufB; p1.C = b.C; p1.N = N; p1.H = b.H; p1.W = b.W;
@@ -650,7 +675,7 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     if (b.mod2) {
       // AdaIN 1 folded into conv_2: no pass over the tensor, only the per-sample weights / bias
       ProfScope ps(tag + "modulate2", 0, 0, st);
-      launch_modulate(b.conv2, w.coef[l1], b.b2, N, m2->w, m2->bias_n, m2->bdelta, st); g_launches += 2;
+      launch_modulate(b.conv2, w.coef[l1], b.b2, N, m2->w, m2->bias_n, m2->bdelta, st); g_launches++;
     } else {
       ApplyArgs a1{};
       a1.in = w.bufB; a1.out = w.bufB; a1.C = b.C; a1.N = N; a1.H = b.H; a1.W = b.W;
@@ -955,7 +980,7 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
       if (feat_coef[i]) {
         const ModBufs& m = w.mod[i];
         { ProfScope ps("d" + std::to_string(i) + ".modulate", 0, 0, st);
-          launch_modulate(l.cvt_ps, feat_coef[i], l.b_cvt, N, m.w, m.bias_n, m.bdelta, st); g_launches += 2; }
+          launch_modulate(l.cvt_ps, feat_coef[i], l.b_cvt, N, m.w, m.bias_n, m.bdelta, st); g_launches++; }
         if (!run_conv(l.cvt_ps, N, feat[i], nullptr, e, st, ("d" + std::to_string(i) + ".cvt").c_str(), &m)) return -2;
       } else if (!run_conv(l.cvt, N, feat[i], nullptr, e, st, ("d" + std::to_string(i) + ".cvt").c_str())) return -2;
     }
@@ -1029,9 +1054,14 @@ extern "C" int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z
     if (!cuda_ok(cudaEventRecord(s->ev_done[slot], st), "record done")) return -2;
     if (!cuda_ok(cudaStreamWaitEvent(cs, s->ev_done[slot], 0), "wait done")) return -2;
   }
-  if (img_u8_host && !cuda_ok(cudaMemcpyAsync(img_u8_host, img_dev, (size_t)n * H * W * nc, cudaMemcpyDeviceToHost, cs), "D2H img"))
-    return -2;
-  if (mask_host && !cuda_ok(cudaMemcpyAsync(mask_host, mask_dev, (size_t)n * H * W, cudaMemcpyDeviceToHost, cs), "D2H mask")) return -2;
+  if (img_u8_host && mask_host == img_u8_host + ib) {
+    // image and mask sit back to back on both sides (GeneratePipeline allocates them that way): one copy per step
+    if (!cuda_ok(cudaMemcpyAsync(img_u8_host, img_dev, ib + (size_t)n * H * W, cudaMemcpyDeviceToHost, cs), "D2H img+mask")) return -2;
+  } else {
+    if (img_u8_host && !cuda_ok(cudaMemcpyAsync(img_u8_host, img_dev, (size_t)n * H * W * nc, cudaMemcpyDeviceToHost, cs), "D2H img"))
+      return -2;
+    if (mask_host && !cuda_ok(cudaMemcpyAsync(mask_host, mask_dev, (size_t)n * H * W, cudaMemcpyDeviceToHost, cs), "D2H mask")) return -2;
+  }
   if (copy_stream && !cuda_ok(cudaEventRecord(s->ev_copied[slot], cs), "record copied")) return -2;
   return 0;
 }

@@ -219,7 +219,7 @@ bool run_conv_layer(const ConvLayer& L, int N, const act_t* x0, const act_t* x1,
 void launch_shiftconv(const ConvParams& p, cudaStream_t st);
 // Per-sample operands of a conv whose input's AdaIN (coef [N][Cin][2] = a, b) is folded into it: modulated 16-bit weight
 // streams wout [N][L.wpack_elems], interior bias bias_n [N][bias_cols] (layer bias `bias` [cout] included, may be null) and
-// border-class corrections bdelta [N][9][bias_cols].  Two launches.
+// border-class corrections bdelta [N][9][bias_cols].  One launch.
 void launch_modulate(const ConvLayer& L, const float* coef, const float* bias, int N, act_t* wout, float* bias_n, float* bdelta,
                      cudaStream_t st);
 

@@ -280,8 +280,12 @@ class GeneratePipeline:
         slots = 2 if overlap else 1
         per_slot = n * (generator.latent_size * 4 + H * W * (nc + 1)) + 4096
         self.stage = torch.empty(per_slot * slots, dtype=torch.uint8, device=dev)
-        self.img_host = [torch.empty((n, H, W, nc), dtype=torch.uint8).pin_memory() for _ in range(slots)]
-        self.mask_host = [torch.empty((n, H, W), dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        # image and mask of a slot share ONE pinned buffer (mask right after the image, 1 KiB-aligned like the device
+        # staging area), so that they leave the device as a single copy
+        ib = (n * H * W * nc + 1023) // 1024 * 1024
+        self._out_host = [torch.empty(ib + n * H * W, dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        self.img_host = [b[:n * H * W * nc].view(n, H, W, nc) for b in self._out_host]
+        self.mask_host = [b[ib:ib + n * H * W].view(n, H, W) for b in self._out_host]
         self.z_host = [torch.empty((n, generator.latent_size), dtype=torch.float32).pin_memory() for _ in range(slots)]
         with torch.cuda.device(dev):
             self.copy_stream = torch.cuda.Stream() if overlap else None
