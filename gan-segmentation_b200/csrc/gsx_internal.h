@@ -189,6 +189,7 @@ struct PlanOverride {
 };
 
 // plan.cpp
+extern int g_plan_epi_groups;     // epilogue warps per TMEM lane quarter planned for new layers (2; 4 = experiment)
 void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cout, int argmax_classes,
                const PlanOverride* ov, int aux_kind = 0, int in_planar = 0, int per_sample = 0);
 void make_noise_tensormap(CUtensorMap* tm, const void* base, int N, int H, int W, int boxW, int boxH, int boxN);

@@ -81,6 +81,7 @@ void pool_release() {
   g_pool.swap(keep);
 }
 
+int g_plan_epi_groups = 2;
 static const int kSmemLimit = 227 * 1024;
 static const int kHeader = kConvHeaderBytes;
 static const int kSlack = 8192;     // garbage-tolerant over-read of the last (partial) MMA tile
@@ -149,7 +150,8 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   if (ov && ov->max_mtiles > 0) max_mt = std::min(max_mt, ov->max_mtiles);
   // 8 epilogue warps.  A 16-warp variant was measured in round 1 (with one and with two MMA issuers, dense and
   // space-to-depth plans): never faster, and it spills under its 112-register cap -- not built.
-  const int epi_groups = 2;
+  // 8 epilogue warps by default; gsx_set_option("epi_groups", 4) plans 16 (used by the kernels without the generator epilogue)
+  const int epi_groups = g_plan_epi_groups;
   if (ov && ov->epi_groups > 0 && ov->epi_groups != 2) { set_error("plan_conv: only epi_groups = 2 is built"); return; }
   const int stats_bytes = (2 * 4 * epi_groups * 2 * cout_tile * 4 + 1023) / 1024 * 1024;
   // per-channel epilogue operands of every output channel (bias, noise scale), staged once per CTA

@@ -825,11 +825,12 @@ void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
   const ConvParams& pp = p;
 #endif
   const bool gen = p.e.noise != nullptr || p.e.nscale != nullptr || (p.e.flags & EPI_STATS) != 0 || p.e.e_rows != nullptr;
-  if (p.e.flags & EPI_ARGMAX) launch_g<2, false, kEpiArgmax>(pp, grid, st);
+  const bool g4 = g.epi_groups == 4;
+  if (p.e.flags & EPI_ARGMAX) { if (g4) launch_g<4, false, kEpiArgmax>(pp, grid, st); else launch_g<2, false, kEpiArgmax>(pp, grid, st); }
   else if (gen && g.up_cols) launch_g<2, true, kEpiUpCols>(pp, grid, st);    // generator epilogues: noise + statistics (+ border)
   else if (gen) launch_g<2, true, kEpiGeneric>(pp, grid, st);
-  else if (g.up_cols) launch_g<2, false, kEpiUpCols>(pp, grid, st);
-  else launch_g<2, false, kEpiGeneric>(pp, grid, st);
+  else if (g.up_cols) { if (g4) launch_g<4, false, kEpiUpCols>(pp, grid, st); else launch_g<2, false, kEpiUpCols>(pp, grid, st); }
+  else { if (g4) launch_g<4, false, kEpiGeneric>(pp, grid, st); else launch_g<2, false, kEpiGeneric>(pp, grid, st); }
 }
 
 }  // namespace gsx
