@@ -258,6 +258,22 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&vals)[32], int 
   return vals[0];
 }
 
+// 16 values per lane x 32 lanes -> every lane L returns value (L & 15) summed over the warp (15 + 1 shuffles, fixed order)
+__device__ __forceinline__ float warp_transpose_reduce16(float (&vals)[16], int lane) {
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int half = 8 >> step;
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = upper ? vals[half + i] : vals[i];
+      const float send = upper ? vals[i] : vals[half + i];
+      vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return vals[0] + __shfl_xor_sync(0xffffffffu, vals[0], 16);
+}
+
 // ---------------------------------------------------------------- misc
 // One lane of a converged warp; lets the compiler keep the tcgen05 / TMA issue sequence in uniform
 // registers without wrapping every instruction in a per-thread loop (which `lane == 0` does).
