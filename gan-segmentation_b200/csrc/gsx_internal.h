@@ -101,6 +101,12 @@ struct ConvGeom {
   int s2d;                     // 1: 3x3 conv on the 2x2 space-to-depth grid (thin layers, see plan.cpp): H, W, TH, TW,
                                //    BH, BW count 2x2 pixel BLOCKS; a stage holds the 4 input phase planes; the 4 output
                                //    phases are column blocks of one accumulator (up_cols = 1)
+  int varn;                    // 1: stacked-phase up-conv (nearest-x2 + 3x3 / 4x4-s2 transposed conv) whose MMAs only touch the
+                               //    weight blocks of the phases a shift feeds: the 4 phase blocks sit in the accumulator in the
+                               //    cyclic order (0,0) (0,1) (1,1) (1,0), so that the 1 / 2 / 4 phases of a corner / edge / centre
+                               //    shift are one contiguous column range [slot_n0, slot_n0 + slot_n) x cout_tile (the edge shift
+                               //    (1,0) wraps and takes all 4); the centre shift is issued first (it initialises every column)
+  signed char slot_n0[kMaxSlots], slot_n[kMaxSlots];   // varn: first phase block / number of phase blocks per slot
   int n_slots;                 // filter taps per CTA
   int phase_grid;              // 1: blockIdx.z selects the phase (wide up-convs)
   int stages;
@@ -189,6 +195,7 @@ struct PlanOverride {
 };
 
 // plan.cpp
+extern int g_plan_varn;           // 1: variable-N MMAs for the stacked-phase up-convs (gsx_set_option("varn", 0/1))
 extern int g_plan_epi_groups;     // epilogue warps per TMEM lane quarter planned for new layers (2; 4 = experiment)
 void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cout, int argmax_classes,
                const PlanOverride* ov, int aux_kind = 0, int in_planar = 0, int per_sample = 0);
@@ -199,6 +206,15 @@ void finish_geom_for_batch(ConvGeom& g, int N);
 void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& out, std::vector<float>* out_f32 = nullptr);
 // gather form of the packing (4 source indices into the reference weight tensor per packed element, -1 = none)
 bool pack_conv_sources(const ConvLayer& L, std::vector<int>& src);
+// slot -> (sy, sx) in {0,1,2}^2 of the 3x3 shift grid (CONV3 / stacked-phase plans): row-major, or centre-first for varn plans
+inline void slot_yx(const ConvGeom& g, int slot, int* sy, int* sx) {
+  static const int order[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};
+  const int s = g.varn ? order[slot] : slot;
+  *sy = s / 3; *sx = s % 3;
+}
+// accumulator column block <-> output phase (py*2 + px) of a stacked-phase plan
+__host__ __device__ inline int phase_block(int varn, int py, int px) { return varn ? (py ? 3 - px : px) : 2 * py + px; }
+inline int block_phase(int varn, int blk) { static const int inv[4] = {0, 1, 3, 2}; return varn ? inv[blk] : blk; }
 // tap offset (dy, dx) in {-1,0,1} of every slot of a CONV3 / s2d / stacked-phase up-conv plan (input-grid units)
 void slot_offsets(const ConvLayer& L, int* dy, int* dx);
 void make_act_tensormap(CUtensorMap* tm, const void* base, int C, int N, int H, int W, int boxW, int boxH, int boxN,

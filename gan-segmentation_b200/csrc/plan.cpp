@@ -82,6 +82,7 @@ void pool_release() {
 }
 
 int g_plan_epi_groups = 2;
+int g_plan_varn = 1;
 static const int kSmemLimit = 227 * 1024;
 static const int kHeader = kConvHeaderBytes;
 static const int kSlack = 8192;     // garbage-tolerant over-read of the last (partial) MMA tile
@@ -245,6 +246,10 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   g.cb_stride_bytes = NB * g.BH * BW * 16;
   g.a_stage_bytes = g.cb_stride_bytes * CBK * planes;
   g.s2d = s2d; g.in_planar = in_planar;
+  // variable-N MMAs for the stacked-phase up-convs with >= 32 output channels (measured r02: d6.conv_a 0.367 -> 0.344 ms,
+  // g9.deconv 0.400 -> 0.381; at 16 channels the narrower MMAs save less than the per-MMA issue overhead they add:
+  // d7.conv_a 0.748 -> 0.773; gsx_set_option("varn", 2) forces it everywhere, 0 switches it off)
+  g.varn = (up_cols && !s2d && (mode == UPCONV3 || mode == DECONV4) && (g_plan_varn == 2 || (g_plan_varn == 1 && cout_tile >= 32))) ? 1 : 0;
   g.plane_stride = (g.cb_stride_bytes * CBK + 127) / 128 * 128;
   g.a_stage_stride = planes * g.plane_stride;
   g.b_stage_bytes = n_slots * (CBK / 2) * N_tile * 32;
@@ -282,11 +287,20 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
         g.slot_group[s] = 0; g.slot_first[s] = (s == 0);
       }
   } else if (mode == CONV3 || up_cols) {
-    for (int ky = 0; ky < 3; ++ky)
-      for (int kx = 0; kx < 3; ++kx) {
-        const int s = ky * 3 + kx;
-        g.slot_shift[0][s] = (short)(ky * BW + kx); g.slot_group[s] = 0; g.slot_first[s] = (s == 0);
+    for (int s = 0; s < 9; ++s) {
+      int ky, kx;
+      slot_yx(g, s, &ky, &kx);
+      g.slot_shift[0][s] = (short)(ky * BW + kx); g.slot_group[s] = 0; g.slot_first[s] = (s == 0);
+      g.slot_n0[s] = 0; g.slot_n[s] = 4;
+      if (g.varn) {
+        // phases fed by shift (ky,kx): py in {ky-1, ky} /\ {0,1}, px likewise; as a range of the cyclic block order
+        const int py0 = ky == 2 ? 1 : 0, py1 = ky == 0 ? 0 : 1, px0 = kx == 2 ? 1 : 0, px1 = kx == 0 ? 0 : 1;
+        int lo = 4, hi = -1, cnt = 0;
+        for (int py = py0; py <= py1; ++py)
+          for (int px = px0; px <= px1; ++px) { const int b = phase_block(1, py, px); lo = std::min(lo, b); hi = std::max(hi, b); ++cnt; }
+        if (hi - lo + 1 == cnt) { g.slot_n0[s] = (signed char)lo; g.slot_n[s] = (signed char)cnt; }      // contiguous (all but (1,0))
       }
+    }
   } else if (mode == CONV1) {
     g.slot_shift[0][0] = (short)(BW + 1); g.slot_group[0] = 0; g.slot_first[0] = 1;
   } else {
@@ -303,9 +317,11 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
 }
 
 void build_tap_table(const ConvGeom& g, int4* out) {
+  // {A shift in bytes, first accumulator column, columns (0 = all N_tile), 0}
   for (int ph = 0; ph < 4; ++ph)
     for (int s = 0; s < kMaxSlots; ++s)
-      out[ph * kMaxSlots + s] = make_int4(g.slot_shift[ph][s] * 16, g.slot_group[s], g.slot_first[s], 0);
+      out[ph * kMaxSlots + s] = make_int4(g.slot_shift[ph][s] * 16, g.varn ? g.slot_n0[s] * g.cout_tile : 0,
+                                          g.varn ? g.slot_n[s] * g.cout_tile : 0, 0);
 }
 
 void finish_geom_for_batch(ConvGeom& g, int N) {
@@ -325,7 +341,7 @@ void slot_offsets(const ConvLayer& L, int* dy, int* dx) {
   for (int s = 0; s < L.g.n_slots; ++s) {
     if (L.g.s2d) { dy[s] = kT[s / 4]; dx[s] = kT[s % 4]; }
     else if (L.mode == CONV1) { dy[s] = 0; dx[s] = 0; }
-    else { dy[s] = s / 3 - 1; dx[s] = s % 3 - 1; }
+    else { int sy, sx; slot_yx(L.g, s, &sy, &sx); dy[s] = sy - 1; dx[s] = sx - 1; }
   }
 }
 
@@ -378,8 +394,10 @@ void pack_conv_weights(const ConvLayer& L, const float* w, std::vector<act_t>& o
     if (g.phase_grid) { ph = z; a = slot >> 1; b = slot & 1; }
     else {
       // up_cols: slot = input shift (dy,dx) in box coordinates, row block of the weight tile = phase
-      ph = co / g.cout_tile; co = co % g.cout_tile;
-      a = slot / 3 - (ph >> 1); b = slot % 3 - (ph & 1);
+      ph = block_phase(g.varn, co / g.cout_tile); co = co % g.cout_tile;
+      int sy, sx;
+      slot_yx(g, slot, &sy, &sx);
+      a = sy - (ph >> 1); b = sx - (ph & 1);
       if (a < 0 || a > 1 || b < 0 || b > 1) return 0.f;       // this phase does not read that shift
     }
     const int py = ph >> 1, px = ph & 1;
@@ -443,8 +461,10 @@ bool pack_conv_sources(const ConvLayer& L, std::vector<int>& src) {
     int ph, a, b;
     if (g.phase_grid) { ph = z; a = slot >> 1; b = slot & 1; }
     else {
-      ph = co / g.cout_tile; co = co % g.cout_tile;
-      a = slot / 3 - (ph >> 1); b = slot % 3 - (ph & 1);
+      ph = block_phase(g.varn, co / g.cout_tile); co = co % g.cout_tile;
+      int sy, sx;
+      slot_yx(g, slot, &sy, &sx);
+      a = sy - (ph >> 1); b = sx - (ph & 1);
       if (a < 0 || a > 1 || b < 0 || b > 1) return;
     }
     if (co >= cout) return;

@@ -52,6 +52,7 @@ struct __align__(16) SmemHeader {
   uint32_t tmem_base;
   uint32_t stats_cnt[2];      // epilogue warps that have finished the statistics of the tile in slot buffer 0 / 1
   uint2 sched[64 + 16];       // per (phase, slot, k16 step): {A offset, B offset} in 16-byte units (+16: group over-read)
+  uint2 sched2[64 + 16];      //   ... {first accumulator column, instruction descriptor}: variable-N plans issue narrower MMAs
 };
 static_assert(sizeof(SmemHeader) <= kConvHeaderBytes, "header too large");
 
@@ -120,14 +121,15 @@ __device__ __forceinline__ void argmax_phases(const uint32_t (&v)[16], const Con
 }
 
 // CNT MMAs (one schedule group) for every 128-row MMA tile of the work item, as straight-line code.
-template <int CNT>
+template <int CNT, bool VARN>
 __device__ __forceinline__ void issue_group(uint32_t d, int n_mtiles, uint32_t n_tile, uint32_t mt_desc, const uint32_t (&ab)[16],
-                                            const uint32_t (&bk)[16], uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
-                                            uint32_t first_acc) {
+                                            const uint32_t (&bk)[16], const uint32_t (&dc)[16], const uint32_t (&id)[16], uint32_t a_hi,
+                                            uint32_t b_hi, uint32_t idesc, uint32_t first_acc) {
   uint32_t moff = 0;
   for (int mt = 0; mt < n_mtiles; ++mt, moff += mt_desc, d += n_tile) {
 #pragma unroll
-    for (int k = 0; k < CNT; ++k) umma_f16kind_lohi(d, ab[k] + moff, a_hi, bk[k], b_hi, idesc, k == 0 ? first_acc : 1u);
+    for (int k = 0; k < CNT; ++k)
+      umma_f16kind_lohi(VARN ? d + dc[k] : d, ab[k] + moff, a_hi, bk[k], b_hi, VARN ? id[k] : idesc, k == 0 ? first_acc : 1u);
   }
 }
 
@@ -164,7 +166,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int t) {
 // MODE = which epilogue the instantiation contains (one per kernel: the three bodies together cost instruction-cache
 // misses -- 11 % of the warp stalls of the r01 kernel were "no instruction").
 enum { kEpiGeneric = 0, kEpiUpCols = 1, kEpiArgmax = 2 };
-template <int G, bool GEN, int MODE>
+template <int G, bool GEN, int MODE, bool VARN>
 __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid_constant__ ConvParams p) {
   constexpr int kEpiWarps = 4 * G;
   constexpr int kEpiThreads = 128 * G;
@@ -214,14 +216,17 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     // MMA schedule: entry (phase, slot, j) = {tap shift + j k16-steps of A, (slot * k16_per_chunk + j) B tiles}
     const int i = threadIdx.x - 64, k16pc = g.CBK >> 1, len = g.n_slots * k16pc;
     const int nph = g.phase_grid ? 4 : 1;
-    uint2 v = make_uint2(0u, 0u);
+    uint2 v = make_uint2(0u, 0u), v2 = make_uint2(0u, umma_idesc_16bit(128, (uint32_t)g.N_tile, GSX_FP16 ? 0u : 1u));
     if (i < nph * len) {
       const int ph = i / len, idx = i - ph * len, slot = idx / k16pc, j = idx - slot * k16pc;
-      const int4 tp = __ldg(p.taps + ph * kMaxSlots + slot);
+      const int4 tp = __ldg(p.taps + ph * kMaxSlots + slot);       // {A shift bytes, first column, columns (0 = all), -}
       v.x = ((uint32_t)tp.x >> 4) + (uint32_t)j * ((2u * (uint32_t)g.cb_stride_bytes) >> 4);
-      v.y = (uint32_t)idx * (((uint32_t)g.N_tile * 32) >> 4);
+      v.y = (uint32_t)idx * (((uint32_t)g.N_tile * 32) >> 4) + (uint32_t)tp.y;     // B rows are 16 bytes apart: + first column
+      v2.x = (uint32_t)tp.y;
+      if (tp.z > 0) v2.y = umma_idesc_16bit(128, (uint32_t)tp.z, GSX_FP16 ? 0u : 1u);
     }
     hdr->sched[i] = v;
+    hdr->sched2[i] = v2;
   }
   if (warp == 1) {
     tmem_alloc(&hdr->tmem_base, (uint32_t)g.tmem_cols);
@@ -328,9 +333,9 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     uint32_t empty_par = 1;          // parity of the "tmem_empty" wait = (round - 1) & 1, round = tl / nbuf
     const int sp_nt = g.tiles_x * g.tiles_y * g.tiles_n * g.n_ntiles;
     const bool phased = g.phase_grid != 0;
-    uint32_t aa[16], bb[16];
+    uint32_t aa[16], bb[16], dc[16], id[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { aa[i] = 0; bb[i] = 0; }
+    for (int i = 0; i < 16; ++i) { aa[i] = 0; bb[i] = 0; dc[i] = 0; id[i] = idesc; }
     int w_next = t_first;                           // first tile of the next sample (per-sample resident weights)
     const int tiles_per_sample = g.tiles_x * g.tiles_y;
     for (int t = t_first; t < t_last; t += t_step, ++tl) {
@@ -354,8 +359,13 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
           if (key != cur_key) {
             cur_key = key;
             const uint2* sc = hdr->sched + phase * sched_len + g0;      // (reads past the end are never issued)
+            const uint2* sc2 = hdr->sched2 + phase * sched_len + g0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { const uint2 v = sc[i]; aa[i] = v.x; bb[i] = v.y; }
+            for (int i = 0; i < 16; ++i) {
+              const uint2 v = sc[i];
+              aa[i] = v.x; bb[i] = v.y;
+              if (VARN) { const uint2 v2 = sc2[i]; dc[i] = v2.x; id[i] = v2.y; }
+            }
           }
           const int cnt = sched_len - g0;
           // absolute descriptor low words of this chunk's schedule entries (the MMA tile offset is added per MMA)
@@ -366,18 +376,18 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
           if (elect_one()) {
             const uint32_t first_acc = (kc > 0 || g0 > 0) ? 1u : 0u;   // the very first MMA of a tile overwrites
             // straight-line bodies for the schedule lengths the planner produces; predicated fallback otherwise
-            if (cnt >= 16)      issue_group<16>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, a_hi, b_hi, idesc, first_acc);
-            else if (cnt == 9)  issue_group<9>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, a_hi, b_hi, idesc, first_acc);
-            else if (cnt == 4)  issue_group<4>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, a_hi, b_hi, idesc, first_acc);
-            else if (cnt == 8)  issue_group<8>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, a_hi, b_hi, idesc, first_acc);
-            else if (cnt == 2)  issue_group<2>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, a_hi, b_hi, idesc, first_acc);
-            else if (cnt == 1)  issue_group<1>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, a_hi, b_hi, idesc, first_acc);
+            if (cnt >= 16)      issue_group<16, VARN>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, dc, id, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 9)  issue_group<9, VARN>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, dc, id, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 4)  issue_group<4, VARN>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, dc, id, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 8)  issue_group<8, VARN>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, dc, id, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 2)  issue_group<2, VARN>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, dc, id, a_hi, b_hi, idesc, first_acc);
+            else if (cnt == 1)  issue_group<1, VARN>(acc_base, n_mtiles, n_tile, mt_step, ab, bk, dc, id, a_hi, b_hi, idesc, first_acc);
             else {
               uint32_t moff = 0, d = acc_base;
               for (int mt = 0; mt < n_mtiles; ++mt, moff += mt_step, d += n_tile) {
 #pragma unroll
                 for (int k = 0; k < 16; ++k)
-                  if (k < cnt) umma_f16kind_lohi(d, ab[k] + moff, a_hi, bk[k], b_hi, idesc, k == 0 ? first_acc : 1u);
+                  if (k < cnt) umma_f16kind_lohi(VARN ? d + dc[k] : d, ab[k] + moff, a_hi, bk[k], b_hi, VARN ? id[k] : idesc, k == 0 ? first_acc : 1u);
               }
             }
           }
@@ -537,8 +547,9 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
 #pragma unroll
             for (int py = 0; py < 2; ++py) {
               uint32_t va[16], vb[16];
-              tmem_ld16(tbase + (uint32_t)((2 * py) * cpp * 16), va);
-              tmem_ld16(tbase + (uint32_t)((2 * py + 1) * cpp * 16), vb);
+              const int blkA = phase_block(VARN ? 1 : 0, py, 0), blkB = phase_block(VARN ? 1 : 0, py, 1);    // accumulator blocks of the 2 phases
+              tmem_ld16(tbase + (uint32_t)(blkA * cpp * 16), va);
+              tmem_ld16(tbase + (uint32_t)(blkB * cpp * 16), vb);
               const int Y = 2 * lc.y + py;
               const size_t pix = pix0 + (size_t)py * e.Wo;
               f32x2 nz0 = 0ull, nz1 = 0ull;
@@ -552,11 +563,11 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
               if (tile_edge) {
                 const int cls = (lc.y == 0 ? 0 : (lc.y == g.H - 1 ? 2 : 1)) * 3 + (lc.x == 0 ? 0 : (lc.x == g.W - 1 ? 2 : 1));
                 if (lc.valid && cls != 4) {
-                  const float* dp = e.bdelta + ((size_t)lc.n * 9 + cls) * g.bias_cols + ((2 * py) * cpp + c16) * 16;
+                  const float* dp = e.bdelta + ((size_t)lc.n * 9 + cls) * g.bias_cols + c16 * 16;
 #pragma unroll
                   for (int i = 0; i < 16; ++i) {
-                    va[i] = __float_as_uint(__uint_as_float(va[i]) + __ldg(dp + i));
-                    vb[i] = __float_as_uint(__uint_as_float(vb[i]) + __ldg(dp + cpp * 16 + i));
+                    va[i] = __float_as_uint(__uint_as_float(va[i]) + __ldg(dp + blkA * cpp * 16 + i));
+                    vb[i] = __float_as_uint(__uint_as_float(vb[i]) + __ldg(dp + blkB * cpp * 16 + i));
                   }
                 }
               }
@@ -598,8 +609,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
                   }
                   const uint32_t r4[4] = {rv.x, rv.y, rv.z, rv.w};
                   // bias: per channel (shared table), or per column of the two phases (per-sample layers)
-                  const ulonglong2* bpa = reinterpret_cast<const ulonglong2*>(per_sample ? bias_w + ((2 * py) * cpp + c16) * 16 : chan_s + c0) + 2 * h;
-                  const ulonglong2* bpb = reinterpret_cast<const ulonglong2*>(per_sample ? bias_w + ((2 * py + 1) * cpp + c16) * 16 : chan_s + c0) + 2 * h;
+                  const ulonglong2* bpa = reinterpret_cast<const ulonglong2*>(per_sample ? bias_w + (blkA * cpp + c16) * 16 : chan_s + c0) + 2 * h;
+                  const ulonglong2* bpb = reinterpret_cast<const ulonglong2*>(per_sample ? bias_w + (blkB * cpp + c16) * 16 : chan_s + c0) + 2 * h;
                   const ulonglong2 bq0 = bpa[0], bq1 = bpa[1], bq2 = bpb[0], bq3 = bpb[1];
                   const f32x2 bias4[4] = {bq0.x, bq0.y, bq1.x, bq1.y};
                   const f32x2 bias4b[4] = {bq2.x, bq2.y, bq3.x, bq3.y};
@@ -798,15 +809,15 @@ static int current_device() {
   return dev < 0 ? 0 : (dev > 63 ? 63 : dev);
 }
 
-template <int G, bool GEN, int MODE>
+template <int G, bool GEN, int MODE, bool VARN = false>
 static void launch_g(const ConvParams& p, int grid, cudaStream_t st) {
   static bool configured[64] = {false};
   const int dev = current_device();
   if (!configured[dev]) {
-    cudaFuncSetAttribute(shiftconv_kernel<G, GEN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(shiftconv_kernel<G, GEN, MODE, VARN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured[dev] = true;
   }
-  launch_pdl_kind(1, shiftconv_kernel<G, GEN, MODE>, dim3(grid), dim3(64 + 128 * G), (size_t)p.g.smem_bytes, st, p);
+  launch_pdl_kind(1, shiftconv_kernel<G, GEN, MODE, VARN>, dim3(grid), dim3(64 + 128 * G), (size_t)p.g.smem_bytes, st, p);
 }
 
 void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
@@ -827,8 +838,12 @@ void launch_shiftconv(const ConvParams& p, cudaStream_t st) {
   const bool gen = p.e.noise != nullptr || p.e.nscale != nullptr || (p.e.flags & EPI_STATS) != 0 || p.e.e_rows != nullptr;
   const bool g4 = g.epi_groups == 4;
   if (p.e.flags & EPI_ARGMAX) { if (g4) launch_g<4, false, kEpiArgmax>(pp, grid, st); else launch_g<2, false, kEpiArgmax>(pp, grid, st); }
-  else if (gen && g.up_cols) launch_g<2, true, kEpiUpCols>(pp, grid, st);    // generator epilogues: noise + statistics (+ border)
+  else if (gen && g.up_cols) {                                                  // generator epilogues: noise + statistics (+ border)
+    if (g.varn) launch_g<2, true, kEpiUpCols, true>(pp, grid, st); else launch_g<2, true, kEpiUpCols>(pp, grid, st);
+  }
   else if (gen) launch_g<2, true, kEpiGeneric>(pp, grid, st);
+  else if (g.up_cols && g.varn) launch_g<2, false, kEpiUpCols, true>(pp, grid, st);   // variable-N MMAs: its own instantiation, so that
+                                                                                      //   the uniform-N issue loop of every other layer is untouched
   else if (g.up_cols) { if (g4) launch_g<4, false, kEpiUpCols>(pp, grid, st); else launch_g<2, false, kEpiUpCols>(pp, grid, st); }
   else { if (g4) launch_g<4, false, kEpiGeneric>(pp, grid, st); else launch_g<2, false, kEpiGeneric>(pp, grid, st); }
 }

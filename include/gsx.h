@@ -63,7 +63,10 @@ uint64_t gsx_launch_count(void);
  *                 that consume it (per-sample modulated weights) instead of a separate pass over the tensor; 0 keeps the
  *                 reference's operator order (networks_stylegan.py:56-73) everywhere -- for A/B tests.
  *   "fold_deconv_maxc" (default 16): the transposed conv + blur + noise/bias/lrelu/statistics of a block run as ONE kernel
- *                 when the block has at most this many channels (0: never). */
+ *                 when the block has at most this many channels (0: never).
+ *   "varn" (default 1): stacked-phase up-convs issue MMAs only over the phase blocks a shift feeds (1: layers with >= 32
+ *                 output channels, 2: all, 0: off);  "epi_groups" (default 2; 4 = experiment): epilogue warps per TMEM lane quarter
+ *                 of the kernels without the generator epilogue. */
 int gsx_set_option(const char* name, int value);
 
 /* ---- generator: replaces Generator(config) / load_parameters / __call__
