@@ -109,6 +109,62 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int NT, in
   rvar[c] = 0.9f * rvar[c] + 0.1f * (float)var;
 }
 
+// "last block finishes" helper for the two-level per-channel reductions: every block publishes its partial, takes a ticket;
+// the block that draws the last ticket sums all partials in their fixed order (so the result does not depend on which block
+// that is) and resets the counter.  Saves one tiny dependent launch per reduction (~75 per training step).
+__device__ __forceinline__ bool t_last_block(unsigned int* counter) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    s_last = atomicAdd(counter, 1u) == total - 1;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
+
+struct BnStatArgs {
+  const act_t* z; float* partial; unsigned int* counter;
+  int C, N, HW;
+  const float* gamma; const float* beta; float* rmean; float* rvar; float4* bnp;     // gamma == null: channel sums only -> out
+  float* out; int c_real;
+};
+// per-(sample, tile) channel sums / sums of squares of a blocked tensor; the last block turns them into the BatchNorm
+// coefficients bnp[c] = {a = gamma*rstd, b = beta - mean*a, mean, rstd} and updates the moving statistics (0.9 / 0.1, biased
+// variance) -- or, without gamma, writes the channel sums (bias gradients)
+__global__ void __launch_bounds__(256) bn_stats_kernel(const BnStatArgs a) {
+  const int plane = blockIdx.y, cb = plane / a.N, n = plane - cb * a.N;
+  const act_t* src = a.z + (size_t)plane * a.HW * 8;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < a.HW; p += gridDim.x * 256) {
+    float f[8];
+    t_unpack8(__ldg(reinterpret_cast<const uint4*>(src + (size_t)p * 8)), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i] += f[i]; acc[8 + i] = fmaf(f[i], f[i], acc[8 + i]); }
+  }
+  const int T = gridDim.x;
+  t_block_reduce16(acc, a.partial + (((size_t)n * T + blockIdx.x) * a.C + cb * 8) * 2, 256);
+  if (!t_last_block(a.counter)) return;
+  const int NT = a.N * T;
+  const double count = (double)a.N * a.HW;
+  for (int c = threadIdx.x; c < a.C; c += 256) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int t = 0; t < NT; ++t) { s1 += __ldcg(a.partial + ((size_t)t * a.C + c) * 2); s2 += __ldcg(a.partial + ((size_t)t * a.C + c) * 2 + 1); }
+    if (!a.gamma) { if (c < a.c_real) a.out[c] = (float)s1; continue; }
+    const double mean = s1 / count, var = fmax(s2 / count - mean * mean, 0.0);
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    const float ca = a.gamma[c] * rstd;
+    a.bnp[c] = make_float4(ca, a.beta[c] - (float)mean * ca, (float)mean, rstd);
+    a.rmean[c] = 0.9f * a.rmean[c] + 0.1f * (float)mean;
+    a.rvar[c] = 0.9f * a.rvar[c] + 0.1f * (float)var;
+  }
+  if (threadIdx.x == 0) *a.counter = 0;
+}
+
 struct BnFwdArgs {
   const act_t* z; act_t* y; const float4* bnp;
   int C, N, H, W;
@@ -155,6 +211,7 @@ struct BnBwdArgs {
   int drop_site; unsigned long long seed;
   float m;
   const unsigned long long* seed_dev;
+  unsigned int* counter; float* dgamma_out; float* dbeta_out; float2* dparam_w;      // last-block finalize of the reduction
 };
 // g = dy * dropout' * lrelu'(pre);  partial sums of g (-> dbeta) and g * xhat (-> dgamma) per (sample, block)
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
@@ -183,8 +240,18 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
     }
   }
   t_block_reduce16(acc, a.partial + (((size_t)n * a.T + blockIdx.x) * a.C + cb * 8) * 2, 256);
+  if (!t_last_block(a.counter)) return;
+  // dbeta / dgamma = fixed-order sums of the partials -> the gradient bucket and dparam (read by bn_bwd_apply_kernel)
+  const int NT = a.N * a.T;
+  for (int c = threadIdx.x; c < a.C; c += 256) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int t = 0; t < NT; ++t) { s0 += __ldcg(a.partial + ((size_t)t * a.C + c) * 2); s1 += __ldcg(a.partial + ((size_t)t * a.C + c) * 2 + 1); }
+    a.dbeta_out[c] = (float)s0; a.dgamma_out[c] = (float)s1;
+    a.dparam_w[c] = make_float2((float)s0, (float)s1);
+  }
+  if (threadIdx.x == 0) *a.counter = 0;
 }
-// dbeta / dgamma = fixed-order sums of the partials -> the gradient bucket and dparam
+// (stand-alone form of the finalize, kept for reference / tests)
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int NT, int C, float* __restrict__ dgamma_out,
                                        float* __restrict__ dbeta_out, float2* __restrict__ dparam) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -380,6 +447,7 @@ struct gsx_train {
   int4* pack_idx = nullptr;
   size_t pack_count = 0;
   float* bn_mem = nullptr;
+  unsigned int* counter = nullptr;                   // ticket counter of the last-block-finishes reductions (zero between launches)
   const unsigned long long* seed_dev = nullptr;     // gsx_train_set_seed_buffer
   int sms = 148;
 };
@@ -577,6 +645,7 @@ extern "C" int gsx_train_create(const gsx_dec_cfg* cfg, int n, int use_dropout, 
   size_t bn_floats = 0;
   for (auto& l : h->levels) bn_floats += 6 * (size_t)(l.bn_cvt.C + l.bn_a.C + l.bn_b.C);
   ok = ok && cuda_ok(cudaMalloc(&h->bn_mem, std::max<size_t>(bn_floats, 1) * sizeof(float)), "cudaMalloc");
+  ok = ok && cuda_ok(cudaMalloc(&h->counter, sizeof(unsigned int)), "cudaMalloc") && cuda_ok(cudaMemset(h->counter, 0, sizeof(unsigned int)), "memset");
   if (!ok) { delete h; return -2; }
   float* bm = h->bn_mem;
   auto bn_take = [&](TBn& b) { if (!b.C) return; b.bnp = reinterpret_cast<float4*>(bm); bm += 4 * b.C; b.dparam = reinterpret_cast<float2*>(bm); bm += 2 * b.C; };
@@ -608,7 +677,7 @@ extern "C" void gsx_train_destroy(gsx_train* h) {
   if (!h) return;
   for (auto& l : h->levels)
     for (TConv* c : {&l.cvt, &l.conv_a, &l.conv_b, &l.sc, &l.fin}) { cudaFree(c->fwd.taps_dev); cudaFree(c->dgrad.taps_dev); }
-  cudaFree(h->wpack_all); cudaFree(h->pack_idx); cudaFree(h->bn_mem);
+  cudaFree(h->wpack_all); cudaFree(h->pack_idx); cudaFree(h->bn_mem); cudaFree(h->counter);
   delete h;
 }
 
@@ -656,12 +725,11 @@ bool t_conv_dgrad(const TConv& c, int N, const act_t* dy, act_t* dx, cudaStream_
   return run_conv_layer(c.dgrad, N, dy, nullptr, e, st, label);
 }
 void t_bn_stats(const gsx_train* h, const TBn& b, const act_t* z, int HW, const float* p, float* r, float* stats, cudaStream_t st) {
-  // enough blocks to fill the GPU at batch 1: (C/8)*N planes x T tiles
+  // enough blocks to fill the GPU at batch 1: (C/8)*N planes x T tiles; the last block finalizes
   const int T = t_tiles(HW, (b.C / 8) * h->n);
-  launch_stats(z, stats, b.C, h->n, HW, st, T);
-  bn_finalize_kernel<<<(b.C + 63) / 64, 64, 0, st>>>(stats, h->n * T, b.C, (double)h->n * HW, p + b.gamma_off, p + b.beta_off,
-                                                     r + b.rmean_off, r + b.rvar_off, b.bnp);
-  g_launches += 2;
+  BnStatArgs a{z, stats, h->counter, b.C, h->n, HW, p + b.gamma_off, p + b.beta_off, r + b.rmean_off, r + b.rvar_off, b.bnp, nullptr, 0};
+  bn_stats_kernel<<<dim3(T, (b.C / 8) * h->n), 256, 0, st>>>(a);
+  g_launches++;
 }
 void t_bn_fwd(const gsx_train* h, const TBn& b, const act_t* z, act_t* y, int H, int W, int site, uint64_t seed, const act_t* addsrc, cudaStream_t st) {
   BnFwdArgs a{z, y, b.bnp, b.C, h->n, H, W, site, seed, h->seed_dev, addsrc};
@@ -672,11 +740,11 @@ void t_bn_fwd(const gsx_train* h, const TBn& b, const act_t* z, act_t* y, int H,
 void t_bn_bwd(const gsx_train* h, const TBn& b, const act_t* z, const act_t* dy, act_t* dz, int HW, int site, uint64_t seed, float* g,
               float* stats, cudaStream_t st) {
   const int T = t_tiles(HW, (b.C / 8) * h->n);
-  BnBwdArgs a{z, dy, dz, b.bnp, b.dparam, stats, b.C, h->n, HW, T, site, seed, (float)h->n * (float)HW, h->seed_dev};
+  BnBwdArgs a{z, dy, dz, b.bnp, b.dparam, stats, b.C, h->n, HW, T, site, seed, (float)h->n * (float)HW, h->seed_dev,
+              h->counter, g + b.gamma_off, g + b.beta_off, b.dparam};
   bn_bwd_reduce_kernel<<<dim3(T, (b.C / 8) * h->n), 256, 0, st>>>(a);
-  bn_bwd_finalize_kernel<<<(b.C + 63) / 64, 64, 0, st>>>(stats, h->n * T, b.C, g + b.gamma_off, g + b.beta_off, b.dparam);
   bn_bwd_apply_kernel<<<dim3(ew_grid(HW), (b.C / 8) * h->n), 256, 0, st>>>(a);
-  g_launches += 3;
+  g_launches += 2;
 }
 bool t_wgrad(const gsx_train* h, const TConv& c, const act_t* x0, const act_t* x1, const act_t* dy, float* g, float* scratch, cudaStream_t st,
              int Hx, int Wx) {
@@ -687,9 +755,9 @@ bool t_wgrad(const gsx_train* h, const TConv& c, const act_t* x0, const act_t* x
 }
 void t_bias_grad(const gsx_train* h, const act_t* dy, int Cpad, int Creal, int HW, float* out, float* stats, cudaStream_t st) {
   const int T = t_tiles(HW, (Cpad / 8) * h->n);
-  launch_stats(dy, stats, Cpad, h->n, HW, st, T);
-  chan_sum_finalize_kernel<<<1, 64, 0, st>>>(stats, h->n * T, Cpad, Creal, out);
-  g_launches += 2;
+  BnStatArgs a{dy, stats, h->counter, Cpad, h->n, HW, nullptr, nullptr, nullptr, nullptr, nullptr, out, Creal};
+  bn_stats_kernel<<<dim3(T, (Cpad / 8) * h->n), 256, 0, st>>>(a);
+  g_launches++;
 }
 
 }  // namespace
