@@ -404,7 +404,7 @@ __global__ void dropout_mask_kernel(float* out, int N, int C, int HW, int site, 
 
 static int ew_grid(int HW) { return std::max(1, std::min((HW + 255) / 256, 2048)); }
 // tiles of a two-level per-channel reduction: ~4 blocks per SM over all planes, at least 1024 pixels per block
-static int t_tiles(int HW, int planes) { return std::max(1, std::min(std::min((HW + 1023) / 1024, 64), (592 + planes - 1) / planes)); }
+static int t_tiles(int HW, int planes) { return std::max(1, std::min(std::min((HW + 1023) / 1024, 512), (1184 + planes - 1) / planes)); }
 
 }  // namespace gsx
 

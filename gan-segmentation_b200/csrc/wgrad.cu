@@ -7,7 +7,9 @@
 // vector of 8 channels, consecutive pixels are 16 bytes apart: read with pixels as K that is exactly the canonical
 // MN-major, no-swizzle UMMA operand layout (core matrix = 8 pixels x 8 channels = 128 contiguous bytes; K groups 128 B
 // apart, channel blocks one plane apart).  So the same TMA boxes as the forward pass feed the MMAs without a transpose:
-//   A = X   (M = input channels, up to 128 per CTA), read through a descriptor whose start address is shifted by the
+//   A = X   (M = input channels, up to 128 per CTA; M = 64 MMAs when the layer has <= 64 of them: half the operand bytes --
+//            their accumulator row i sits in TMEM lane 32*(i/16) + i%16, probed by tools/wgrad_m64_probe.py), read through a
+//            descriptor whose start address is shifted by the
 //            tap offset ((ky-1)*BW + (kx-1)) * 16 B -- the forward kernel's trick, now along K;
 //   B = dY  (N = output channels, 16..64), rows of the same pixel tile;
 //   D[tap]  = [ci][co] fp32 in TMEM, one 128 x Cout block per tap (9 * Cout <= 512 columns), accumulated over ALL pixel
@@ -35,6 +37,8 @@ struct WgradGeom {
   int x_cb_stride, y_cb_stride;       // bytes between channel blocks in smem
   int q_steps;                        // K steps of 16 pixels per tile = TH * BW / 16
   int rows;                           // valid accumulator rows per CTA = min(Cin, 128): only these reach the partials
+  int m64;                            // 0: M = 128 MMAs; 1 / 2: M = 64 (Cin <= 64: half the A operand bytes per MMA), accumulator row i in
+                                      //   TMEM lane i (1) or lane 32*(i/16) + i%16 (2)
 };
 
 struct WgradParams {
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     }
   } else if (warp == 1) {
     // ---- MMA issuer
-    uint32_t idesc = umma_idesc_16bit(128, (uint32_t)g.Cout, GSX_FP16 ? 0u : 1u) | (1u << 15) | (1u << 16);   // A, B MN-major
+    uint32_t idesc = umma_idesc_16bit(g.m64 ? 64 : 128, (uint32_t)g.Cout, GSX_FP16 ? 0u : 1u) | (1u << 15) | (1u << 16);   // A, B MN-major
     int it = 0;
     bool first = true;
     const int P = g.K / 2;
@@ -181,9 +185,12 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       tc_fence_after();
     }
     float* out = p.partial + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * taps) * g.rows * g.Cout;
-    const int row = quarter * 32 + lane;
-    const bool live = row < g.rows && quarter * 32 < g.rows;
-    for (int tp = 0; tp < taps && quarter * 32 < g.rows; ++tp)
+    // accumulator row held by this thread's TMEM lane
+    int row = quarter * 32 + lane;
+    if (g.m64 == 2) row = lane < 16 ? quarter * 16 + lane : 128;
+    const bool quarter_live = g.m64 == 2 ? quarter * 16 < g.rows : quarter * 32 < g.rows;
+    const bool live = row < g.rows && quarter_live;
+    for (int tp = 0; tp < taps && quarter_live; ++tp)
       for (int c = 0; c < g.Cout; c += 16) {
         uint32_t v[16];
         if (t1 > t0) {
@@ -218,11 +225,14 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 }
 
 static int g_wg_sms = 0;
+int g_wgrad_m64 = 2;        // gsx_set_option("wgrad_m64", 0 / 2): M = 64 MMAs for layers with <= 64 input channels (default on)
 
 bool plan_wgrad(WgradGeom& g, int K, int N, int H, int W, int Cin, int Cout) {
   g = WgradGeom{};
   g.K = K; g.N = N; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
   if ((K != 1 && K != 3) || Cin % 8 || Cout % 16 || Cout > 56 || Cout * K * K > 512) return false;
+  g.m64 = (Cin <= 64) ? g_wgrad_m64 : 0;
+  const int m_blocks = g.m64 ? 8 : 16;       // channel blocks of A one MMA reads, whatever Cin is
   int BW = 16;
   while (BW < W + 2 && BW < 128) BW <<= 1;
   g.BW = BW;
@@ -235,9 +245,9 @@ bool plan_wgrad(WgradGeom& g, int K, int N, int H, int W, int Cin, int Cout) {
   int TH = std::min(H, 32);
   for (;; --TH) {
     const long xb = (long)g.cbx * (TH + halo) * BW * 16, yb = (long)g.cbo * TH * BW * 16;
-    // the MMA reads 16 channel blocks of A whatever Cin is: the over-read must stay inside the stage
+    // the MMA reads 16 (M = 128) or 8 (M = 64) channel blocks of A whatever Cin is: the over-read must stay inside the stage
     const long xs_stride = (long)(TH + halo) * BW * 16;
-    const long stage = kWgPad + std::max(xb, 16 * xs_stride) + kWgPad + yb + 512;
+    const long stage = kWgPad + std::max(xb, m_blocks * xs_stride) + kWgPad + yb + 512;
     if (kWgStages * stage + 1024 <= 200 * 1024 || TH == 1) {
       g.TH = TH;
       g.x_cb_stride = (int)xs_stride; g.y_cb_stride = TH * BW * 16;
