@@ -125,6 +125,11 @@ def lib(dtype=None):
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
+        # A/B switches for whole test / bench runs: GSX_OPTIONS="pdl=1,varn=0" -> gsx_set_option at load time
+        for kv in filter(None, os.environ.get('GSX_OPTIONS', '').split(',')):
+            k, v = kv.split('=')
+            if l.gsx_set_option(k.strip().encode(), int(v)) < 0:
+                raise GsxError(f'GSX_OPTIONS: {l.gsx_last_error().decode()}')
         _libs[dtype] = l
     return _libs[dtype]
 

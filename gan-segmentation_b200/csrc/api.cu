@@ -303,6 +303,11 @@ extern "C" int gsx_set_option(const char* name, int value) {
   if (name && std::strcmp(name, "fold_apply") == 0) { g_opt_fold_apply = value != 0; return 0; }
   if (name && std::strcmp(name, "fold_deconv_maxc") == 0) { g_opt_fold_deconv_maxc = value; return 0; }
   if (name && std::strcmp(name, "wgrad_m64") == 0 && value >= 0 && value <= 2) { g_wgrad_m64 = value; return 0; }
+  if (name && std::strcmp(name, "pdl") == 0 && value >= 0 && value <= 4) {
+    g_pdl_mode = value;
+    set_pdl_late_conv(value >= 3); set_pdl_late_ew(value >= 3);
+    return 0;
+  }
   if (name && std::strcmp(name, "varn") == 0 && value >= 0 && value <= 2) { g_plan_varn = value; return 0; }
   if (name && std::strcmp(name, "epi_groups") == 0 && (value == 2 || value == 4)) { g_plan_epi_groups = value; return 0; }
   set_error(std::string("unknown option: ") + (name ? name : "(null)"));

@@ -10,6 +10,9 @@
 
 namespace gsx {
 
+__device__ int d_pdl_late_ew = 1;          // see shiftconv.cu: d_pdl_late_conv
+void set_pdl_late_ew(int v) { cudaMemcpyToSymbol(d_pdl_late_ew, &v, sizeof(int)); }
+
 __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -85,7 +88,8 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(kP1Warps * 32) pass1_kernel(const Pass1Args a, int strips, int rowblocks) {
-  pdl_launch_dependents();
+  const int pdl_late = d_pdl_late_ew;
+  if (!pdl_late) pdl_launch_dependents();
   pdl_wait();
   const int plane = blockIdx.y;                 // cb * N + n
   const int cb = plane / a.N, n = plane - cb * a.N;
@@ -172,6 +176,7 @@ __global__ void __launch_bounds__(kP1Warps * 32) pass1_kernel(const Pass1Args a,
     cp_async_wait<0>();
     (void)n_rows;
   }
+  if (pdl_late) pdl_launch_dependents();
   if (a.stats) {
     float* st = a.stats + (((size_t)n * gridDim.x + blockIdx.x) * a.C + cb * 8) * 2;
     block_reduce_store<16>(acc, st, st + 1, kP1Warps * 32);
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(256) stats_kernel(const act_t* in, float* stat
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   for (int pix = blockIdx.x * 256 + threadIdx.x; pix < HW; pix += gridDim.x * 256) {
     float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(src + (size_t)pix * 8)), f);
+    unpack8(ld_dep_u4(src + (size_t)pix * 8), f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { acc[i] += f[i]; acc[8 + i] += f[i] * f[i]; }
   }
@@ -227,9 +232,9 @@ void launch_stats(const act_t* in, float* stats_partial, int C, int N, int HW, c
 // ------------------------------------------------------------------------------------------ finalize
 // One warp per (n, c): lane l sums tiles l, l+32, ... (fixed order), then a fixed butterfly adds the 32 partials,
 // so the result is bit-reproducible and the tile loop is 32-way parallel (544 tiles at 1024^2).
-__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ partial, int T, int N, int C, float inv_hw,
-                                                       const float* __restrict__ styles, int style_stride, int style_off,
-                                                       float* __restrict__ coef) {
+__global__ void __launch_bounds__(256) finalize_kernel(const float* partial, int T, int N, int C, float inv_hw,
+                                                       const float* styles, int style_stride, int style_off,
+                                                       float* coef) {
   pdl_launch_dependents();
   pdl_wait();
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // (n, c)
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
   float s1 = 0.f, s2 = 0.f;
   const float2* p = reinterpret_cast<const float2*>(partial) + ((size_t)n * T * C + c);
   for (int t = lane; t < T; t += 32) {
-    const float2 v = __ldg(p + (size_t)t * C);
+    const float2 v = ld_dep_f2(p + (size_t)t * C);
     s1 += v.x;
     s2 += v.y;
   }
@@ -254,9 +259,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
   const float var = fmaxf(s2 * inv_hw - mean * mean, 0.f);  // biased variance (InstanceNorm)
   const float rstd = rsqrtf(var + 1e-5f);                   // gluon InstanceNorm eps
   const float* sty = styles + (size_t)n * style_stride + style_off;
-  const float a = rstd * (sty[c] + 1.f);                    // ys + 1   (networks_stylegan.py:262)
+  const float a = rstd * (ld_dep_f32(sty + c) + 1.f);                    // ys + 1   (networks_stylegan.py:262)
   coef[(size_t)i * 2] = a;
-  coef[(size_t)i * 2 + 1] = sty[C + c] - mean * a;          // yb
+  coef[(size_t)i * 2 + 1] = ld_dep_f32(sty + C + c) - mean * a;          // yb
 }
 
 void launch_finalize(const float* partial, int T, int N, int C, int HW, const float* styles, int style_stride,
@@ -277,7 +282,8 @@ static constexpr int kApThreads = 256;
 static constexpr int kApPixPerThread = 8;
 
 __global__ void __launch_bounds__(kApThreads) apply_kernel(const ApplyArgs a) {
-  pdl_launch_dependents();
+  const int pdl_late = d_pdl_late_ew;
+  if (!pdl_late) pdl_launch_dependents();
   pdl_wait();
   const int plane = blockIdx.y;
   const int cb = plane / a.N, n = plane - cb * a.N;
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(kApThreads) apply_kernel(const ApplyArgs a) {
 #pragma unroll
   for (int it = 0; it < kApPixPerThread; ++it) {
     const int pix = base + it * kApThreads + threadIdx.x;
-    if (pix < HW) r[it] = ldg_nc_u4(in + (size_t)pix * 8);
+    if (pix < HW) r[it] = ld_dep_u4(in + (size_t)pix * 8);
   }
 #pragma unroll
   for (int it = 0; it < kApPixPerThread; ++it) {
@@ -310,6 +316,7 @@ __global__ void __launch_bounds__(kApThreads) apply_kernel(const ApplyArgs a) {
       }
     }
   }
+  if (pdl_late) pdl_launch_dependents();
 }
 
 // Last layer: all channels of a pixel are needed for ToRGB, so one thread owns a pixel and walks the channel blocks.
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(256) apply_rgb_kernel(const ApplyArgs a) {
     for (int cb = 0; cb < CB; ++cb) {
       const size_t off = (((size_t)cb * a.N + n) * HW + pix) * 8;
       float f[8];
-      unpack8(ldg_nc_u4(a.in + off), f);
+      unpack8(ld_dep_u4(a.in + off), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         f[i] = fmaf(f[i], s_ca[cb * 8 + i], s_cc[cb * 8 + i]);
@@ -367,7 +374,8 @@ __global__ void __launch_bounds__(256) apply_rgb_kernel(const ApplyArgs a) {
 // One thread = PIX pixels, all CB x PIX 16-byte loads issued before the first use; 3 bytes out per pixel.
 template <int CB, int PIX>
 __global__ void __launch_bounds__(256) rgb_kernel(const ApplyArgs a) {
-  pdl_launch_dependents();
+  const int pdl_late = d_pdl_late_ew;
+  if (!pdl_late) pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_w[4][CB * 8];
   __shared__ float s_b[4];
@@ -391,7 +399,7 @@ __global__ void __launch_bounds__(256) rgb_kernel(const ApplyArgs a) {
     const int pix = base + i * 256;
 #pragma unroll
     for (int cb = 0; cb < CB; ++cb)
-      if (pix < HW) r[i][cb] = ldg_nc_u4(a.in + (((size_t)cb * a.N + n) * HW + pix) * 8);
+      if (pix < HW) r[i][cb] = ld_dep_u4(a.in + (((size_t)cb * a.N + n) * HW + pix) * 8);
   }
 #pragma unroll
   for (int i = 0; i < PIX; ++i) {
@@ -451,7 +459,7 @@ __global__ void blocked_to_nchw_kernel(const act_t* in, float* out, int C, int N
   const int cb = plane / N, n = plane - cb * N;
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
     float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(in + ((size_t)plane * HW + pix) * 8)), f);
+    unpack8(ld_dep_u4(in + ((size_t)plane * HW + pix) * 8), f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) out[((size_t)n * C + cb * 8 + i) * HW + pix] = f[i];
   }
@@ -464,7 +472,7 @@ __global__ void nchw_to_blocked_kernel(const float* in, act_t* out, int C, int N
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
     float f[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = __ldg(in + ((size_t)n * C + cb * 8 + i) * HW + pix);
+    for (int i = 0; i < 8; ++i) f[i] = ld_dep_f32(in + ((size_t)n * C + cb * 8 + i) * HW + pix);
     *reinterpret_cast<uint4*>(out + ((size_t)plane * HW + pix) * 8) = pack8(f);
   }
 }
@@ -595,10 +603,10 @@ void launch_advance_counter(unsigned long long* counter, unsigned long long by, 
 static constexpr int kBorderSeg = 30;                 // border pixels per block (ring positions: +2)
 static constexpr int kBorderThreads = 128;
 
-__global__ void __launch_bounds__(kBorderThreads) deconv_border_kernel(const act_t* __restrict__ x, const float* __restrict__ wt,
+__global__ void __launch_bounds__(kBorderThreads) deconv_border_kernel(const act_t* x, const float* __restrict__ wt,
                                                                        float* __restrict__ e_rows, float* __restrict__ e_cols,
                                                                        int N, int Cin, int Cout, int H, int W,
-                                                                       const float* __restrict__ coef) {
+                                                                       const float* coef) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float ring[];                      // [kBorderSeg + 2][Cout]
@@ -630,7 +638,7 @@ __global__ void __launch_bounds__(kBorderThreads) deconv_border_kernel(const act
           const int kx = ax == 0 ? 3 - qp : 1 - qp;
           const float* wk = wt + ((size_t)(ky * 4 + kx) * Cin) * Cout + co;
           for (int cb = 0; cb < Cin / 8; ++cb) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)cb * N + n) * plane + (size_t)iy * W + ix) * 8));
+            const uint4 v = ld_dep_u4(x + (((size_t)cb * N + n) * plane + (size_t)iy * W + ix) * 8);
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -641,7 +649,7 @@ __global__ void __launch_bounds__(kBorderThreads) deconv_border_kernel(const act
 #endif
               float x0 = f.x, x1 = f.y;
               if (coef) {          // the stored tensor is the un-normalised t: x = a*t + b (AdaIN folded into the consumers)
-                const float4 ab = __ldg(reinterpret_cast<const float4*>(coef + ((size_t)n * Cin + cb * 8 + 2 * k) * 2));
+                const float4 ab = ld_dep_f4(coef + ((size_t)n * Cin + cb * 8 + 2 * k) * 2);
                 x0 = fmaf(x0, ab.x, ab.y); x1 = fmaf(x1, ab.z, ab.w);
               }
               acc = fmaf(x0, __ldg(wk + (size_t)(cb * 8 + 2 * k) * Cout), acc);

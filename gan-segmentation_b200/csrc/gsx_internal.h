@@ -308,6 +308,9 @@ bool launch_mapping(const MapArgs& a, cudaStream_t st);
 // Launch with programmatic stream serialization (see ptx.cuh) when the current forward pass is small enough for it to
 // pay (plan.cpp); GSX_NO_PDL=1: never, GSX_PDL=1: always.
 // kind: 1 = shiftconv (one persistent CTA per SM holding most of the shared memory), 0 = everything else.
+extern int g_pdl_mode;
+void set_pdl_late_conv(int v);
+void set_pdl_late_ew(int v);
 bool pdl_enabled(int kind);
 void pdl_set_for_work(double top_level_pixels);   // called at the top of the forward passes
 template <class... KArgs, class... Args>

@@ -33,7 +33,7 @@ __device__ __forceinline__ int mod_channel(const ModGeom& g, int i) {
 // the slots that class keeps (bias_n, class 4) or loses (bdelta), of  sum_ci Wf[slot][ci][col] * b[n][ci]  -- every block
 // redoes the slot sums it needs (a few 10^4 MACs) instead of sharing them through a second pass; block 9 (and up) = the
 // modulated weight stream  wout[n][i] = 16-bit( Wf[i] * a[n][channel(i)] ).
-__global__ void __launch_bounds__(256) modulate_kernel(const float* __restrict__ wf, const float* __restrict__ coef,
+__global__ void __launch_bounds__(256) modulate_kernel(const float* __restrict__ wf, const float* coef,
                                                        const float* __restrict__ bias, act_t* __restrict__ wout,
                                                        float* __restrict__ bias_n, float* __restrict__ bdelta, const ModGeom g) {
   pdl_launch_dependents();
@@ -49,14 +49,14 @@ __global__ void __launch_bounds__(256) modulate_kernel(const float* __restrict__
       const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
       __align__(16) act_t o[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = to_act(wv[k] * __ldg(cf + (size_t)(c0 + k) * 2));
+      for (int k = 0; k < 8; ++k) o[k] = to_act(wv[k] * ld_dep_f32(cf + (size_t)(c0 + k) * 2));       // coef: written by the finalize kernel before this one
       *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<const uint4*>(o);
     }
     return;
   }
   extern __shared__ float bsh[];               // b[Cin], then partial sums [parts][2][bias_cols]
   float* part_s = bsh + g.Cin;
-  for (int c = threadIdx.x; c < g.Cin; c += 256) bsh[c] = cf[(size_t)c * 2 + 1];
+  for (int c = threadIdx.x; c < g.Cin; c += 256) bsh[c] = ld_dep_f32(cf + (size_t)c * 2 + 1);
   __syncthreads();
   const int cls = blockIdx.x, ry = cls / 3, rx = cls - 3 * ry;       // 0 first row / column, 1 interior, 2 last
   const int tile = g.N_tile * 16;

@@ -20,17 +20,20 @@ bool cuda_ok(cudaError_t e, const char* what) {
   return false;
 }
 
-// Programmatic dependent launch pays when the kernels are short (batch 1 at 256^2: 1.19 -> 1.07 ms per step).  At the
-// large-batch operating point it costs ~2 % when applied everywhere: a conv CTA that becomes resident early pins the
-// shared-memory carve-out at its maximum while the HBM-bound pass before it drains.  So: small forward passes use it
-// for every kernel; large ones only for a shift-GEMM conv that directly follows another one (the decoder is a chain
-// of them) -- those cannot co-reside anyway, the successor's CTA takes over an SM when the predecessor's CTA exits
-// and does its prologue (barriers, TMEM, resident weights) under the predecessor's tail.
+// Programmatic dependent launch.  Round 1: every kernel released its dependents at its START; that pays when the kernels
+// are short (batch 1 at 256^2: 1.19 -> 1.07 ms per step) but costs ~2 % at the large-batch operating point (a conv CTA that
+// becomes resident early pins the shared-memory carve-out while the HBM-bound pass before it drains), so large passes used
+// it only for conv -> conv chains (mode 1).  Round 2 (mode 3, the default): the big kernels (convs, pass1, apply, ToRGB)
+// release their dependents when a CTA has FINISHED its work, so a successor only overlaps its launch latency and prologue
+// with the predecessor's tail -- and every launch carries the attribute.  Measured (device / end-to-end samples/s):
+// FFHQ 3129 / 3033 -> 3115 / 3074, cars 6980 / 6802 -> 7047 / 6962, bedrooms batch 1 901 / 893 -> 923 / 915.
 static thread_local bool g_pdl_small = false, g_pdl_chain = false, g_prev_conv = false;
+int g_pdl_mode = 3;     // gsx_set_option("pdl", v): 0 off / 1 by size (+ conv chains) / 2 always / 3 always, big kernels trigger late /
+                        //   4 = policy of 1 with the late trigger
 void pdl_set_for_work(double top_level_pixels) {
-  static const int mode = tune_env("GSX_NO_PDL") ? 0 : (tune_env("GSX_PDL") ? 2 : 1);     // off / by size / always
-  g_pdl_small = mode == 2 || (mode == 1 && top_level_pixels <= 2.0 * 1024 * 1024);
-  g_pdl_chain = mode != 0 && !tune_env("GSX_NO_PDL_CHAIN");
+  const int mode = g_pdl_mode;
+  g_pdl_small = mode == 2 || mode == 3 || ((mode == 1 || mode == 4) && top_level_pixels <= 2.0 * 1024 * 1024);
+  g_pdl_chain = mode != 0;
 }
 bool pdl_enabled(int kind) {
   const bool on = g_pdl_small || (g_pdl_chain && kind == 1 && g_prev_conv);

@@ -291,13 +291,20 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void keep_in_reg(uint32_t& v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ void keep_in_reg(int& v) { asm volatile("" : "+r"(v)); }
 
-__device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
-}
+// Loads of data that an EARLIER KERNEL OF THE STREAM produced (activations, statistics, AdaIN coefficients, per-sample
+// weights and biases, noise).  Under programmatic dependent launch a kernel's lifetime overlaps its producer's -- and a
+// chain of such launches has no ordinary kernel boundary in it -- so the non-coherent path (__ldg / ld.global.nc, also
+// what the compiler picks for const __restrict__ pointers) must not be used for this data: it is outside the memory
+// model, griddepcontrol.wait does not order it, and it returned lines the SM had cached before the producer's write
+// (seen as the previous layer's statistics -> NaN features; tests/test_dropin_gpu.py::test_forward_is_independent_...
+// and ::test_dependent_launch_does_not_change_results pin this).  These are ordinary weak loads (ld.global.ca), which
+// pdl_wait() orders; as compiler intrinsics they are scheduled freely but never across pdl_wait()'s memory clobber.
+// Measured at FFHQ batch 32: 10.21 ms (nc, wrong) -> 10.29 ms (weak); ld.global.cg (LDG.STRONG.GPU) instead: 10.50 ms.
+// __ldg stays for what no kernel writes (weights, biases, tap tables).
+__device__ __forceinline__ uint4 ld_dep_u4(const void* p) { return __ldca(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ float4 ld_dep_f4(const void* p) { return __ldca(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float2 ld_dep_f2(const void* p) { return __ldca(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float ld_dep_f32(const void* p) { return __ldca(reinterpret_cast<const float*>(p)); }
 // 256-bit global store (sm_100: STG.E.ENL2.256); address 32-byte aligned
 __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),

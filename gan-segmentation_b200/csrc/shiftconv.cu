@@ -39,6 +39,12 @@
 
 namespace gsx {
 
+// 1: the big kernels release their programmatic dependents when a CTA has finished its work instead of at its start
+// (gsx_set_option("pdl", 3)): the successor's launch latency still overlaps this kernel's tail, but its CTAs do not sit on
+// shared memory while this kernel runs
+__device__ int d_pdl_late_conv = 1;
+void set_pdl_late_conv(int v) { cudaMemcpyToSymbol(d_pdl_late_conv, &v, sizeof(int)); }
+
 static constexpr int kMaxStages = 8;
 
 struct __align__(16) SmemHeader {
@@ -177,7 +183,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
   uint8_t* a_base = smem + g.a_off;
   uint8_t* b_base = a_base + (size_t)g.stages * g.a_stage_stride;
 
-  pdl_launch_dependents();
+  const int pdl_late = d_pdl_late_conv;
+  if (!pdl_late) pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = g.tiles_x * g.tiles_y * g.tiles_n * g.n_ntiles * (g.phase_grid ? 4 : 1);
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
       if (per_sample && tc.n0 != bias_sample) {
         bias_sample = tc.n0;
         __syncwarp();
-        for (int i = lane; i < g.bias_cols; i += 32) bias_w[i] = __ldg(e.bias_n + (size_t)tc.n0 * g.bias_cols + i);
+        for (int i = lane; i < g.bias_cols; i += 32) bias_w[i] = ld_dep_f32(e.bias_n + (size_t)tc.n0 * g.bias_cols + i);
         __syncwarp();
       }
       // image-border class of this tile's rows (per-sample layers: the folded AdaIN shift must not flow in through taps
@@ -556,7 +563,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
               if (GEN && lc.valid) {
                 float2 t2 = make_float2(0.f, 0.f);
                 if (g.aux_kind == 1) t2 = *reinterpret_cast<const float2*>(nzp + (size_t)py * (2 * g.TW));
-                else if (e.noise) t2 = __ldg(reinterpret_cast<const float2*>(e.noise + (size_t)lc.n * plane_out + pix));
+                else if (e.noise) t2 = ld_dep_f2(e.noise + (size_t)lc.n * plane_out + pix);
                 nz0 = pk2(t2.x, t2.x); nz1 = pk2(t2.y, t2.y);
               }
               tmem_ld_wait();
@@ -566,8 +573,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
                   const float* dp = e.bdelta + ((size_t)lc.n * 9 + cls) * g.bias_cols + c16 * 16;
 #pragma unroll
                   for (int i = 0; i < 16; ++i) {
-                    va[i] = __float_as_uint(__uint_as_float(va[i]) + __ldg(dp + blkA * cpp * 16 + i));
-                    vb[i] = __float_as_uint(__uint_as_float(vb[i]) + __ldg(dp + blkB * cpp * 16 + i));
+                    va[i] = __float_as_uint(__uint_as_float(va[i]) + ld_dep_f32(dp + blkA * cpp * 16 + i));
+                    vb[i] = __float_as_uint(__uint_as_float(vb[i]) + ld_dep_f32(dp + blkB * cpp * 16 + i));
                   }
                 }
               }
@@ -580,19 +587,19 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
                   const float* er = e.e_rows + (((size_t)lc.n * 2 + (Y ? 1 : 0)) * e.Wo + 2 * lc.x) * e.Cout + c0;
 #pragma unroll
                   for (int i = 0; i < 16; ++i) {
-                    va[i] = __float_as_uint(__uint_as_float(va[i]) - __ldg(er + i));
-                    vb[i] = __float_as_uint(__uint_as_float(vb[i]) - __ldg(er + e.Cout + i));
+                    va[i] = __float_as_uint(__uint_as_float(va[i]) - ld_dep_f32(er + i));
+                    vb[i] = __float_as_uint(__uint_as_float(vb[i]) - ld_dep_f32(er + e.Cout + i));
                   }
                 }
                 if (bl) {
                   const float* ec = e.e_cols + (((size_t)lc.n * 2) * e.Ho + Y) * e.Cout + c0;
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) - __ldg(ec + i));
+                  for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) - ld_dep_f32(ec + i));
                 }
                 if (br) {
                   const float* ec = e.e_cols + (((size_t)lc.n * 2 + 1) * e.Ho + Y) * e.Cout + c0;
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) vb[i] = __float_as_uint(__uint_as_float(vb[i]) - __ldg(ec + i));
+                  for (int i = 0; i < 16; ++i) vb[i] = __float_as_uint(__uint_as_float(vb[i]) - ld_dep_f32(ec + i));
                 }
               }
               if (lc.valid) {
@@ -604,8 +611,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
                     if (g.aux_kind == 2)
                       rv = reinterpret_cast<const uint4*>(aux)[((size_t)((c16 * 2 + h) * g.NB + lc.nb) * g.aux_bh + lc.yl) * g.aux_bw + lc.xl];
                     else
-                      rv = __ldg(reinterpret_cast<const uint4*>(
-                          e.addsrc + ((((size_t)(c0 >> 3) + h) * g.N + lc.n) * (plane_out >> 2) + (size_t)lc.y * (e.Wo >> 1) + lc.x) * 8));
+                      rv = ld_dep_u4(
+                          e.addsrc + ((((size_t)(c0 >> 3) + h) * g.N + lc.n) * (plane_out >> 2) + (size_t)lc.y * (e.Wo >> 1) + lc.x) * 8);
                   }
                   const uint32_t r4[4] = {rv.x, rv.y, rv.z, rv.w};
                   // bias: per channel (shared table), or per column of the two phases (per-sample layers)
@@ -690,7 +697,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
               if (GEN) {
                 float t1 = 0.f;
                 if (g.aux_kind == 1) t1 = reinterpret_cast<const float*>(aux)[(lc.nb * g.TH + lc.yl) * g.TW + lc.xl];
-                else if (e.noise) t1 = __ldg(e.noise + (size_t)lc.n * plane_out + pix);
+                else if (e.noise) t1 = ld_dep_f32(e.noise + (size_t)lc.n * plane_out + pix);
                 nz = pk2(t1, t1);
               }
               if (g.aux_kind == 2) {
@@ -704,8 +711,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
                 const size_t plane_lo = (size_t)(e.Ho >> 1) * (e.Wo >> 1);
                 const size_t pl = (size_t)(y >> 1) * (e.Wo >> 1) + (x >> 1);
                 const act_t* ap = e.addsrc + (((size_t)(c0 >> 3) * g.N + lc.n) * plane_lo + pl) * 8;
-                add0 = __ldg(reinterpret_cast<const uint4*>(ap));
-                add1 = __ldg(reinterpret_cast<const uint4*>(ap + (size_t)g.N * plane_lo * 8));
+                add0 = ld_dep_u4(ap);
+                add1 = ld_dep_u4(ap + (size_t)g.N * plane_lo * 8);
               }
             }
             tmem_ld_wait();
@@ -714,7 +721,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
               if (lc.valid && cls != 4) {
                 const float* dp = e.bdelta + ((size_t)lc.n * 9 + cls) * g.bias_cols + cc * 16;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldg(dp + i));
+                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + ld_dep_f32(dp + i));
               }
             }
             if (lc.valid) {
@@ -797,6 +804,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) shiftconv_kernel(const __grid
     }
   }
 
+  if (pdl_late) pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);

@@ -64,6 +64,8 @@ uint64_t gsx_launch_count(void);
  *                 reference's operator order (networks_stylegan.py:56-73) everywhere -- for A/B tests.
  *   "fold_deconv_maxc" (default 16): the transposed conv + blur + noise/bias/lrelu/statistics of a block run as ONE kernel
  *                 when the block has at most this many channels (0: never).
+ *   "pdl" (default 3): programmatic dependent launch -- 0 off, 1 small passes + conv chains (round 1), 2 always with the trigger
+ *                 at kernel start, 3 always with the big kernels triggering when their CTAs finish, 4 = policy of 1 with late triggers.
  *   "varn" (default 1): stacked-phase up-convs issue MMAs only over the phase blocks a shift feeds (1: layers with >= 32
  *                 output channels, 2: all, 0: off);  "epi_groups" (default 2; 4 = experiment): epilogue warps per TMEM lane quarter
  *                 of the kernels without the generator epilogue. */

@@ -41,6 +41,66 @@ def test_main_generate_loop_single_gpu(tmp_path):
     _run([0], tmp_path, batch=2)
 
 
+def test_forward_is_independent_of_earlier_work_in_the_process(tmp_path):
+    """A forward pass gives bit-identical features whatever ran on the device before it.  Regression test: kernels chained
+    by programmatic dependent launch read producer-written data (statistics, AdaIN coefficients, activations) through the
+    non-coherent load path, and a res-8 generate loop before a res-6 forward left stale lines behind -> NaN features."""
+    from gan_segmentation_b200.networks import Generator
+    gc = generator_config(6)
+
+    def features():
+        G = Generator(gc)
+        G.set_parameters(init_generator_params(gc, seed=0))
+        outs = []
+        for _ in range(3):
+            out = G.forward(n=3, seed=5, return_u8=True, return_features=True)
+            outs.append([f.float().cpu().numpy() for f in out['features']] + [out['img_u8'].cpu().numpy()])
+        return outs
+
+    before = features()
+    _run([0], tmp_path, batch=2)
+    after = features()
+    for rep in before + after:
+        for a, b in zip(before[0], rep):
+            assert np.isfinite(b).all() and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize('res', [6, 8])
+def test_dependent_launch_does_not_change_results(res):
+    """Programmatic dependent launch (gsx_set_option("pdl", ...)) only overlaps launches: a sequence of forward passes with
+    DIFFERENT latents / noise per pass gives bit-identical images, features, logits and masks with it off and in every
+    mode.  Catches any read of a buffer before (or through a cache line from before) its producer's write of this pass."""
+    import gan_segmentation_b200._lib as L
+    from gan_segmentation_b200.networks import Generator, Decoder
+    gc, dc = generator_config(res), decoder_config(res)
+    lib = L.lib()
+
+    def run(mode):
+        assert lib.gsx_set_option(b'pdl', mode) == 0
+        G = Generator(gc)
+        G.set_parameters(init_generator_params(gc, seed=0))
+        D = Decoder(dc)
+        D.set_parameters(init_decoder_params(dc, seed=2))
+        outs = []
+        for seed in (1, 2, 3, 4, 5, 6):
+            n = 1 + seed % 3
+            out = G.forward(n=n, seed=seed, return_u8=True, return_features=True)
+            dec = D.forward(generator=G, n=n, return_logits=True)
+            outs.append([f.float().cpu().numpy() for f in out['features']] +
+                        [out['img_u8'].cpu().numpy(), dec['logits'].cpu().numpy(), dec['mask'].cpu().numpy()])
+        return outs
+
+    try:
+        ref = run(0)
+        for mode in (1, 2, 3, 4):
+            got = run(mode)
+            for i, (a, b) in enumerate(zip(ref, got)):
+                for j, (x, y) in enumerate(zip(a, b)):
+                    assert np.isfinite(y).all() and np.array_equal(x, y), (mode, i, j)
+    finally:
+        lib.gsx_set_option(b'pdl', 3)
+
+
 def test_multi_context_matches_single(tmp_path):
     """split_and_load over two contexts (image_generator.py:95-101) gives the same samples as one context."""
     if torch.cuda.device_count() < 2:
