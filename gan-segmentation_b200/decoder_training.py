@@ -316,6 +316,8 @@ class ResidentTrainer:
         self.wd = (cfg.get('wd', 0.0) or 0.0) if wd is None else wd
         self.beta1, self.beta2, self.eps = beta1, beta2, eps
         self.t = 0
+        if cfg.get('start_res', 0) != 0:
+            raise NotImplementedError('training with start_res != 0 (0 in the reference config, seg_solver.py:118)')
         nf = len(cfg['in_channels'])
         c = L.DecCfg()
         c.num_levels = nf

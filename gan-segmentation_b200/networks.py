@@ -9,6 +9,7 @@ torch owns device memory / streams only; all arithmetic happens in libgsx.so.  N
 from __future__ import annotations
 
 import ctypes as C
+import re
 
 import numpy as np
 import torch
@@ -167,21 +168,27 @@ class Decoder:
         self.dtype = dtype or L.DEFAULT_DTYPE
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self._lib = L.lib(self.dtype)
-        if cfg.get('start_res', 0) != 0:
-            raise NotImplementedError('start_res != 0')
         if cfg.get('use_sync_bn', False):
             raise NotImplementedError('SyncBatchNorm (off in the reference config, seg_solver.py:120)')
-        nf = len(cfg['in_channels'])
+        # start_res = s (networks_seg.py:55,63,80,107): levels below s have no blocks and their feature maps are ignored.
+        # The library sees the decoder of the remaining levels (its level 0 = reference level s, at base_hw << s);
+        # parameter names keep the reference's level numbers and are renumbered on the way in.
+        s0 = self.start_res = int(cfg.get('start_res', 0))
+        nf_all = len(cfg['in_channels'])
+        if not 0 <= s0 < nf_all:
+            raise ValueError(f'start_res {s0} outside the {nf_all} feature levels')
+        nf = nf_all - s0
         c = L.DecCfg()
         c.num_levels = nf
-        for i, v in enumerate(cfg['in_channels']):
+        for i, v in enumerate(cfg['in_channels'][s0:]):
             c.in_channels[i] = v
-        for i, v in enumerate(cfg['features']):
+        for i, v in enumerate(cfg['features'][s0:]):
             c.features[i] = v
         c.use_bn = int(bool(cfg['use_bn']))
-        c.base_y, c.base_x = base_hw
-        self.base_hw = tuple(base_hw)
+        c.base_y, c.base_x = base_hw[0] << s0, base_hw[1] << s0
+        self.base_hw = (base_hw[0] << s0, base_hw[1] << s0)
         self.num_levels = nf
+        self.num_levels_all = nf_all
         self.num_classes = cfg['features'][-1]
         h = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -190,7 +197,7 @@ class Decoder:
         self._ws = None
         self._ws_n = 0
         self._shapes = decoder_param_shapes(cfg)
-        self.out_hw = (base_hw[0] << (nf - 1), base_hw[1] << (nf - 1))
+        self.out_hw = (self.base_hw[0] << (nf - 1), self.base_hw[1] << (nf - 1))
 
     def __del__(self):
         try:
@@ -200,9 +207,16 @@ class Decoder:
         except Exception:
             pass
 
+    def _lib_name(self, cname):
+        # reference level number -> the library's (levels renumbered from start_res)
+        return re.sub(r'^(cvt_block|main_block)_(\d+)', lambda m: f'{m.group(1)}_{int(m.group(2)) - self.start_res}', cname)
+
     def set_parameters(self, params):
         with torch.cuda.device(self.device):
-            extra = _set_params(self._lib.gsx_dec_set_param, self._h, params, self._shapes, 'Decoder', self.dtype)
+            setter = self._lib.gsx_dec_set_param
+            if self.start_res:
+                setter = lambda h, name, *rest: self._lib.gsx_dec_set_param(h, self._lib_name(name.decode()).encode(), *rest)
+            extra = _set_params(setter, self._h, params, self._shapes, 'Decoder', self.dtype)
             L.check(self._lib.gsx_dec_finalize(self._h), 'gsx_dec_finalize', self.dtype)
         self._params = {canonical(k): np.asarray(v, np.float32) for k, v in params.items() if canonical(k) in self._shapes}
         return extra
@@ -234,10 +248,10 @@ class Decoder:
             feat_ptrs = None
             gh, gws = None, None
             if features is not None:
-                if len(features) != self.num_levels:
-                    raise ValueError(f'expected {self.num_levels} feature maps')
+                if len(features) != self.num_levels_all:
+                    raise ValueError(f'expected {self.num_levels_all} feature maps')
                 feat_ptrs = (C.c_void_p * self.num_levels)()
-                for i, f in enumerate(features):
+                for i, f in enumerate(features[self.start_res:]):
                     t = torch.as_tensor(f, dtype=torch.float32).to(self.device)
                     if t.dim() == 3:
                         t = t.unsqueeze(0)                         # seg_solver.py:313-314
@@ -248,6 +262,8 @@ class Decoder:
             else:
                 if generator is None:
                     raise ValueError('need features or generator')
+                if self.start_res:
+                    raise NotImplementedError('start_res != 0 with generator-resident features: pass the feature list')
                 n = generator._last_n if n is None else n
                 gh, gws = generator._h, L.ptr(generator.workspace(n))
             ws = self.workspace(n)

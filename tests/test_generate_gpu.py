@@ -91,6 +91,32 @@ def test_decoder_from_host_features_matches_device_path():
     assert torch.equal(dec2['logits'], dec['logits'])
 
 
+@pytest.mark.parametrize('start_res', [1, 3])
+def test_decoder_start_res(start_res):
+    """cfg['start_res'] = s (networks_seg.py:55,63,80,107): no blocks below level s, their feature maps are ignored, the
+    first block takes level s un-concatenated; parameters keep the reference's level numbers.  Logits vs the oracle on the
+    same fp32 features."""
+    from gan_segmentation_b200.networks import Decoder
+    from gan_segmentation_b200.random_init import init_decoder_params
+    from oracle import generate_oracle as O
+    gc, dc, gp, dp, z, noise = make_case(6, 2, seed=21)
+    dc = dict(dc, start_res=start_res)
+    dp = init_decoder_params(dc, seed=4)
+    assert not any(k.startswith('cvt_block_0') for k in dp)
+    with torch.no_grad():
+        _, feats = O.generator_forward(gp, gc, z, noise)
+        ref = O.decoder_forward(dp, dc, feats).numpy()
+    D = Decoder(dc)
+    assert D.set_parameters(dp) == []
+    dec = D.forward([f.numpy() for f in feats])
+    lg = dec['logits'].cpu().numpy()
+    assert lg.shape == ref.shape
+    assert rel_rms(lg, ref) < TOL['fp16']['feat'], rel_rms(lg, ref)
+    assert np.array_equal(dec['mask'].cpu().numpy(), first_max_argmax(lg))
+    with pytest.raises(ValueError):
+        D.forward([f.numpy() for f in feats[start_res:]])          # the full pyramid is expected, as in the reference
+
+
 def test_device_rng_path_matches_oracle_on_exported_noise():
     """Philox noise / latents generated on the device: export them and replay through the oracle."""
     from gan_segmentation_b200.networks import Generator
