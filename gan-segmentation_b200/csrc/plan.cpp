@@ -31,6 +31,7 @@ static thread_local bool g_pdl_small = false, g_pdl_chain = false, g_prev_conv =
 int g_pdl_mode = 3;     // gsx_set_option("pdl", v): 0 off / 1 by size (+ conv chains) / 2 always / 3 always, big kernels trigger late /
                         //   4 = policy of 1 with the late trigger
 void pdl_set_for_work(double top_level_pixels) {
+  if (top_level_pixels < 0) { g_pdl_small = g_pdl_chain = false; return; }      // plain stream order (the training step)
   const int mode = g_pdl_mode;
   g_pdl_small = mode == 2 || mode == 3 || ((mode == 1 || mode == 4) && top_level_pixels <= 2.0 * 1024 * 1024);
   g_pdl_chain = mode != 0;

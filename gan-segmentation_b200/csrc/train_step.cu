@@ -447,7 +447,13 @@ struct gsx_train {
   int4* pack_idx = nullptr;
   size_t pack_count = 0;
   float* bn_mem = nullptr;
-  unsigned int* counter = nullptr;                   // ticket counter of the last-block-finishes reductions (zero between launches)
+  unsigned int* counter = nullptr;                   // ticket counters of the last-block-finishes reductions, one per branch (zero between launches)
+  // Branches of one step (gsx_train_step): the cvt block of every level (forward, and its BatchNorm backward) on its own
+  // stream, the weight gradients on two more; joined to the caller's stream by events, so that a CUDA-graph capture of the
+  // step records the dependency graph instead of one chain.
+  std::vector<cudaStream_t> lvl_streams;
+  cudaStream_t wg_streams[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> events;
   const unsigned long long* seed_dev = nullptr;     // gsx_train_set_seed_buffer
   int sms = 148;
 };
@@ -456,8 +462,10 @@ namespace {
 
 struct TWs {
   std::vector<act_t*> feat, z_cvt, y_cvt, z_a, y_a, z_b, prev, sc;
-  act_t *upx, *g_out[2], *g1, *g2, *g_up, *g_sc, *g_in1, *dzc, *dlog;
-  float *stats, *wg_scratch, *logits, *ce_partial;
+  std::vector<act_t*> dzc;                                      // per level: the cvt branch runs beside the main chain
+  act_t *upx, *g_out[2], *g1, *g2, *g3, *g_up, *g_sc, *g_in1, *dlog;
+  std::vector<float*> stats;                                    // per branch (index = branch id, see gsx_train_step)
+  float *wg_scratch[2], *logits, *ce_partial;
   size_t total;
 };
 
@@ -476,6 +484,7 @@ TWs train_layout(const gsx_train* h, void* base, bool own_feats) {
     w.feat.push_back(own_feats ? reinterpret_cast<act_t*>(take(px * l.cin * 2)) : nullptr);
     w.z_cvt.push_back(reinterpret_cast<act_t*>(take(px * l.f * 2)));
     w.y_cvt.push_back(reinterpret_cast<act_t*>(take(px * l.f * 2)));
+    w.dzc.push_back(reinterpret_cast<act_t*>(take(px * l.f * 2)));
     if (!l.last) {
       w.z_a.push_back(reinterpret_cast<act_t*>(take(px * 4 * l.fnext * 2)));
       w.y_a.push_back(reinterpret_cast<act_t*>(take(px * 4 * l.fnext * 2)));
@@ -496,15 +505,16 @@ TWs train_layout(const gsx_train* h, void* base, bool own_feats) {
   for (int i = 0; i < 2; ++i) w.g_out[i] = reinterpret_cast<act_t*>(take(std::max(max_lo, max_hi) * 2));
   w.g1 = reinterpret_cast<act_t*>(take(max_hi * 2));
   w.g2 = reinterpret_cast<act_t*>(take(max_hi * 2));
+  w.g3 = reinterpret_cast<act_t*>(take(max_hi * 2));
   w.g_sc = reinterpret_cast<act_t*>(take(max_lo * 2));
   w.g_in1 = reinterpret_cast<act_t*>(take(max_lo * 2));
-  w.dzc = reinterpret_cast<act_t*>(take(max_lo * 2));
   const TLevel& top = h->levels[nf - 1];
   w.dlog = reinterpret_cast<act_t*>(take((size_t)N * top.H * top.W * 16 * 2));
   w.logits = reinterpret_cast<float*>(take((size_t)N * h->K * top.H * top.W * 4));
-  w.stats = reinterpret_cast<float*>(take((size_t)N * 2048 * 512 * 2 * 4 / 8));      // [N * T][C][2], T <= 2048/... (bounded below)
+  // reduction partials: one block writes 16 floats, a launch has at most 1184 + (C/8) N <= 1184 + 64 N blocks (t_tiles)
+  for (int b = 0; b < nf + 3; ++b) w.stats.push_back(reinterpret_cast<float*>(take((size_t)(1184 + 64 * N) * 16 * 4 * 2)));
   w.ce_partial = reinterpret_cast<float*>(take((size_t)N * 256 * 4));
-  w.wg_scratch = reinterpret_cast<float*>(take(max_wg * 4));
+  for (int i = 0; i < 2; ++i) w.wg_scratch[i] = reinterpret_cast<float*>(take(max_wg * 4));
   w.total = off;
   return w;
 }
@@ -645,7 +655,14 @@ extern "C" int gsx_train_create(const gsx_dec_cfg* cfg, int n, int use_dropout, 
   size_t bn_floats = 0;
   for (auto& l : h->levels) bn_floats += 6 * (size_t)(l.bn_cvt.C + l.bn_a.C + l.bn_b.C);
   ok = ok && cuda_ok(cudaMalloc(&h->bn_mem, std::max<size_t>(bn_floats, 1) * sizeof(float)), "cudaMalloc");
-  ok = ok && cuda_ok(cudaMalloc(&h->counter, sizeof(unsigned int)), "cudaMalloc") && cuda_ok(cudaMemset(h->counter, 0, sizeof(unsigned int)), "memset");
+  const int n_branches = h->nf + 3;                  // caller's stream, two weight-gradient streams, one per level
+  ok = ok && cuda_ok(cudaMalloc(&h->counter, n_branches * sizeof(unsigned int)), "cudaMalloc") &&
+       cuda_ok(cudaMemset(h->counter, 0, n_branches * sizeof(unsigned int)), "memset");
+  h->lvl_streams.resize(h->nf, nullptr);
+  for (int i = 0; ok && i < h->nf; ++i) ok = cuda_ok(cudaStreamCreateWithFlags(&h->lvl_streams[i], cudaStreamNonBlocking), "stream");
+  for (int i = 0; ok && i < 2; ++i) ok = cuda_ok(cudaStreamCreateWithFlags(&h->wg_streams[i], cudaStreamNonBlocking), "stream");
+  h->events.resize((size_t)h->nf * 12 + 16, nullptr);       // created up front: nothing is allocated while a step is being captured
+  for (size_t i = 0; ok && i < h->events.size(); ++i) ok = cuda_ok(cudaEventCreateWithFlags(&h->events[i], cudaEventDisableTiming), "event");
   if (!ok) { delete h; return -2; }
   float* bm = h->bn_mem;
   auto bn_take = [&](TBn& b) { if (!b.C) return; b.bnp = reinterpret_cast<float4*>(bm); bm += 4 * b.C; b.dparam = reinterpret_cast<float2*>(bm); bm += 2 * b.C; };
@@ -678,6 +695,9 @@ extern "C" void gsx_train_destroy(gsx_train* h) {
   for (auto& l : h->levels)
     for (TConv* c : {&l.cvt, &l.conv_a, &l.conv_b, &l.sc, &l.fin}) { cudaFree(c->fwd.taps_dev); cudaFree(c->dgrad.taps_dev); }
   cudaFree(h->wpack_all); cudaFree(h->pack_idx); cudaFree(h->bn_mem); cudaFree(h->counter);
+  for (cudaStream_t s : h->lvl_streams) if (s) cudaStreamDestroy(s);
+  for (cudaStream_t s : h->wg_streams) if (s) cudaStreamDestroy(s);
+  for (cudaEvent_t e : h->events) if (e) cudaEventDestroy(e);
   delete h;
 }
 
@@ -724,10 +744,14 @@ bool t_conv_dgrad(const TConv& c, int N, const act_t* dy, act_t* dx, cudaStream_
   e.out = dx; e.Ho = up ? 2 * c.H : c.H; e.Wo = up ? 2 * c.W : c.W; e.flags = 0; e.Cout = c.cin0 + c.cin1;
   return run_conv_layer(c.dgrad, N, dy, nullptr, e, st, label);
 }
-void t_bn_stats(const gsx_train* h, const TBn& b, const act_t* z, int HW, const float* p, float* r, float* stats, cudaStream_t st) {
+// A branch of the step: its stream and its own reduction scratch + ticket counter (branches run concurrently).
+struct TBranch { cudaStream_t st; float* stats; unsigned int* counter; };
+
+void t_bn_stats(const gsx_train* h, const TBn& b, const act_t* z, int HW, const float* p, float* r, const TBranch& br) {
   // enough blocks to fill the GPU at batch 1: (C/8)*N planes x T tiles; the last block finalizes
   const int T = t_tiles(HW, (b.C / 8) * h->n);
-  BnStatArgs a{z, stats, h->counter, b.C, h->n, HW, p + b.gamma_off, p + b.beta_off, r + b.rmean_off, r + b.rvar_off, b.bnp, nullptr, 0};
+  cudaStream_t st = br.st; float* stats = br.stats;
+  BnStatArgs a{z, stats, br.counter, b.C, h->n, HW, p + b.gamma_off, p + b.beta_off, r + b.rmean_off, r + b.rvar_off, b.bnp, nullptr, 0};
   bn_stats_kernel<<<dim3(T, (b.C / 8) * h->n), 256, 0, st>>>(a);
   g_launches++;
 }
@@ -738,10 +762,11 @@ void t_bn_fwd(const gsx_train* h, const TBn& b, const act_t* z, act_t* y, int H,
 }
 // dz (may alias dy) from dy, and dgamma / dbeta into the gradient bucket
 void t_bn_bwd(const gsx_train* h, const TBn& b, const act_t* z, const act_t* dy, act_t* dz, int HW, int site, uint64_t seed, float* g,
-              float* stats, cudaStream_t st) {
+              const TBranch& br) {
   const int T = t_tiles(HW, (b.C / 8) * h->n);
+  cudaStream_t st = br.st; float* stats = br.stats;
   BnBwdArgs a{z, dy, dz, b.bnp, b.dparam, stats, b.C, h->n, HW, T, site, seed, (float)h->n * (float)HW, h->seed_dev,
-              h->counter, g + b.gamma_off, g + b.beta_off, b.dparam};
+              br.counter, g + b.gamma_off, g + b.beta_off, b.dparam};
   bn_bwd_reduce_kernel<<<dim3(T, (b.C / 8) * h->n), 256, 0, st>>>(a);
   bn_bwd_apply_kernel<<<dim3(ew_grid(HW), (b.C / 8) * h->n), 256, 0, st>>>(a);
   g_launches += 2;
@@ -753,9 +778,10 @@ bool t_wgrad(const gsx_train* h, const TConv& c, const act_t* x0, const act_t* x
   if (c.cin1 && !launch_wgrad(c.k, h->n, Hx, Wx, c.cin1, c.cout_pad, c.cout, x1, dy, g + c.w_off, c.cin0, cin, 1.f, scratch, st)) return false;
   return true;
 }
-void t_bias_grad(const gsx_train* h, const act_t* dy, int Cpad, int Creal, int HW, float* out, float* stats, cudaStream_t st) {
+void t_bias_grad(const gsx_train* h, const act_t* dy, int Cpad, int Creal, int HW, float* out, const TBranch& br) {
   const int T = t_tiles(HW, (Cpad / 8) * h->n);
-  BnStatArgs a{dy, stats, h->counter, Cpad, h->n, HW, nullptr, nullptr, nullptr, nullptr, nullptr, out, Creal};
+  cudaStream_t st = br.st; float* stats = br.stats;
+  BnStatArgs a{dy, stats, br.counter, Cpad, h->n, HW, nullptr, nullptr, nullptr, nullptr, nullptr, out, Creal};
   bn_stats_kernel<<<dim3(T, (Cpad / 8) * h->n), 256, 0, st>>>(a);
   g_launches++;
 }
@@ -773,34 +799,68 @@ extern "C" int gsx_train_step(gsx_train* h, const float* params_dev, float* grad
   const int nf = h->nf, N = h->n;
   TWs w = train_layout(h, ws, true);
   if (w.total > ws_bytes) { set_error("training workspace too small"); return -1; }
-  pdl_set_for_work(1e12);                                  // plain stream order between the kernels of the step
+  pdl_set_for_work(-1);                                    // plain stream order between the kernels of the step
   const float* P = params_dev;
   float* R = const_cast<float*>(params_dev);               // the moving statistics live behind the learnable prefix
   float* G = grads_dev;
   const bool drop = h->use_dropout;
   set_error("");
+
+  // Branches.  At batch 1 most of the ~300 kernels of a step fill a fraction of the GPU (a 512-channel cvt conv at 4^2..32^2
+  // is ONE CTA for 25-80 us), and more than half of them are leaves of the dependency graph: the cvt block of a level needs
+  // only that level's features, nothing but the optimizer waits for a weight gradient, and the cvt block's backward ends in
+  // one.  So: the caller's stream runs the main chain (res-blocks forward, loss, data gradients), every level's cvt block
+  // runs on its own stream, the weight gradients on two more; events join them.  Captured into a CUDA graph this is the
+  // step's dependency DAG.  Each branch has its own reduction scratch, ticket counter and (weight gradients) partial buffer;
+  // a scratch tensor that a side branch reads is not overwritten by the main chain before that read is done (ev_* below).
+  const TBranch main_br{st, w.stats[0], h->counter};
+  const TBranch wg_br[2] = {{h->wg_streams[0], w.stats[1], h->counter + 1}, {h->wg_streams[1], w.stats[2], h->counter + 2}};
+  std::vector<TBranch> lvl_br;
+  for (int i = 0; i < nf; ++i) lvl_br.push_back(TBranch{h->lvl_streams[i], w.stats[3 + i], h->counter + 3 + i});
+  size_t next_event = 0;
+  bool ev_ok = true;
+  auto record = [&](cudaStream_t on) -> cudaEvent_t {
+    if (next_event >= h->events.size()) { ev_ok = false; return nullptr; }
+    cudaEvent_t e = h->events[next_event++];
+    ev_ok = ev_ok && cudaEventRecord(e, on) == cudaSuccess;
+    return e;
+  };
+  auto wait = [&](cudaStream_t on, cudaEvent_t e) { if (e) ev_ok = ev_ok && cudaStreamWaitEvent(on, e, 0) == cudaSuccess; };
+  auto link = [&](cudaStream_t from, cudaStream_t to) { wait(to, record(from)); };
+
   // 16-bit operand streams of every conv (forward + data gradient) from the fp32 master weights
   pack_kernel<<<std::max(1, std::min((int)((h->pack_count + 255) / 256), 1184)), 256, 0, st>>>(P, h->pack_idx, h->wpack_all, h->pack_count);
   g_launches++;
   // gradient bucket: every entry is written exactly once below, except the biases in front of a BatchNorm (exactly zero)
   if (!cuda_ok(cudaMemsetAsync(G, 0, h->n_learn * sizeof(float), st), "zero grads")) return -2;
+  {
+    cudaEvent_t start = record(st);                        // operands packed, bucket zeroed, the caller's earlier work done
+    for (int i = 0; i < nf; ++i) wait(lvl_br[i].st, start);
+    for (int i = 0; i < 2; ++i) wait(wg_br[i].st, start);
+  }
 
   // ---------------------------------------------------------------- forward (train mode)
-  for (int i = 0; i < nf; ++i) {
+  for (int i = 0; i < nf; ++i) {                           // cvt blocks: one branch per level
+    const TLevel& l = h->levels[i];
+    const TBranch& br = lvl_br[i];
+    const int HW = l.H * l.W;
+    launch_nchw_to_blocked(feats_f32_dev[i], w.feat[i], l.cin, N, HW, br.st); g_launches++;
+    if (!t_conv_fwd(l.cvt, N, w.feat[i], nullptr, w.z_cvt[i], P + l.cvt.b_off, br.st, "t.cvt")) return -2;
+    t_bn_stats(h, l.bn_cvt, w.z_cvt[i], HW, P, R, br);
+    t_bn_fwd(h, l.bn_cvt, w.z_cvt[i], w.y_cvt[i], l.H, l.W, drop ? i : -1, dropout_seed, nullptr, br.st);
+  }
+  for (int i = 0; i < nf; ++i) {                           // main chain
     const TLevel& l = h->levels[i];
     const int HW = l.H * l.W;
-    launch_nchw_to_blocked(feats_f32_dev[i], w.feat[i], l.cin, N, HW, st); g_launches++;
-    if (!t_conv_fwd(l.cvt, N, w.feat[i], nullptr, w.z_cvt[i], P + l.cvt.b_off, st, "t.cvt")) return -2;
-    t_bn_stats(h, l.bn_cvt, w.z_cvt[i], HW, P, R, w.stats, st);
-    t_bn_fwd(h, l.bn_cvt, w.z_cvt[i], w.y_cvt[i], l.H, l.W, drop ? i : -1, dropout_seed, nullptr, st);
+    link(lvl_br[i].st, st);                                // y_cvt[i]
     const act_t* x0 = i > 0 ? w.prev[i - 1] : w.y_cvt[i];
     const act_t* x1 = i > 0 ? w.y_cvt[i] : nullptr;
     if (!l.last) {
       if (!t_conv_fwd(l.conv_a, N, x0, x1, w.z_a[i], P + l.conv_a.b_off, st, "t.conv_a")) return -2;
-      t_bn_stats(h, l.bn_a, w.z_a[i], 4 * HW, P, R, w.stats, st);
+      t_bn_stats(h, l.bn_a, w.z_a[i], 4 * HW, P, R, main_br);
       t_bn_fwd(h, l.bn_a, w.z_a[i], w.y_a[i], 2 * l.H, 2 * l.W, -1, 0, nullptr, st);
       if (!t_conv_fwd(l.conv_b, N, w.y_a[i], nullptr, w.z_b[i], P + l.conv_b.b_off, st, "t.conv_b")) return -2;
-      t_bn_stats(h, l.bn_b, w.z_b[i], 4 * HW, P, R, w.stats, st);
+      t_bn_stats(h, l.bn_b, w.z_b[i], 4 * HW, P, R, main_br);
       const act_t* sc = x0;
       if (l.has_sc) {
         if (!t_conv_fwd(l.sc, N, x0, x1, w.sc[i], P + l.sc.b_off, st, "t.shortcut")) return -2;
@@ -829,7 +889,11 @@ extern "C" int gsx_train_step(gsx_train* h, const float* params_dev, float* grad
   if (grad_scale_out) *grad_scale_out = gscale;
 
   // ---------------------------------------------------------------- backward
+  // main chain: BatchNorm backward -> data gradient, level by level; weight gradients branch off to wg_br[0] (the res-block's
+  // two convs) and wg_br[1] (shortcut, final conv, cvt), the cvt block's BatchNorm backward to the level's own stream.
   const act_t* d_prev_out = nullptr;        // gradient w.r.t. prev_{i+1} while level i is processed
+  cudaEvent_t ev_g1 = nullptr, ev_g3 = nullptr, ev_gsc = nullptr;      // last side-branch read of the scratch tensors g1 / g3 / g_sc
+  std::vector<cudaEvent_t> ev_cvt_bwd(nf + 2, nullptr);               // level i's cvt branch has read its slice of g_out[i & 1]
   for (int i = nf - 1; i >= 0; --i) {
     const TLevel& l = h->levels[i];
     const int HW = l.H * l.W, cm = l.c0 + l.c1;
@@ -837,45 +901,65 @@ extern "C" int gsx_train_step(gsx_train* h, const float* params_dev, float* grad
     const act_t* x1 = i > 0 ? w.y_cvt[i] : nullptr;
     act_t* dxin = w.g_out[i & 1];           // [cm/8][N][H][W][8]: first c0 channels -> prev_i, rest -> cvt_i
     if (l.last) {
-      if (!t_wgrad(h, l.fin, x0, x1, w.dlog, G, w.wg_scratch, st, l.H, l.W)) return -2;
-      t_bias_grad(h, w.dlog, 16, l.fnext, HW, G + l.fin.b_off, w.stats, st);
-      if (i > 0 && !t_conv_dgrad(l.fin, N, w.dlog, dxin, st, "t.final.dgrad")) return -2;
       if (i == 0) { set_error("single-level decoders are not supported by the training step"); return -1; }
+      link(st, wg_br[1].st);                                                                            // dlog
+      if (!t_wgrad(h, l.fin, x0, x1, w.dlog, G, w.wg_scratch[1], wg_br[1].st, l.H, l.W)) return -2;
+      t_bias_grad(h, w.dlog, 16, l.fnext, HW, G + l.fin.b_off, wg_br[1]);
+      if (!t_conv_dgrad(l.fin, N, w.dlog, dxin, st, "t.final.dgrad")) return -2;
     } else {
       // second conv of the res-block
-      t_bn_bwd(h, l.bn_b, w.z_b[i], d_prev_out, w.g1, 4 * HW, -1, 0, G, w.stats, st);                 // dz_b
+      wait(st, ev_g1);
+      t_bn_bwd(h, l.bn_b, w.z_b[i], d_prev_out, w.g1, 4 * HW, -1, 0, G, main_br);                      // dz_b
+      link(st, wg_br[0].st);
       if (!launch_wgrad(3, N, 2 * l.H, 2 * l.W, l.fnext, l.conv_b.cout_pad, l.fnext, w.y_a[i], w.g1, G + l.conv_b.w_off, 0, l.fnext, 1.f,
-                        w.wg_scratch, st)) return -2;
+                        w.wg_scratch[0], wg_br[0].st)) return -2;
+      ev_g1 = record(wg_br[0].st);
       // (bias in front of a BatchNorm: sum(dz) == 0 exactly -- the bucket was zeroed at the start of the step)
       if (!t_conv_dgrad(l.conv_b, N, w.g1, w.g2, st, "t.conv_b.dgrad")) return -2;                     // dy_a
       // first conv (nearest-x2 + 3x3)
-      t_bn_bwd(h, l.bn_a, w.z_a[i], w.g2, w.g1, 4 * HW, -1, 0, G, w.stats, st);                       // dz_a
+      wait(st, ev_g3);
+      t_bn_bwd(h, l.bn_a, w.z_a[i], w.g2, w.g3, 4 * HW, -1, 0, G, main_br);                            // dz_a
+      link(st, wg_br[0].st);
       {
-        upsample2_blocked_kernel<<<dim3(ew_grid(4 * HW), (l.c0 / 8) * N), 256, 0, st>>>(x0, w.upx, l.H, l.W);
-        if (l.c1) upsample2_blocked_kernel<<<dim3(ew_grid(4 * HW), (l.c1 / 8) * N), 256, 0, st>>>(x1, w.upx + (size_t)N * 4 * HW * l.c0, l.H, l.W);
+        cudaStream_t ws0 = wg_br[0].st;
+        upsample2_blocked_kernel<<<dim3(ew_grid(4 * HW), (l.c0 / 8) * N), 256, 0, ws0>>>(x0, w.upx, l.H, l.W);
+        if (l.c1) upsample2_blocked_kernel<<<dim3(ew_grid(4 * HW), (l.c1 / 8) * N), 256, 0, ws0>>>(x1, w.upx + (size_t)N * 4 * HW * l.c0, l.H, l.W);
         g_launches += 2;
-        if (!launch_wgrad(3, N, 2 * l.H, 2 * l.W, cm, l.conv_a.cout_pad, l.fnext, w.upx, w.g1, G + l.conv_a.w_off, 0, cm, 1.f, w.wg_scratch, st))
+        if (!launch_wgrad(3, N, 2 * l.H, 2 * l.W, cm, l.conv_a.cout_pad, l.fnext, w.upx, w.g3, G + l.conv_a.w_off, 0, cm, 1.f, w.wg_scratch[0], ws0))
           return -2;
+        ev_g3 = record(ws0);
       }
-      if (!t_conv_dgrad(l.conv_a, N, w.g1, w.g_up, st, "t.conv_a.dgrad")) return -2;                   // gradient at 2H x 2W
+      if (!t_conv_dgrad(l.conv_a, N, w.g3, w.g_up, st, "t.conv_a.dgrad")) return -2;                   // gradient at 2H x 2W
       // shortcut branch
+      wait(st, ev_gsc);
       sumpool2_blocked_kernel<<<dim3(ew_grid(HW), (l.fnext / 8) * N), 256, 0, st>>>(d_prev_out, nullptr, w.g_sc, 0, l.H, l.W);
-      g_launches += 3;
+      g_launches++;
       const act_t* addend = w.g_sc;
       if (l.has_sc) {
-        if (!t_wgrad(h, l.sc, x0, x1, w.g_sc, G, w.wg_scratch, st, l.H, l.W)) return -2;
-        t_bias_grad(h, w.g_sc, l.sc.cout_pad, l.fnext, HW, G + l.sc.b_off, w.stats, st);
+        link(st, wg_br[1].st);
+        if (!t_wgrad(h, l.sc, x0, x1, w.g_sc, G, w.wg_scratch[1], wg_br[1].st, l.H, l.W)) return -2;
+        t_bias_grad(h, w.g_sc, l.sc.cout_pad, l.fnext, HW, G + l.sc.b_off, wg_br[1]);
+        ev_gsc = record(wg_br[1].st);
         if (!t_conv_dgrad(l.sc, N, w.g_sc, w.g_in1, st, "t.shortcut.dgrad")) return -2;
         addend = w.g_in1;
       }
+      wait(st, ev_cvt_bwd[i + 2]);          // g_out[i & 1] was level i+2's dxin
       sumpool2_blocked_kernel<<<dim3(ew_grid(HW), (cm / 8) * N), 256, 0, st>>>(w.g_up, addend, dxin, 0, l.H, l.W);
       g_launches++;
     }
     // cvt block: the last l.f channels of dxin (all of them at level 0)
     const act_t* d_c = dxin + (size_t)N * HW * l.c0 * (i > 0 ? 1 : 0);
-    t_bn_bwd(h, l.bn_cvt, w.z_cvt[i], d_c, w.dzc, HW, drop ? i : -1, dropout_seed, G, w.stats, st);
-    if (!launch_wgrad(3, N, l.H, l.W, l.cin, l.cvt.cout_pad, l.f, w.feat[i], w.dzc, G + l.cvt.w_off, 0, l.cin, 1.f, w.wg_scratch, st)) return -2;
+    link(st, lvl_br[i].st);
+    t_bn_bwd(h, l.bn_cvt, w.z_cvt[i], d_c, w.dzc[i], HW, drop ? i : -1, dropout_seed, G, lvl_br[i]);
+    ev_cvt_bwd[i] = record(lvl_br[i].st);
+    wait(wg_br[1].st, ev_cvt_bwd[i]);
+    if (!launch_wgrad(3, N, l.H, l.W, l.cin, l.cvt.cout_pad, l.f, w.feat[i], w.dzc[i], G + l.cvt.w_off, 0, l.cin, 1.f, w.wg_scratch[1], wg_br[1].st))
+      return -2;
     d_prev_out = dxin;                      // its first c0 channel blocks = gradient w.r.t. prev_i (level i-1's output)
   }
+  // join: the step is complete on the caller's stream
+  for (int i = 0; i < nf; ++i) link(lvl_br[i].st, st);
+  for (int i = 0; i < 2; ++i) link(wg_br[i].st, st);
+  if (!ev_ok) { set_error("train step: event record / wait failed"); return -2; }
   return cuda_ok(cudaGetLastError(), "train step") ? 0 : -2;
 }
