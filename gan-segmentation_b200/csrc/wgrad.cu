@@ -211,17 +211,28 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// dW[co][ci][ky][kx] (+ optional accumulate) = scale * sum over CTAs of partial[mt][cta][tap][ci % 128][co]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int ctas, int m_tiles, int taps,
-                                    int Cin, int Cout, int cout_real, int cin_off, int cin_total, float scale, int rows) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  const int total = taps * Cin * cout_real;
-  if (e >= total) return;
-  const int tp = e % taps, ci = (e / taps) % Cin, co = e / (taps * Cin);
+// dW[co][ci][ky][kx] = scale * sum over CTAs of partial[mt][cta][tap][ci % 128][co].  One block per (tap, ci): thread
+// (part, co) adds the CTAs part, part + parts, ... (reads coalesced over co), the parts are combined in a fixed order ->
+// bit-reproducible.  (One thread per output walking all CTAs was 19 us for the 148-CTA layers: 2 blocks, 148 dependent-
+// latency rounds of scattered 4-byte reads.)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int ctas, int m_tiles,
+                                                           int taps, int Cin, int Cout, int cout_real, int cin_off, int cin_total,
+                                                           float scale, int rows) {
+  __shared__ float sh[256];
+  (void)m_tiles; (void)Cin;
+  const int tp = blockIdx.x % taps, ci = blockIdx.x / taps;
   const int mt = ci / 128, r = ci - mt * 128;
+  const int parts = 256 / Cout;
+  const int co = threadIdx.x % Cout, part = threadIdx.x / Cout;
   float s = 0.f;
-  for (int c = 0; c < ctas; ++c) s += partial[(((size_t)(mt * ctas + c) * taps + tp) * rows + r) * Cout + co];   // fixed order
-  dw[((size_t)co * cin_total + cin_off + ci) * taps + tp] = s * scale;
+  if (part < parts)
+    for (int c = part; c < ctas; c += parts) s += partial[(((size_t)(mt * ctas + c) * taps + tp) * rows + r) * Cout + co];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  if (part == 0 && co < cout_real) {
+    for (int q = 1; q < parts; ++q) s += sh[q * Cout + co];
+    dw[((size_t)co * cin_total + cin_off + ci) * taps + tp] = s * scale;
+  }
 }
 
 static int g_wg_sms = 0;
@@ -290,8 +301,7 @@ bool launch_wgrad(int K, int N, int H, int W, int Cin, int Cout, int cout_real, 
   if (!configured[dev]) { cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); configured[dev] = true; }
   const size_t smem = 1024 + (size_t)kWgStages * g.stage_bytes;
   wgrad_kernel<<<dim3(ctas, g.m_tiles), 192, smem, st>>>(p);
-  const int total = K * K * Cin * cout_real;
-  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(scratch, dw, ctas, g.m_tiles, K * K, Cin, Cout, cout_real, cin_off, cin_total, scale, g.rows);
+  wgrad_reduce_kernel<<<K * K * Cin, 256, 0, st>>>(scratch, dw, ctas, g.m_tiles, K * K, Cin, Cout, cout_real, cin_off, cin_total, scale, g.rows);
   g_launches += 2;
   return cuda_ok(cudaGetLastError(), "wgrad launch");
 }
