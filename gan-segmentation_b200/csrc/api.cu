@@ -109,6 +109,7 @@ static ModBufs take_mod(Arena& a, const ConvLayer& L, int N) {
   return m;
 }
 static int g_opt_fold_apply = 1;           // gsx_set_option("fold_apply", 0/1), read when a handle is finalized
+static int g_opt_dec_branches = 1;         // gsx_set_option("dec_branches", 0/1): decoder cvt blocks / shortcuts of the small levels on side streams
 static int g_opt_fold_deconv_maxc = 16;    // gsx_set_option("fold_deconv_maxc", C): deconv+blur folded into one kernel up to C channels
 
 // Runs one planned conv layer: builds the tensor maps for this batch / these buffers and launches.
@@ -302,6 +303,7 @@ extern "C" uint64_t gsx_launch_count(void) { return g_launches.load(); }
 extern "C" int gsx_set_option(const char* name, int value) {
   if (name && std::strcmp(name, "fold_apply") == 0) { g_opt_fold_apply = value != 0; return 0; }
   if (name && std::strcmp(name, "fold_deconv_maxc") == 0) { g_opt_fold_deconv_maxc = value; return 0; }
+  if (name && std::strcmp(name, "dec_branches") == 0) { g_opt_dec_branches = value != 0; return 0; }
   if (name && std::strcmp(name, "wgrad_m64") == 0 && value >= 0 && value <= 2) { g_wgrad_m64 = value; return 0; }
   if (name && std::strcmp(name, "pdl") == 0 && value >= 0 && value <= 4) {
     g_pdl_mode = value;
@@ -760,6 +762,10 @@ struct gsx_dec {
   std::map<std::string, HostTensor> params;
   bool finalized = false;
   std::vector<DecLevel> levels;
+  // side branches of a forward pass (gsx_dec_forward): one stream per level for the cvt block, one for the 1x1 shortcuts
+  std::vector<cudaStream_t> cvt_streams;
+  cudaStream_t sc_stream = nullptr;
+  std::vector<cudaEvent_t> events;
 };
 
 struct DecWs {
@@ -818,6 +824,9 @@ static void free_level(DecLevel& l) {
 extern "C" void gsx_dec_destroy(gsx_dec* d) {
   if (!d) return;
   for (auto& l : d->levels) free_level(l);
+  for (cudaStream_t st : d->cvt_streams) if (st) cudaStreamDestroy(st);
+  if (d->sc_stream) cudaStreamDestroy(d->sc_stream);
+  for (cudaEvent_t e : d->events) if (e) cudaEventDestroy(e);
   delete d;
 }
 
@@ -935,6 +944,15 @@ extern "C" int gsx_dec_finalize(gsx_dec* d) {
   }
   if (!cuda_ok(cudaDeviceSynchronize(), "dec finalize")) return -2;
   set_error("");
+  if (d->cvt_streams.empty()) {        // created once, up front: nothing is allocated while a forward pass is being captured
+    d->cvt_streams.assign(nf, nullptr);
+    bool ok = true;
+    for (int i = 0; ok && i < nf; ++i) ok = cuda_ok(cudaStreamCreateWithFlags(&d->cvt_streams[i], cudaStreamNonBlocking), "stream");
+    ok = ok && cuda_ok(cudaStreamCreateWithFlags(&d->sc_stream, cudaStreamNonBlocking), "stream");
+    d->events.assign((size_t)3 * nf + 4, nullptr);
+    for (size_t i = 0; ok && i < d->events.size(); ++i) ok = cuda_ok(cudaEventCreateWithFlags(&d->events[i], cudaEventDisableTiming), "event");
+    if (!ok) return -2;
+  }
   d->finalized = true;
   return 0;
 }
@@ -980,33 +998,68 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
       }
     }
   }
+  // Branches.  The cvt block of a level needs only that level's feature map, the 1x1 shortcut only the level's input; at the
+  // levels whose convs fill a fraction of the GPU (all of them at batch 1; 4^2..32^2 at batch 32) they run on side streams
+  // beside the main chain conv_a -> conv_b and join it by events (the same shape as the training step's branches,
+  // train_step.cu).  Off while the per-layer table is being taken (its events time the caller's stream).
+  const bool branches = g_opt_dec_branches && !g_prof_on && !d->cvt_streams.empty();
+  auto is_small = [&](int i) { return branches && (double)N * d->levels[i].H * d->levels[i].W <= 96.0 * 1024; };
+  size_t next_event = 0;
+  bool ev_ok = true;
+  auto record = [&](cudaStream_t on) -> cudaEvent_t {
+    if (next_event >= d->events.size()) { ev_ok = false; return nullptr; }
+    cudaEvent_t e = d->events[next_event++];
+    ev_ok = ev_ok && cudaEventRecord(e, on) == cudaSuccess;
+    return e;
+  };
+  auto wait = [&](cudaStream_t on, cudaEvent_t e) { if (e) ev_ok = ev_ok && cudaStreamWaitEvent(on, e, 0) == cudaSuccess; };
+  auto run_cvt = [&](int i, cudaStream_t on) -> bool {
+    const DecLevel& l = d->levels[i];
+    ConvEpi e{};
+    e.out = w.c[i]; e.Ho = l.H; e.Wo = l.W; e.flags = EPI_LRELU; e.Cout = l.f; e.bias = l.b_cvt;
+    if (feat_coef[i]) {
+      const ModBufs& m = w.mod[i];
+      { ProfScope ps("d" + std::to_string(i) + ".modulate", 0, 0, on);
+        launch_modulate(l.cvt_ps, feat_coef[i], l.b_cvt, N, m.w, m.bias_n, m.bdelta, on); g_launches++; }
+      return run_conv(l.cvt_ps, N, feat[i], nullptr, e, on, ("d" + std::to_string(i) + ".cvt").c_str(), &m);
+    }
+    return run_conv(l.cvt, N, feat[i], nullptr, e, on, ("d" + std::to_string(i) + ".cvt").c_str());
+  };
+  std::vector<cudaEvent_t> ev_cvt(nf, nullptr);
+  {
+    cudaEvent_t start = nullptr;
+    for (int i = 0; i < nf; ++i) {
+      if (!is_small(i)) continue;
+      if (!start) start = record(st);                    // the features (and everything earlier on the caller's stream)
+      wait(d->cvt_streams[i], start);
+      if (!run_cvt(i, d->cvt_streams[i])) return -2;
+      ev_cvt[i] = record(d->cvt_streams[i]);
+    }
+  }
   for (int i = 0; i < nf; ++i) {
     const DecLevel& l = d->levels[i];
-    {
-      ConvEpi e{};
-      e.out = w.c[i]; e.Ho = l.H; e.Wo = l.W; e.flags = EPI_LRELU; e.Cout = l.f; e.bias = l.b_cvt;
-      if (feat_coef[i]) {
-        const ModBufs& m = w.mod[i];
-        { ProfScope ps("d" + std::to_string(i) + ".modulate", 0, 0, st);
-          launch_modulate(l.cvt_ps, feat_coef[i], l.b_cvt, N, m.w, m.bias_n, m.bdelta, st); g_launches++; }
-        if (!run_conv(l.cvt_ps, N, feat[i], nullptr, e, st, ("d" + std::to_string(i) + ".cvt").c_str(), &m)) return -2;
-      } else if (!run_conv(l.cvt, N, feat[i], nullptr, e, st, ("d" + std::to_string(i) + ".cvt").c_str())) return -2;
-    }
+    if (ev_cvt[i]) wait(st, ev_cvt[i]);
+    else if (!run_cvt(i, st)) return -2;
     const act_t* x0 = i > 0 ? w.prev[i] : w.c[i];
     const act_t* x1 = i > 0 ? w.c[i] : nullptr;
     if (i < nf - 1) {
+      const act_t* sc = x0;
+      cudaEvent_t ev_sc = nullptr;
+      if (l.has_shortcut) {
+        ConvEpi e{};
+        e.out = w.sc[i]; e.Ho = l.H; e.Wo = l.W; e.flags = 0; e.Cout = l.fnext; e.bias = l.b_sc;
+        cudaStream_t on = st;
+        if (is_small(i)) { on = d->sc_stream; wait(on, record(st)); }       // x0 / x1 are complete on the caller's stream here
+        if (!run_conv(l.shortcut, N, x0, x1, e, on, ("d" + std::to_string(i) + ".shortcut").c_str())) return -2;
+        if (on != st) ev_sc = record(on);
+        sc = w.sc[i];
+      }
       {
         ConvEpi e{};
         e.out = w.a[i]; e.Ho = 2 * l.H; e.Wo = 2 * l.W; e.up = 1; e.flags = EPI_LRELU; e.Cout = l.fnext; e.bias = l.b_a;
         if (!run_conv(l.conv_a, N, x0, x1, e, st, ("d" + std::to_string(i) + ".conv_a").c_str())) return -2;
       }
-      const act_t* sc = x0;
-      if (l.has_shortcut) {
-        ConvEpi e{};
-        e.out = w.sc[i]; e.Ho = l.H; e.Wo = l.W; e.flags = 0; e.Cout = l.fnext; e.bias = l.b_sc;
-        if (!run_conv(l.shortcut, N, x0, x1, e, st, ("d" + std::to_string(i) + ".shortcut").c_str())) return -2;
-        sc = w.sc[i];
-      }
+      wait(st, ev_sc);
       {
         ConvEpi e{};
         e.out = w.prev[i + 1]; e.Ho = 2 * l.H; e.Wo = 2 * l.W; e.flags = EPI_LRELU; e.Cout = l.fnext; e.bias = l.b_b;
@@ -1020,6 +1073,7 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
       if (!run_conv(l.final_, N, x0, x1, e, st, ("d" + std::to_string(i) + ".final+argmax").c_str())) return -2;
     }
   }
+  if (!ev_ok) { set_error("dec forward: event record / wait failed"); return -2; }
   return cuda_ok(cudaGetLastError(), "dec forward") ? 0 : -2;
 }
 
