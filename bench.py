@@ -409,10 +409,8 @@ def main():
     def step_device(i):
         # latents already resident in HBM; noise from the on-device Philox stream of the global sample index
         first = (i * world + rank) * B
-        L.check(lib.gsx_synth_forward(G._h, B, L.ptr(z_dev), L.np_ptr(psi), None, 7, first, None, L.ptr(img_dev), None,
-                                      L.ptr(pipe.gws), pipe.gws.numel(), sp), 'synth', args.dtype)
-        L.check(lib.gsx_dec_forward(D._h, B, None, G._h, L.ptr(pipe.gws), None, L.ptr(mask_dev), L.ptr(pipe.dws),
-                                    pipe.dws.numel(), sp), 'dec', args.dtype)
+        L.check(lib.gsx_generate_dev(G._h, D._h, B, L.ptr(z_dev), L.np_ptr(psi), 7, first, L.ptr(img_dev), L.ptr(mask_dev),
+                                     L.ptr(pipe.gws), pipe.gws.numel(), L.ptr(pipe.dws), pipe.dws.numel(), sp), 'generate', args.dtype)
 
     z_host = np.random.RandomState(99 + rank).randn(B, 512).astype(np.float32)
 

@@ -78,6 +78,7 @@ _SIGS = {
     'gsx_dec_finalize': (_i, [_vp]),
     'gsx_dec_workspace_bytes': (_i, [_vp, _i, C.POINTER(_sz)]),
     'gsx_dec_forward': (_i, [_vp, _i, C.POINTER(_vp), _vp, _vp, _fp, _vp, _vp, _sz, _vp]),
+    'gsx_generate_dev': (_i, [_vp, _vp, _i, _fp, _fp, _u64, _u64, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     'gsx_generate_host': (_i, [_vp, _vp, _i, _fp, _fp, _u64, _u64, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _i]),
     'gsx_synth_device_counter': (_i, [_vp, _i, C.c_uint64]),
     'gsx_op_conv_wgrad': (_i, [_i, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _vp]),

@@ -109,7 +109,13 @@ static ModBufs take_mod(Arena& a, const ConvLayer& L, int N) {
   return m;
 }
 static int g_opt_fold_apply = 1;           // gsx_set_option("fold_apply", 0/1), read when a handle is finalized
+static int g_opt_dec_branch_kpx = 1 << 20;  // ... for levels with at most this many thousand pixels in the batch ("dec_branch_kpx"; measured: branching every level is best -- FFHQ batch 32: 96 K px 3147, 600 K 3169, all 3178 samples/s)
 static int g_opt_dec_branches = 1;         // gsx_set_option("dec_branches", 0/1): decoder cvt blocks / shortcuts of the small levels on side streams
+// Set by the fused generate calls around gsx_synth_forward: the ToRGB pass (a read of the last tensor and the image write,
+// HBM-bound) goes to the generator's side stream and runs beside the decoder, which does not need the image; the fused
+// call joins it before it returns.  gsx_synth_forward on its own always finishes the image on the caller's stream.
+static thread_local bool t_defer_rgb = false;
+static int g_opt_defer_rgb = 1;            // gsx_set_option("defer_rgb", 0/1)
 static int g_opt_fold_deconv_maxc = 16;    // gsx_set_option("fold_deconv_maxc", C): deconv+blur folded into one kernel up to C channels
 
 // Runs one planned conv layer: builds the tensor maps for this batch / these buffers and launches.
@@ -216,6 +222,8 @@ struct gsx_synth {
   unsigned long long* d_counter = nullptr;   // running global sample index in HBM (gsx_synth_device_counter; CUDA-graph replays)
   cudaStream_t side = nullptr;               // the Philox noise fill runs here, concurrently with the mapping network
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_rgb_fork = nullptr, ev_rgb_done = nullptr;     // ToRGB deferred to the side stream by the fused generate calls
+  bool rgb_pending = false;
 
   int nf(int r) const {
     const int f = (int)(cfg.fmap_base / std::pow(2.0, (r - 1) * (double)cfg.fmap_decay));
@@ -304,6 +312,8 @@ extern "C" int gsx_set_option(const char* name, int value) {
   if (name && std::strcmp(name, "fold_apply") == 0) { g_opt_fold_apply = value != 0; return 0; }
   if (name && std::strcmp(name, "fold_deconv_maxc") == 0) { g_opt_fold_deconv_maxc = value; return 0; }
   if (name && std::strcmp(name, "dec_branches") == 0) { g_opt_dec_branches = value != 0; return 0; }
+  if (name && std::strcmp(name, "defer_rgb") == 0) { g_opt_defer_rgb = value != 0; return 0; }
+  if (name && std::strcmp(name, "dec_branch_kpx") == 0 && value >= 0) { g_opt_dec_branch_kpx = value; return 0; }
   if (name && std::strcmp(name, "wgrad_m64") == 0 && value >= 0 && value <= 2) { g_wgrad_m64 = value; return 0; }
   if (name && std::strcmp(name, "pdl") == 0 && value >= 0 && value <= 4) {
     g_pdl_mode = value;
@@ -347,6 +357,8 @@ extern "C" void gsx_synth_destroy(gsx_synth* h) {
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_rgb_fork) cudaEventDestroy(h->ev_rgb_fork);
+  if (h->ev_rgb_done) cudaEventDestroy(h->ev_rgb_done);
   for (int i = 0; i < 8; ++i) { cudaFree(h->d_map_w[i]); cudaFree(h->d_map_b[i]); }
   cudaFree(h->d_aff_w); cudaFree(h->d_aff_b); cudaFree(h->d_unit_layer); cudaFree(h->d_latent_avg);
   cudaFree(h->d_psi); cudaFree(h->d_wrgb); cudaFree(h->d_brgb); cudaFree(h->d_const);
@@ -721,8 +733,19 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
       double by = (b.t2 ? 1.0 : 2.0) * act_bytes;
       if (last) by += (img_u8_dev ? 1.0 : 0.0) * N * b.H * b.W * h->cfg.channels + (img_f32_dev ? 4.0 : 0.0) * N * b.H * b.W * h->cfg.channels;
       if (a2.out_nchw_f32) by += 2.0 * act_bytes;
-      ProfScope ps(tag + (last ? (b.t2 ? "rgb" : "apply2+rgb") : "apply2"), by, last ? 2.0 * N * b.H * b.W * b.C * h->cfg.channels : 0, st);
-      launch_apply(a2, st); g_launches++;
+      cudaStream_t on = st;
+      if (last && b.t2 && !a2.out_nchw_f32 && t_defer_rgb && g_opt_defer_rgb && !g_prof_on && h->side) {
+        if (!h->ev_rgb_fork) {
+          cudaEventCreateWithFlags(&h->ev_rgb_fork, cudaEventDisableTiming);
+          cudaEventCreateWithFlags(&h->ev_rgb_done, cudaEventDisableTiming);
+        }
+        if (h->ev_rgb_fork && h->ev_rgb_done && cudaEventRecord(h->ev_rgb_fork, st) == cudaSuccess &&
+            cudaStreamWaitEvent(h->side, h->ev_rgb_fork, 0) == cudaSuccess)
+          on = h->side;
+      }
+      ProfScope ps(tag + (last ? (b.t2 ? "rgb" : "apply2+rgb") : "apply2"), by, last ? 2.0 * N * b.H * b.W * b.C * h->cfg.channels : 0, on);
+      launch_apply(a2, on); g_launches++;
+      if (on != st) { cudaEventRecord(h->ev_rgb_done, on); h->rgb_pending = true; }
     }
   }
   if (!cuda_ok(cudaGetLastError(), "synth forward")) return -2;
@@ -1003,7 +1026,7 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
   // beside the main chain conv_a -> conv_b and join it by events (the same shape as the training step's branches,
   // train_step.cu).  Off while the per-layer table is being taken (its events time the caller's stream).
   const bool branches = g_opt_dec_branches && !g_prof_on && !d->cvt_streams.empty();
-  auto is_small = [&](int i) { return branches && (double)N * d->levels[i].H * d->levels[i].W <= 96.0 * 1024; };
+  auto is_small = [&](int i) { return branches && (double)N * d->levels[i].H * d->levels[i].W <= 1024.0 * g_opt_dec_branch_kpx; };
   size_t next_event = 0;
   bool ev_ok = true;
   auto record = [&](cudaStream_t on) -> cudaEvent_t {
@@ -1077,6 +1100,29 @@ extern "C" int gsx_dec_forward(gsx_dec* d, int N, const float* const* feats_f32_
   return cuda_ok(cudaGetLastError(), "dec forward") ? 0 : -2;
 }
 
+// generator + decoder on device buffers; the image pass runs beside the decoder and is joined here
+static int generate_dev_impl(gsx_synth* s, gsx_dec* d, int n, const float* z_dev, const float* psi_host, uint64_t seed, uint64_t first_sample,
+                             uint8_t* img_u8_dev, uint8_t* mask_dev, void* synth_ws, size_t synth_ws_bytes, void* dec_ws,
+                             size_t dec_ws_bytes, cudaStream_t st) {
+  t_defer_rgb = true;
+  int rc = gsx_synth_forward(s, n, z_dev, psi_host, nullptr, seed, first_sample, nullptr, img_u8_dev, nullptr, synth_ws, synth_ws_bytes, st);
+  t_defer_rgb = false;
+  if (!rc) rc = gsx_dec_forward(d, n, nullptr, s, synth_ws, nullptr, mask_dev, dec_ws, dec_ws_bytes, st);
+  if (s && s->rgb_pending) {                               // also on the error path: the side stream must rejoin the caller's
+    s->rgb_pending = false;
+    if (!cuda_ok(cudaStreamWaitEvent(st, s->ev_rgb_done, 0), "join image pass") && !rc) rc = -2;
+  }
+  return rc;
+}
+
+extern "C" int gsx_generate_dev(gsx_synth* s, gsx_dec* d, int n, const float* z_dev, const float* psi_host, uint64_t seed,
+                                uint64_t first_sample, uint8_t* img_u8_dev, uint8_t* mask_dev, void* synth_ws,
+                                size_t synth_ws_bytes, void* dec_ws, size_t dec_ws_bytes, gsx_stream stream) {
+  if (!s || !d || !img_u8_dev || !mask_dev) { set_error("bad argument"); return -1; }
+  return generate_dev_impl(s, d, n, z_dev, psi_host, seed, first_sample, img_u8_dev, mask_dev, synth_ws, synth_ws_bytes, dec_ws,
+                           dec_ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z_host, const float* psi_host,
                                  uint64_t seed, uint64_t first_sample, uint8_t* img_u8_host, uint8_t* mask_host,
                                  void* synth_ws, size_t synth_ws_bytes, void* dec_ws, size_t dec_ws_bytes,
@@ -1106,10 +1152,8 @@ extern "C" int gsx_generate_host(gsx_synth* s, gsx_dec* d, int n, const float* z
   }
   if (z_host && !cuda_ok(cudaMemcpyAsync(z_dev, z_host, (size_t)n * Z * sizeof(float), cudaMemcpyHostToDevice, st), "H2D z"))
     return -2;
-  int rc = gsx_synth_forward(s, n, z_host ? z_dev : nullptr, psi_host, nullptr, seed, first_sample, nullptr, img_dev,
-                             nullptr, synth_ws, synth_ws_bytes, stream);
-  if (rc) return rc;
-  rc = gsx_dec_forward(d, n, nullptr, s, synth_ws, nullptr, mask_dev, dec_ws, dec_ws_bytes, stream);
+  int rc = generate_dev_impl(s, d, n, z_host ? z_dev : nullptr, psi_host, seed, first_sample, img_dev, mask_dev, synth_ws, synth_ws_bytes,
+                             dec_ws, dec_ws_bytes, st);
   if (rc) return rc;
   if (copy_stream) {
     // device-to-host copies run on the copy stream and overlap the next step's kernels

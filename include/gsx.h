@@ -68,7 +68,12 @@ uint64_t gsx_launch_count(void);
  *                 at kernel start, 3 always with the big kernels triggering when their CTAs finish, 4 = policy of 1 with late triggers.
  *   "varn" (default 1): stacked-phase up-convs issue MMAs only over the phase blocks a shift feeds (1: layers with >= 32
  *                 output channels, 2: all, 0: off);  "epi_groups" (default 2; 4 = experiment): epilogue warps per TMEM lane quarter
- *                 of the kernels without the generator epilogue. */
+ *                 of the kernels without the generator epilogue.
+ * Read at every call:
+ *   "dec_branches" (default 1): gsx_dec_forward runs the cvt block of every level and the 1x1 shortcuts on side streams
+ *                 beside the main chain conv_a -> conv_b (joined by events; capturable); "dec_branch_kpx": only for levels
+ *                 with at most that many thousand pixels in the batch (default: all).
+ *   "defer_rgb" (default 1): the fused generate calls run the ToRGB / image pass beside the decoder. */
 int gsx_set_option(const char* name, int value);
 
 /* ---- generator: replaces Generator(config) / load_parameters / __call__
@@ -116,6 +121,14 @@ int gsx_dec_workspace_bytes(const gsx_dec* h, int n, size_t* bytes);
 int gsx_dec_forward(gsx_dec* h, int n, const float* const* feats_f32_dev, const gsx_synth* synth,
                     const void* synth_ws, float* logits_dev, uint8_t* mask_dev, void* ws, size_t ws_bytes,
                     gsx_stream stream);
+
+/* ---- whole generate step on DEVICE buffers (main.py:97-99 per batch, nothing leaves HBM): z_dev [n,latent] (or NULL: Philox
+ *      latents of (seed, first_sample)) -> img_u8_dev [n,H,W,3] + mask_dev [n,H,W].  Same results as gsx_synth_forward followed by
+ *      gsx_dec_forward(synth = s); fused so that the image pass (ToRGB) runs beside the decoder, which does not need it.  Both
+ *      outputs are complete in `stream` order when the call returns. ---- */
+int gsx_generate_dev(gsx_synth* s, gsx_dec* d, int n, const float* z_dev, const float* psi_host, uint64_t seed,
+                     uint64_t first_sample, uint8_t* img_u8_dev, uint8_t* mask_dev, void* synth_ws, size_t synth_ws_bytes,
+                     void* dec_ws, size_t dec_ws_bytes, gsx_stream stream);
 
 /* ---- whole generate step with HOST buffers (main.py:97-99 per batch): z_host (or NULL) in,
  *      uint8 image + uint8 mask out; H2D/D2H copies are enqueued inside the call.

@@ -117,6 +117,40 @@ def test_decoder_start_res(start_res):
         D.forward([f.numpy() for f in feats[start_res:]])          # the full pyramid is expected, as in the reference
 
 
+def test_fused_device_call_matches_the_two_calls():
+    """gsx_generate_dev (image pass beside the decoder, decoder branches on side streams) == gsx_synth_forward followed by
+    gsx_dec_forward, bit for bit, over several batches with different latents; also with the branches switched off."""
+    import ctypes as C
+    import gan_segmentation_b200._lib as L
+    from gan_segmentation_b200.networks import Generator, Decoder, GeneratePipeline
+    gc, dc, gp, dp, _, _ = make_case(7, 3, seed=17)
+    G = Generator(gc); G.set_parameters(gp)
+    D = Decoder(dc); D.set_parameters(dp)
+    pipe = GeneratePipeline(G, D, 3)
+    lib = G._lib
+    H, W = G.out_hw
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    psi = np.full((G.num_layers,), 0.7, np.float32)
+    try:
+        for opt in (1, 0):
+            assert lib.gsx_set_option(b'dec_branches', opt) == 0 and lib.gsx_set_option(b'defer_rgb', opt) == 0
+            for k in range(3):
+                z = torch.randn((3, 512), generator=torch.Generator(device='cuda').manual_seed(k), device='cuda')
+                img_a = torch.empty((3, H, W, 3), dtype=torch.uint8, device='cuda'); mask_a = torch.empty((3, H, W), dtype=torch.uint8, device='cuda')
+                img_b = torch.zeros_like(img_a); mask_b = torch.zeros_like(mask_a)
+                L.check(lib.gsx_synth_forward(G._h, 3, L.ptr(z), L.np_ptr(psi), None, 5, 3 * k, None, L.ptr(img_a), None,
+                                              L.ptr(pipe.gws), pipe.gws.numel(), sp), 'synth')
+                L.check(lib.gsx_dec_forward(D._h, 3, None, G._h, L.ptr(pipe.gws), None, L.ptr(mask_a), L.ptr(pipe.dws),
+                                            pipe.dws.numel(), sp), 'dec')
+                L.check(lib.gsx_generate_dev(G._h, D._h, 3, L.ptr(z), L.np_ptr(psi), 5, 3 * k, L.ptr(img_b), L.ptr(mask_b),
+                                             L.ptr(pipe.gws), pipe.gws.numel(), L.ptr(pipe.dws), pipe.dws.numel(), sp), 'generate')
+                torch.cuda.synchronize()
+                assert torch.equal(img_a, img_b) and torch.equal(mask_a, mask_b), (opt, k)
+                assert int(mask_a.max()) <= 1 and img_a.float().std() > 1
+    finally:
+        lib.gsx_set_option(b'dec_branches', 1); lib.gsx_set_option(b'defer_rgb', 1)
+
+
 def test_device_rng_path_matches_oracle_on_exported_noise():
     """Philox noise / latents generated on the device: export them and replay through the oracle."""
     from gan_segmentation_b200.networks import Generator
