@@ -361,10 +361,10 @@ class GraphedGenerate:
 
         def enqueue():
             sp = _stream(None)
-            L.check(lib.gsx_synth_forward(generator._h, n, None, None, None, seed, 0, None, L.ptr(self.img), None,
-                                          L.ptr(self.gws), self.gws.numel(), sp), 'gsx_synth_forward', generator.dtype)
-            L.check(lib.gsx_dec_forward(decoder._h, n, None, generator._h, L.ptr(self.gws), None, L.ptr(self.mask),
-                                        L.ptr(self.dws), self.dws.numel(), sp), 'gsx_dec_forward', generator.dtype)
+            # the fused call: the image pass and the decoder's cvt / shortcut branches become branches of the captured graph
+            L.check(lib.gsx_generate_dev(generator._h, decoder._h, n, None, None, seed, 0, L.ptr(self.img), L.ptr(self.mask),
+                                         L.ptr(self.gws), self.gws.numel(), L.ptr(self.dws), self.dws.numel(), sp),
+                    'gsx_generate_dev', generator.dtype)
 
         with torch.cuda.device(dev):
             L.check(lib.gsx_synth_device_counter(generator._h, 1, first_sample), 'gsx_synth_device_counter', generator.dtype)
