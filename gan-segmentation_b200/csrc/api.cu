@@ -315,6 +315,7 @@ extern "C" int gsx_set_option(const char* name, int value) {
   if (name && std::strcmp(name, "defer_rgb") == 0) { g_opt_defer_rgb = value != 0; return 0; }
   if (name && std::strcmp(name, "dec_branch_kpx") == 0 && value >= 0) { g_opt_dec_branch_kpx = value; return 0; }
   if (name && std::strcmp(name, "wgrad_m64") == 0 && value >= 0 && value <= 2) { g_wgrad_m64 = value; return 0; }
+  if (name && std::strcmp(name, "wgrad_kxm") == 0) { g_wgrad_kxm = value != 0; return 0; }
   if (name && std::strcmp(name, "pdl") == 0 && value >= 0 && value <= 4) {
     g_pdl_mode = value;
     set_pdl_late_conv(value >= 3); set_pdl_late_ew(value >= 3);

@@ -338,6 +338,7 @@ void pool_put(void* p);
 void pool_release();
 
 extern int g_wgrad_m64;
+extern int g_wgrad_kxm;
 // wgrad.cu: tensor-core weight gradient (see there).  scratch: wgrad_scratch_floats(...) floats.
 size_t wgrad_scratch_floats(int K, int Cin, int Cout, int sms);
 bool launch_wgrad(int K, int N, int H, int W, int Cin, int Cout, int cout_real, const act_t* x, const act_t* dy, float* dw,

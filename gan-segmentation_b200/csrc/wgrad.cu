@@ -39,6 +39,9 @@ struct WgradGeom {
   int rows;                           // valid accumulator rows per CTA = min(Cin, 128): only these reach the partials
   int m64;                            // 0: M = 128 MMAs; 1 / 2: M = 64 (Cin <= 64: half the A operand bytes per MMA), accumulator row i in
                                       //   TMEM lane i (1) or lane 32*(i/16) + i%16 (2)
+  int kxm;                            // 1: layers with <= 16 input channels -- the kx taps ride along M: A descriptors with SBO = 16 B, so the
+                                      //   8 row groups of an M = 64 MMA are the SAME channel block shifted by 0..7 pixels (0..2 used);
+                                      //   one MMA per (ky, channel block) instead of one per tap: 6 instead of 9 at 16 channels
 };
 
 struct WgradParams {
@@ -156,7 +159,24 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       const uint32_t ncol = (uint32_t)g.Cout;
       if (elect_one()) {
         uint32_t acc = first ? 0u : 1u;
-        if (taps == 9) {
+        if (g.kxm) {
+          // accumulator (ky, cb) at columns (ky * cbx + cb) * Cout; its row kx * 8 + c = tap (ky, kx), channel cb * 8 + c
+          const uint32_t a_hi_kx = (uint32_t)(wg_desc(0, 16u) >> 32);
+          uint32_t a_lo_kx[6];
+#pragma unroll
+          for (int a = 0; a < 6; ++a) {
+            const int ky = a / g.cbx, cb = a - ky * g.cbx;
+            a_lo_kx[a] = a < 3 * g.cbx ? ((((xa + (uint32_t)(cb * g.x_cb_stride) + (uint32_t)((ky * g.BW - P) * 16)) >> 4) & 0x3FFF) | lbo) : 0u;
+          }
+          const int n_acc = 3 * g.cbx;
+          for (int q = 0; q < g.q_steps; ++q) {
+            const uint32_t ko = (uint32_t)q * 16u;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+              if (a < n_acc) umma_f16kind_lohi(tmem_base + (uint32_t)a * ncol, a_lo_kx[a] + ko, a_hi_kx, b_lo0 + ko, b_hi, idesc, acc);
+            acc = 1u;
+          }
+        } else if (taps == 9) {
           for (int q = 0; q < g.q_steps; ++q) {
             const uint32_t ko = (uint32_t)q * 16u;
 #pragma unroll
@@ -190,6 +210,27 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     if (g.m64 == 2) row = lane < 16 ? quarter * 16 + lane : 128;
     const bool quarter_live = g.m64 == 2 ? quarter * 16 < g.rows : quarter * 32 < g.rows;
     const bool live = row < g.rows && quarter_live;
+    if (g.kxm) {
+      // rows 0..23 of every (ky, cb) accumulator: kx = row / 8, channel cb * 8 + row % 8 (M = 64: rows 0..15 in lanes 0..15 of
+      // quarter 0, rows 16..23 in lanes 0..7 of quarter 1)
+      const bool live_kx = row < 24 && quarter < 2;
+      for (int a = 0; a < 3 * g.cbx && quarter < 2; ++a)
+        for (int c = 0; c < g.Cout; c += 16) {
+          uint32_t v[16];
+          if (t1 > t0) {
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * g.Cout + c), v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0u;
+          }
+          const int ky = a / g.cbx, cb = a - ky * g.cbx, kx = row >> 3, ci = cb * 8 + (row & 7);
+          float4* o = reinterpret_cast<float4*>(out + ((size_t)(ky * 3 + kx) * g.rows + ci) * g.Cout + c);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (live_kx) o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
+    } else
     for (int tp = 0; tp < taps && quarter_live; ++tp)
       for (int c = 0; c < g.Cout; c += 16) {
         uint32_t v[16];
@@ -236,6 +277,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 }
 
 static int g_wg_sms = 0;
+int g_wgrad_kxm = 1;        // gsx_set_option("wgrad_kxm", 0/1): kx taps along M for layers with <= 16 input channels
 int g_wgrad_m64 = 2;        // gsx_set_option("wgrad_m64", 0 / 2): M = 64 MMAs for layers with <= 64 input channels (default on)
 
 bool plan_wgrad(WgradGeom& g, int K, int N, int H, int W, int Cin, int Cout) {
@@ -243,7 +285,8 @@ bool plan_wgrad(WgradGeom& g, int K, int N, int H, int W, int Cin, int Cout) {
   g.K = K; g.N = N; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
   if ((K != 1 && K != 3) || Cin % 8 || Cout % 16 || Cout > 56 || Cout * K * K > 512) return false;
   g.m64 = (Cin <= 64) ? g_wgrad_m64 : 0;
-  const int m_blocks = g.m64 ? 8 : 16;       // channel blocks of A one MMA reads, whatever Cin is
+  g.kxm = (K == 3 && Cin <= 16 && g.m64 == 2 && g_wgrad_kxm) ? 1 : 0;
+  const int m_blocks = g.kxm ? 1 : (g.m64 ? 8 : 16);       // channel blocks of A one MMA reads, whatever Cin is (kxm: 7 pixels past its own)
   int BW = 16;
   while (BW < W + 2 && BW < 128) BW <<= 1;
   g.BW = BW;

@@ -73,6 +73,8 @@ uint64_t gsx_launch_count(void);
  *   "dec_branches" (default 1): gsx_dec_forward runs the cvt block of every level and the 1x1 shortcuts on side streams
  *                 beside the main chain conv_a -> conv_b (joined by events; capturable); "dec_branch_kpx": only for levels
  *                 with at most that many thousand pixels in the batch (default: all).
+ *   "wgrad_kxm" (default 1): weight gradients of layers with <= 16 input channels issue one MMA per (ky, channel block) with the
+ *                 kx taps along M (6 instead of 9 per 16 pixels).
  *   "defer_rgb" (default 1): the fused generate calls run the ToRGB / image pass beside the decoder. */
 int gsx_set_option(const char* name, int value);
 
