@@ -116,6 +116,7 @@ static int g_opt_dec_branches = 1;         // gsx_set_option("dec_branches", 0/1
 // call joins it before it returns.  gsx_synth_forward on its own always finishes the image on the caller's stream.
 static thread_local bool t_defer_rgb = false;
 static int g_opt_defer_rgb = 1;            // gsx_set_option("defer_rgb", 0/1)
+static int g_opt_inline_finalize = 1;      // gsx_set_option("inline_finalize", 0/1): AdaIN coefficients computed in the apply pass's prologue (no finalize launch)
 static int g_opt_fold_deconv_maxc = 16;    // gsx_set_option("fold_deconv_maxc", C): deconv+blur folded into one kernel up to C channels
 
 // Runs one planned conv layer: builds the tensor maps for this batch / these buffers and launches.
@@ -313,6 +314,7 @@ extern "C" int gsx_set_option(const char* name, int value) {
   if (name && std::strcmp(name, "fold_deconv_maxc") == 0) { g_opt_fold_deconv_maxc = value; return 0; }
   if (name && std::strcmp(name, "dec_branches") == 0) { g_opt_dec_branches = value != 0; return 0; }
   if (name && std::strcmp(name, "defer_rgb") == 0) { g_opt_defer_rgb = value != 0; return 0; }
+  if (name && std::strcmp(name, "inline_finalize") == 0) { g_opt_inline_finalize = value != 0; return 0; }
   if (name && std::strcmp(name, "dec_branch_kpx") == 0 && value >= 0) { g_opt_dec_branch_kpx = value; return 0; }
   if (name && std::strcmp(name, "wgrad_m64") == 0 && value >= 0 && value <= 2) { g_wgrad_m64 = value; return 0; }
   if (name && std::strcmp(name, "wgrad_kxm") == 0) { g_wgrad_kxm = value != 0; return 0; }
@@ -691,9 +693,13 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
       p1.in = w.bufA; p1.in_broadcast = 0; p1.blur = 1;
     }
     if (!b.fold) { ProfScope ps(tag + "pass1", (b.r == 2 ? 1.0 : 2.0) * act_bytes + plane_bytes, 0, st); launch_pass1(p1, st); g_launches++; }
-    { ProfScope ps(tag + "finalize", 0, 0, st);
+    // the coefficients of AdaIN 1 are only read by the apply pass of a block that does not fold it: computed there
+    const bool inline1 = !b.mod2 && g_opt_inline_finalize;
+    if (!inline1) {
+      ProfScope ps(tag + "finalize", 0, 0, st);
       launch_finalize(st1, w.stats_T[l1], N, b.C, b.H * b.W, w.styles, h->S_total, h->style_off[l1], w.coef[l1], st);
-      g_launches++; }
+      g_launches++;
+    }
     const ModBufs* m2 = b.mod2 ? &w.mod2[bi] : nullptr;
     if (b.mod2) {
       // AdaIN 1 folded into conv_2: no pass over the tensor, only the per-sample weights / bias
@@ -703,6 +709,7 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
       ApplyArgs a1{};
       a1.in = w.bufB; a1.out = w.bufB; a1.C = b.C; a1.N = N; a1.H = b.H; a1.W = b.W;
       a1.coef = w.coef[l1];
+      if (inline1) { a1.coef = nullptr; a1.partial = st1; a1.T = w.stats_T[l1]; a1.styles = w.styles; a1.style_stride = h->S_total; a1.style_off = h->style_off[l1]; }
       ProfScope ps(tag + "apply1", 2.0 * act_bytes, 0, st); launch_apply(a1, st); g_launches++;
     }
 
@@ -716,15 +723,20 @@ extern "C" int gsx_synth_forward(gsx_synth* h, int N, const float* z_dev, const 
     e2.stats_T = w.stats_T[l2];
     if (!run_conv(b.conv2, N, w.bufB, nullptr, e2, st, (tag + "conv2").c_str(), m2)) return -2;
     if (!fused_stats) { ProfScope ps(tag + "stats", act_bytes, 0, st); launch_stats(t2buf, st2, b.C, N, b.H * b.W, st); g_launches++; }
-    { ProfScope ps(tag + "finalize", 0, 0, st);
+    const bool last = b.r == h->L;
+    // AdaIN 2 of a block that materialises its feature (and is not the ToRGB block): same
+    const bool inline2 = !b.t2 && !last && g_opt_inline_finalize;
+    if (!inline2) {
+      ProfScope ps(tag + "finalize", 0, 0, st);
       launch_finalize(st2, w.stats_T[l2], N, b.C, b.H * b.W, w.styles, h->S_total, h->style_off[l2], w.coef[l2], st);
-      g_launches++; }
+      g_launches++;
+    }
 
     ApplyArgs a2{};
     a2.in = t2buf; a2.out = b.t2 ? nullptr : w.feat[bi]; a2.C = b.C; a2.N = N; a2.H = b.H; a2.W = b.W;
     a2.coef = w.coef[l2];
+    if (inline2) { a2.coef = nullptr; a2.partial = st2; a2.T = w.stats_T[l2]; a2.styles = w.styles; a2.style_stride = h->S_total; a2.style_off = h->style_off[l2]; }
     a2.out_nchw_f32 = feats_f32_dev ? feats_f32_dev[bi] : nullptr;
-    const bool last = b.r == h->L;
     if (last) {
       a2.wrgb = h->d_wrgb; a2.brgb = h->d_brgb; a2.img_f32 = img_f32_dev; a2.img_u8 = img_u8_dev; a2.nc = h->cfg.channels;
     }

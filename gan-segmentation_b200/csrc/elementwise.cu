@@ -290,8 +290,38 @@ __global__ void __launch_bounds__(kApThreads) apply_kernel(const ApplyArgs a) {
   const int HW = a.H * a.W;
   const float inv_hw = 1.f / (float)HW;
   float ca[8], cc[8];
+  if (a.coef) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) adain_coeffs(a, n, cb * 8 + i, inv_hw, ca[i], cc[i]);
+    for (int i = 0; i < 8; ++i) adain_coeffs(a, n, cb * 8 + i, inv_hw, ca[i], cc[i]);
+  } else {
+    // finalize inlined: warp w owns channel cb*8 + w; lane l sums tiles l, l+32, ..., then the same butterfly as
+    // finalize_kernel -> bit-identical coefficients, recomputed by every block of the plane (T <= a few hundred float2 loads)
+    __shared__ float2 s_coef[8];
+    const int wch = threadIdx.x >> 5, lane = threadIdx.x & 31, c = cb * 8 + wch;
+    float s1 = 0.f, s2 = 0.f;
+    const float* p = a.partial + ((size_t)n * a.T * a.C + c) * 2;
+    for (int t = lane; t < a.T; t += 32) {
+      const float2 v = ld_dep_f2(p + (size_t)t * a.C * 2);
+      s1 += v.x;
+      s2 += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+      const float mean = s1 * inv_hw;
+      const float var = fmaxf(s2 * inv_hw - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + 1e-5f);
+      const float* sty = a.styles + (size_t)n * a.style_stride + a.style_off;
+      const float aa = rstd * (ld_dep_f32(sty + c) + 1.f);
+      s_coef[wch] = make_float2(aa, ld_dep_f32(sty + a.C + c) - mean * aa);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ca[i] = s_coef[i].x; cc[i] = s_coef[i].y; }
+  }
   const act_t* in = a.in + (size_t)plane * HW * 8;
   act_t* out = a.out + (size_t)plane * HW * 8;
   const int base = blockIdx.x * (kApThreads * kApPixPerThread);

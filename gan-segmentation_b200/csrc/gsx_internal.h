@@ -263,6 +263,9 @@ struct ApplyArgs {            // InstanceNorm + AdaIN: out = (t-mean)*rstd*(scal
   // optional ToRGB fused on the un-rounded values (last layer): rgb = Wrgb[3][C] x + brgb
   const float* wrgb; const float* brgb; float* img_f32; unsigned char* img_u8; int nc;
   float* out_nchw_f32;        // optional fp32 NCHW copy of the feature (drop-in mode)
+  // optional: the statistics finalize inlined (coef == null): the coefficients of the block's 8 channels are computed from
+  // the per-tile partial sums in the kernel's prologue, in finalize_kernel's summation order -- one launch less per AdaIN
+  const float* partial; int T; const float* styles; int style_stride, style_off;
 };
 void launch_apply(const ApplyArgs& a, cudaStream_t st);
 
