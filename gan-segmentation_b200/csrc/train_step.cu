@@ -474,6 +474,7 @@ struct gsx_train {
   // step records the dependency graph instead of one chain.
   std::vector<cudaStream_t> lvl_streams;
   cudaStream_t wg_streams[2] = {nullptr, nullptr};
+  cudaStream_t sc_stream = nullptr;                  // the 1x1 shortcut: forward conv, and its gradient path (sum-pool + data gradient)
   std::vector<cudaEvent_t> events;
   const unsigned long long* seed_dev = nullptr;     // gsx_train_set_seed_buffer
   int sms = 148;
@@ -682,7 +683,8 @@ extern "C" int gsx_train_create(const gsx_dec_cfg* cfg, int n, int use_dropout, 
   h->lvl_streams.resize(h->nf, nullptr);
   for (int i = 0; ok && i < h->nf; ++i) ok = cuda_ok(cudaStreamCreateWithFlags(&h->lvl_streams[i], cudaStreamNonBlocking), "stream");
   for (int i = 0; ok && i < 2; ++i) ok = cuda_ok(cudaStreamCreateWithFlags(&h->wg_streams[i], cudaStreamNonBlocking), "stream");
-  h->events.resize((size_t)h->nf * 12 + 16, nullptr);       // created up front: nothing is allocated while a step is being captured
+  ok = ok && cuda_ok(cudaStreamCreateWithFlags(&h->sc_stream, cudaStreamNonBlocking), "stream");
+  h->events.resize((size_t)h->nf * 20 + 16, nullptr);       // created up front: nothing is allocated while a step is being captured
   for (size_t i = 0; ok && i < h->events.size(); ++i) ok = cuda_ok(cudaEventCreateWithFlags(&h->events[i], cudaEventDisableTiming), "event");
   if (!ok) { delete h; return -2; }
   float* bm = h->bn_mem;
@@ -718,6 +720,7 @@ extern "C" void gsx_train_destroy(gsx_train* h) {
   cudaFree(h->wpack_all); cudaFree(h->pack_idx); cudaFree(h->bn_mem); cudaFree(h->counter);
   for (cudaStream_t s : h->lvl_streams) if (s) cudaStreamDestroy(s);
   for (cudaStream_t s : h->wg_streams) if (s) cudaStreamDestroy(s);
+  if (h->sc_stream) cudaStreamDestroy(h->sc_stream);
   for (cudaEvent_t e : h->events) if (e) cudaEventDestroy(e);
   delete h;
 }
@@ -858,6 +861,7 @@ extern "C" int gsx_train_step(gsx_train* h, const float* params_dev, float* grad
     cudaEvent_t start = record(st);                        // operands packed, bucket zeroed, the caller's earlier work done
     for (int i = 0; i < nf; ++i) wait(lvl_br[i].st, start);
     for (int i = 0; i < 2; ++i) wait(wg_br[i].st, start);
+    wait(h->sc_stream, start);
   }
 
   // ---------------------------------------------------------------- forward (train mode)
@@ -877,16 +881,20 @@ extern "C" int gsx_train_step(gsx_train* h, const float* params_dev, float* grad
     const act_t* x0 = i > 0 ? w.prev[i - 1] : w.y_cvt[i];
     const act_t* x1 = i > 0 ? w.y_cvt[i] : nullptr;
     if (!l.last) {
+      const act_t* sc = x0;
+      cudaEvent_t ev_scf = nullptr;
+      if (l.has_sc) {                                      // the 1x1 shortcut runs beside conv_a -> BN -> conv_b -> BN
+        link(st, h->sc_stream);                            // x0, x1
+        if (!t_conv_fwd(l.sc, N, x0, x1, w.sc[i], P + l.sc.b_off, h->sc_stream, "t.shortcut")) return -2;
+        ev_scf = record(h->sc_stream);
+        sc = w.sc[i];
+      }
       if (!t_conv_fwd(l.conv_a, N, x0, x1, w.z_a[i], P + l.conv_a.b_off, st, "t.conv_a")) return -2;
       t_bn_stats(h, l.bn_a, w.z_a[i], 4 * HW, P, R, main_br);
       t_bn_fwd(h, l.bn_a, w.z_a[i], w.y_a[i], 2 * l.H, 2 * l.W, -1, 0, nullptr, st);
       if (!t_conv_fwd(l.conv_b, N, w.y_a[i], nullptr, w.z_b[i], P + l.conv_b.b_off, st, "t.conv_b")) return -2;
       t_bn_stats(h, l.bn_b, w.z_b[i], 4 * HW, P, R, main_br);
-      const act_t* sc = x0;
-      if (l.has_sc) {
-        if (!t_conv_fwd(l.sc, N, x0, x1, w.sc[i], P + l.sc.b_off, st, "t.shortcut")) return -2;
-        sc = w.sc[i];
-      }
+      wait(st, ev_scf);
       // prev_{i+1} = up2(shortcut) + lrelu(BN(z_b))      (networks_seg.py:43-46, the 1x1 conv commutes with the upsampling)
       t_bn_fwd(h, l.bn_b, w.z_b[i], w.prev[i], 2 * l.H, 2 * l.W, -1, 0, sc, st);
     } else {
@@ -914,6 +922,7 @@ extern "C" int gsx_train_step(gsx_train* h, const float* params_dev, float* grad
   // two convs) and wg_br[1] (shortcut, final conv, cvt), the cvt block's BatchNorm backward to the level's own stream.
   const act_t* d_prev_out = nullptr;        // gradient w.r.t. prev_{i+1} while level i is processed
   cudaEvent_t ev_g1 = nullptr, ev_g3 = nullptr, ev_gsc = nullptr;      // last side-branch read of the scratch tensors g1 / g3 / g_sc
+  cudaEvent_t ev_sum_done = nullptr;                                   // the level's final sum-pool (reads g_sc / g_in1) is enqueued-complete
   std::vector<cudaEvent_t> ev_cvt_bwd(nf + 2, nullptr);               // level i's cvt branch has read its slice of g_out[i & 1]
   for (int i = nf - 1; i >= 0; --i) {
     const TLevel& l = h->levels[i];
@@ -928,6 +937,27 @@ extern "C" int gsx_train_step(gsx_train* h, const float* params_dev, float* grad
       t_bias_grad(h, w.dlog, 16, l.fnext, HW, G + l.fin.b_off, wg_br[1]);
       if (!t_conv_dgrad(l.fin, N, w.dlog, dxin, st, "t.final.dgrad")) return -2;
     } else {
+      // shortcut branch on its own stream: sum-pool of the incoming gradient, (shortcut conv: weight gradient on wg_br[1],) data gradient
+      const act_t* addend = w.g_sc;
+      cudaEvent_t ev_sc_done = nullptr;
+      {
+        cudaStream_t ss = h->sc_stream;
+        link(st, ss);                                      // d_prev_out
+        wait(ss, ev_gsc);                                  // the previous level's weight gradient has read g_sc
+        if (!l.has_sc) wait(ss, ev_sum_done);              // ... and, without a shortcut conv, its final sum-pool reads g_sc directly
+        sumpool2_blocked_kernel<<<dim3(ew_grid(HW), (l.fnext / 8) * N), 256, 0, ss>>>(d_prev_out, nullptr, w.g_sc, 0, l.H, l.W);
+        g_launches++;
+        if (l.has_sc) {
+          link(ss, wg_br[1].st);
+          if (!t_wgrad(h, l.sc, x0, x1, w.g_sc, G, w.wg_scratch[1], wg_br[1].st, l.H, l.W)) return -2;
+          t_bias_grad(h, w.g_sc, l.sc.cout_pad, l.fnext, HW, G + l.sc.b_off, wg_br[1]);
+          ev_gsc = record(wg_br[1].st);
+          wait(ss, ev_sum_done);                           // the previous level's final sum-pool has read g_in1
+          if (!t_conv_dgrad(l.sc, N, w.g_sc, w.g_in1, ss, "t.shortcut.dgrad")) return -2;
+          addend = w.g_in1;
+        }
+        ev_sc_done = record(ss);
+      }
       // second conv of the res-block
       wait(st, ev_g1);
       t_bn_bwd(h, l.bn_b, w.z_b[i], d_prev_out, w.g1, 4 * HW, -1, 0, G, main_br);                      // dz_b
@@ -951,22 +981,11 @@ extern "C" int gsx_train_step(gsx_train* h, const float* params_dev, float* grad
         ev_g3 = record(ws0);
       }
       if (!t_conv_dgrad(l.conv_a, N, w.g3, w.g_up, st, "t.conv_a.dgrad")) return -2;                   // gradient at 2H x 2W
-      // shortcut branch
-      wait(st, ev_gsc);
-      sumpool2_blocked_kernel<<<dim3(ew_grid(HW), (l.fnext / 8) * N), 256, 0, st>>>(d_prev_out, nullptr, w.g_sc, 0, l.H, l.W);
-      g_launches++;
-      const act_t* addend = w.g_sc;
-      if (l.has_sc) {
-        link(st, wg_br[1].st);
-        if (!t_wgrad(h, l.sc, x0, x1, w.g_sc, G, w.wg_scratch[1], wg_br[1].st, l.H, l.W)) return -2;
-        t_bias_grad(h, w.g_sc, l.sc.cout_pad, l.fnext, HW, G + l.sc.b_off, wg_br[1]);
-        ev_gsc = record(wg_br[1].st);
-        if (!t_conv_dgrad(l.sc, N, w.g_sc, w.g_in1, st, "t.shortcut.dgrad")) return -2;
-        addend = w.g_in1;
-      }
+      wait(st, ev_sc_done);                 // the shortcut branch's gradient (addend)
       wait(st, ev_cvt_bwd[i + 2]);          // g_out[i & 1] was level i+2's dxin
       sumpool2_blocked_kernel<<<dim3(ew_grid(HW), (cm / 8) * N), 256, 0, st>>>(w.g_up, addend, dxin, 0, l.H, l.W);
       g_launches++;
+      ev_sum_done = record(st);
     }
     // cvt block: the last l.f channels of dxin (all of them at level 0)
     const act_t* d_c = dxin + (size_t)N * HW * l.c0 * (i > 0 ? 1 : 0);
@@ -981,6 +1000,7 @@ extern "C" int gsx_train_step(gsx_train* h, const float* params_dev, float* grad
   // join: the step is complete on the caller's stream
   for (int i = 0; i < nf; ++i) link(lvl_br[i].st, st);
   for (int i = 0; i < 2; ++i) link(wg_br[i].st, st);
+  link(h->sc_stream, st);
   if (!ev_ok) { set_error("train step: event record / wait failed"); return -2; }
   return cuda_ok(cudaGetLastError(), "train step") ? 0 : -2;
 }
