@@ -226,6 +226,7 @@ class SegSolver:
             self.save()
         if world > 1:
             torch.distributed.barrier()
+        self._release_scratch()
         return []
 
     def evaluate(self, input_dir, output_dir=None):
@@ -283,4 +284,12 @@ class SegSolver:
                         fp.write(', '.join(str(w) for w in [imname, img_i.shape, pm_out.shape, gm_out.shape, metric_str]) + '\n')
         result = metric.get_name_value()
         result.append(('total-loss', total_loss / total_cnt if total_cnt > 0 else 0.0))
+        self._release_scratch()
         return result
+
+    def _release_scratch(self):
+        """The single-operator hooks (loss, metrics helpers) keep their scratch blocks in a pool outside torch's caching
+        allocator; hand them back when a pass over the data ends so that torch can use the memory."""
+        from . import _lib as L
+        torch.cuda.synchronize(self.net.device)
+        L.lib(self.net.dtype).gsx_op_release_cache()
