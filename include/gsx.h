@@ -75,6 +75,9 @@ uint64_t gsx_launch_count(void);
  *                 with at most that many thousand pixels in the batch (default: all).
  *   "wgrad_kxm" (default 1): weight gradients of layers with <= 16 input channels issue one MMA per (ky, channel block) with the
  *                 kx taps along M (6 instead of 9 per 16 pixels).
+ *   "wgrad_m64" (default 2): weight gradients of layers with <= 64 input channels use M = 64 MMAs (0: M = 128 everywhere).
+ *   "inline_finalize" (default 1): blocks that do not fold their AdaIN compute its coefficients in the apply pass itself
+ *                 (no separate finalize launch; same summation order, bit-identical).
  *   "defer_rgb" (default 1): the fused generate calls run the ToRGB / image pass beside the decoder. */
 int gsx_set_option(const char* name, int value);
 

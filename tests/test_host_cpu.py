@@ -183,3 +183,15 @@ def test_cli_reads_the_reference_config_keys(tmp_path):
         import pytest
         with pytest.raises(Exception):                                                 # no CPU fallback
             M.main(['generate', '--config', str(cfg), '--random-init'])
+
+
+def test_every_runtime_option_is_documented_in_the_header():
+    """gsx_set_option names accepted by csrc/api.cu all appear (quoted) in include/gsx.h."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, 'gan-segmentation_b200', 'csrc', 'api.cu')).read()
+    hdr = open(os.path.join(root, 'include', 'gsx.h')).read()
+    names = set(re.findall(r'std::strcmp\(name, "([a-z_0-9]+)"\)', src))
+    assert len(names) >= 8
+    missing = sorted(n for n in names if f'"{n}"' not in hdr)
+    assert not missing, missing
