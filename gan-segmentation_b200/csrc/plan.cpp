@@ -153,9 +153,10 @@ void plan_conv(ConvLayer& L, int mode, int H, int W, int cin0, int cin1, int cou
   int max_mt = std::max(1, budget_cols / (G * N_tile));
   max_mt = std::min(max_mt, 32);
   if (ov && ov->max_mtiles > 0) max_mt = std::min(max_mt, ov->max_mtiles);
-  // 8 epilogue warps.  A 16-warp variant was measured in round 1 (with one and with two MMA issuers, dense and
-  // space-to-depth plans): never faster, and it spills under its 112-register cap -- not built.
-  // 8 epilogue warps by default; gsx_set_option("epi_groups", 4) plans 16 (used by the kernels without the generator epilogue)
+  // 8 epilogue warps.  16 were measured in round 1 (one and two MMA issuers, dense and space-to-depth plans) and again in
+  // round 2 (kernels without the generator epilogue: 3076 vs 3152 samples/s; generator epilogue of the wide layers: spills
+  // under its register cap, g7.conv2 0.252 -> 0.320 ms) -- never faster.  gsx_set_option("epi_groups", 4) keeps the
+  // 16-warp instantiations of the kernels without the generator epilogue reachable for A/B runs.
   const int epi_groups = g_plan_epi_groups;
   if (ov && ov->epi_groups > 0 && ov->epi_groups != 2) { set_error("plan_conv: only epi_groups = 2 is built"); return; }
   const int stats_bytes = (2 * 4 * epi_groups * 2 * cout_tile * 4 + 1023) / 1024 * 1024;
